@@ -1,0 +1,98 @@
+"""CPU: structural assertions of the reference's renderer tests, re-asserted on the rasteriser oracle
+(tests/test_batch_renderer_panda3d.py:71-242, tests/test_scene_renderer_panda3d.py:206-214).
+Panda3D cannot run here, so these -- not pixel goldens -- are what the reference itself pins."""
+import numpy as np
+import pytest
+
+from oracle import raster
+from tests.scenes import icosphere, reference_test_scene
+
+
+@pytest.fixture(scope="module")
+def can(can_mesh_arrays):
+    d = can_mesh_arrays
+    return raster.OracleMesh(d["verts"], d["faces"], d["normals"], d["uv"], texture=d["texture"], scale=0.001)
+
+
+def test_reference_scene_structure(can):
+    T, K, res = reference_test_scene()
+    Nc = 4
+    out = raster.render([can], [0] * Nc, np.stack([T] * Nc), np.stack([K] * Nc), res,
+                        render_normals=True, render_depth=True, render_binary_mask=True)
+    rgb, nrm, dep, msk = out["rgb"], out["normals"], out["depth"], out["mask"]
+    assert rgb.shape == (Nc, 3, 480, 640) and nrm.shape == (Nc, 3, 480, 640)
+    assert dep.shape == (Nc, 1, 480, 640) and msk.shape == (Nc, 1, 480, 640)
+    assert rgb.dtype == np.float32 and nrm.dtype == np.float32 and dep.dtype == np.float32 and msk.dtype == bool
+    for a in (rgb, nrm, dep, msk):
+        assert (a[0] == a[1]).all()  # identical cameras -> identical renders (:116-122)
+    assert (rgb[0, :, 0, 0] == 0).all() and (rgb[0, :, 240, 320] > 0).any()
+    assert dep[0, 0, 0, 0] == 0 and 0 < dep[0, 0, 240, 320] < 0.3
+    assert (nrm[0, :, 0, 0] == 0).all() and (nrm[0, :, 240, 320] > 0).any()
+    assert not msk[0, 0, 0, 0] and msk[0, 0, 240, 320]
+    # values are 8-bit quantised (uint8 framebuffer / 255, panda3d_batch_renderer.py:249)
+    assert np.abs(rgb * 255 - np.round(rgb * 255)).max() < 1e-4
+    assert nrm.max() <= 247 / 255 + 1e-6  # texel values stop at floor(31*255/32)
+    # can: radius ~51 mm at z=0.3 -> depth of the front surface ~0.249
+    assert abs(dep[0, 0, 240, 320] - (0.3 - 0.0512)) < 2e-3
+    assert (msk == (dep > 0)).all()
+
+
+def test_flag_combinations_return_none(can):
+    T, K, res = reference_test_scene()
+    for n, d in ((False, False), (True, False), (False, True), (True, True)):
+        out = raster.render([can], [0], T[None], K[None], (120, 160), render_normals=n, render_depth=d)
+        assert out["rgb"] is not None
+        assert (out["normals"] is not None) == n and (out["depth"] is not None) == d and out["mask"] is None
+
+
+def test_mask_requires_depth(can):
+    T, K, res = reference_test_scene()
+    with pytest.raises(AssertionError):
+        raster.render([can], [0], T[None], K[None], res, render_binary_mask=True)
+
+
+def test_non_finite_pose_gives_zero_images(can):
+    T, K, res = reference_test_scene()
+    Tb = np.stack([T, T])
+    Tb[1, 0, 3] = np.nan
+    K = K.copy()
+    K[:2] /= 4
+    out = raster.render([can], [0, 0], Tb, np.stack([K, K]), (120, 160), render_normals=True, render_depth=True)
+    assert out["rgb"][0].max() > 0
+    assert out["rgb"][1].max() == 0 and out["normals"][1].max() == 0 and out["depth"][1].max() == 0
+
+
+def test_sphere_depth_is_analytic():
+    """Untextured icosphere: depth at the centre = z - r (vertex on the axis), silhouette radius ~ f*r/sqrt(z^2-r^2)."""
+    v, f, n = icosphere(3, 0.05)
+    m = raster.OracleMesh(v, f, n)
+    T = np.eye(4)
+    T[2, 3] = 0.5
+    K = np.array([[400.0, 0, 80.5], [0, 400, 60.5], [0, 0, 1]])  # pixel (60,80) samples the optical axis
+    out = raster.render([m], [0], T[None], K[None], (120, 160), render_depth=True, render_binary_mask=True, render_normals=True)
+    dep, msk = out["depth"][0, 0], out["mask"][0, 0]
+    assert abs(dep[60, 80] - 0.45) < 5e-4
+    area = msk.sum()
+    r_pix = 400 * 0.05 / np.sqrt(0.5**2 - 0.05**2)
+    assert abs(area - np.pi * r_pix**2) / (np.pi * r_pix**2) < 0.03
+    assert (out["rgb"][0][:, msk] == 1.0).all()  # no texture, no vertex colour -> white * ambient 1
+    # normal facing the camera: n_cv = (0,0,-1) -> Panda axes (0,-1,0) -> frac = (0,0,0) -> every channel is the
+    # half-way blend of texel 31 (247) and texel 0 (0) across the repeat seam = 124
+    c = out["normals"][0][:, 60, 80] * 255
+    assert (np.abs(c - 124) <= 1).all()
+
+
+def test_far_and_near_rules():
+    v, f, n = icosphere(2, 0.05)
+    m = raster.OracleMesh(v, f, n)
+    K = np.array([[400.0, 0, 80], [0, 400, 60], [0, 0, 1]])
+    T = np.tile(np.eye(4), (3, 1, 1))
+    T[0, 2, 3] = 9.5   # beyond d > 0.999 (z > ~9.17 m): drawn in rgb, depth/mask 0 (renderer/utils.py:56-59)
+    T[1, 2, 3] = 10.5  # beyond the far plane: clipped everywhere
+    T[2, 2, 3] = 0.12  # straddles the near plane: triangles with a vertex closer than 0.1 m are dropped
+    K3 = np.stack([K] * 3)
+    K3[0, 0, 0] = K3[0, 1, 1] = K3[1, 0, 0] = K3[1, 1, 1] = 8000
+    out = raster.render([m], [0, 0, 0], T, K3, (120, 160), render_depth=True, render_binary_mask=True)
+    assert out["rgb"][0].max() == 1.0 and out["depth"][0].max() == 0 and not out["mask"][0].any()
+    assert out["rgb"][1].max() == 0
+    assert out["depth"][2].max() > 0 and out["depth"][2][out["depth"][2] > 0].min() >= 0.1
