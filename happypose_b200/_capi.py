@@ -1,0 +1,127 @@
+"""ctypes binding of libhpb200.so (include/hpb200.h).  torch is used only for device memory and streams.
+
+There is NO CPU fallback: if the library is missing or the device is not a B200-class GPU, calls raise.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+from typing import Dict, Optional
+
+import torch
+
+from . import _build
+
+c_void_p, c_int, c_int32, c_int64, c_float, c_uint32 = (
+    ctypes.c_void_p, ctypes.c_int, ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_uint32,
+)
+
+RENDER_RGB, RENDER_NORMALS, RENDER_DEPTH, RENDER_MASK = 1, 2, 4, 8
+POSE_MEGAPOSE, POSE_COSYPOSE_6D, POSE_COSYPOSE_QUAT = 0, 1, 2
+TCO_INIT_AUTODEPTH_WITH_R, TCO_INIT_ZUP_AUTODEPTH, TCO_INIT_FROM_BOXES = 0, 1, 2
+DEPTH_NORM = {"none": 0, "tCR_scale": 1, "tCR_scale_clamp_center": 2, "tCR_center_clamp": 3}
+MV_TYPES = {"TCO+front_1view": 0, "TCO+front_3views": 1, "sphere_26views": 2}
+
+# name -> (restype, argtypes); must list every symbol include/hpb200.h declares (tests/test_capi_symbols.py)
+SIGNATURES = {
+    "hpb_version": (c_int, []),
+    "hpb_last_error": (ctypes.c_char_p, []),
+    "hpb_create": (c_int, [c_int, ctypes.POINTER(c_void_p)]),
+    "hpb_destroy": (c_int, [c_void_p]),
+    "hpb_launch_count": (c_int64, [c_void_p]),
+    "hpb_mesh_upload": (c_int, [c_void_p] * 5 + [c_int64, c_void_p, c_int64, c_void_p, c_int, c_int, c_int, ctypes.POINTER(c_int32)]),
+    "hpb_mesh_count": (c_int, [c_void_p]),
+    "hpb_mesh_get_mip": (c_int, [c_void_p, c_int32, c_int, c_void_p, ctypes.POINTER(c_int), ctypes.POINTER(c_int), ctypes.POINTER(c_int)]),
+    "hpb_render": (c_int, [c_void_p] * 5 + [c_int, c_int, c_int, c_float, c_float, c_uint32,
+                           c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p]),
+    "hpb_crop": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p,
+                         c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_int64, c_void_p,
+                         c_void_p, c_void_p, c_void_p]),
+    "hpb_crop_boxes": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                               c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "hpb_normalize_T": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "hpb_pose_update": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "hpb_tco_init": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_float,
+                             c_int, c_void_p, c_void_p]),
+    "hpb_multiview": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "hpb_normalize_depth": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "hpb_topk_segmented": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+}
+
+_lib = None
+_lib_lock = threading.Lock()
+
+
+class HpbError(RuntimeError):
+    pass
+
+
+def load_library(build_if_missing: bool = True) -> ctypes.CDLL:
+    """Loads libhpb200.so; raises (never falls back) if it cannot be found or built."""
+    global _lib
+    with _lib_lock:
+        if _lib is not None:
+            return _lib
+        path = _build.LIB_PATH
+        if not os.path.exists(path):
+            if not build_if_missing:
+                raise HpbError(f"{path} is missing; run `python -m happypose_b200._build`")
+            _build.build()
+        lib = ctypes.CDLL(path)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError = the library does not export what the header declares
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+        return lib
+
+
+def _check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load_library().hpb_last_error().decode("utf-8", "replace")
+        if rc == -1:
+            raise ValueError(f"{what}: {msg}")
+        raise HpbError(f"{what} failed ({rc}): {msg}")
+
+
+def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def stream_ptr(device: torch.device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+class Context:
+    """One hpb_ctx per device (owns mesh buffers and the rasteriser workspace)."""
+
+    _by_device: Dict[int, "Context"] = {}
+
+    def __init__(self, device: torch.device):
+        if not torch.cuda.is_available():
+            raise HpbError("happypose_b200 needs a CUDA device (B200, sm_100a); there is no CPU path")
+        self.device = torch.device(device)
+        assert self.device.type == "cuda"
+        index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.device = torch.device("cuda", index)
+        self.lib = load_library()
+        h = c_void_p()
+        _check(self.lib.hpb_create(index, ctypes.byref(h)), "hpb_create")
+        self.handle = h
+
+    @classmethod
+    def get(cls, device=None) -> "Context":
+        device = torch.device("cuda" if device is None else device)
+        index = device.index if device.index is not None else torch.cuda.current_device()
+        ctx = cls._by_device.get(index)
+        if ctx is None:
+            ctx = cls(torch.device("cuda", index))
+            cls._by_device[index] = ctx
+        return ctx
+
+    def launch_count(self) -> int:
+        return int(self.lib.hpb_launch_count(self.handle))
+
+    def check(self, rc: int, what: str) -> None:
+        _check(rc, what)

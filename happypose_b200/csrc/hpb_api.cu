@@ -1,0 +1,365 @@
+// C-ABI layer of libhpb200.so (see include/hpb200.h).  Plain pointers and sizes only; no torch types.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "hpb_common.cuh"
+
+int hpb_launch_crop_boxes(hpb_ctx *ctx, int H, int W, const float *points, int n_pts, const int32_t *obj_ids,
+                          const float *K, const float *TCO, const float *tCR, int b, int h, int w, float lamb,
+                          float *K_crop, float *boxes_rend, float *boxes_crop, cudaStream_t stream);
+int hpb_launch_crop_pixels(hpb_ctx *ctx, const float *images, int n_im, int C, int H, int W, const int32_t *im_ids,
+                           const float *boxes, int b, int h, int w, float *crops, int64_t crops_bs,
+                           cudaStream_t stream);
+int hpb_launch_normalize_T(hpb_ctx *ctx, const float *T, int b, float *out, cudaStream_t stream);
+int hpb_launch_pose_update(hpb_ctx *ctx, const float *TCO, const float *K_crop, const float *outv, const float *tCR,
+                           int b, int variant, float *TCO_out, cudaStream_t stream);
+int hpb_launch_tco_init(hpb_ctx *ctx, int variant, const float *boxes, const float *points, int n_pts,
+                        const int32_t *obj_ids, const float *K, const float *R, float z_mean, int b, float *out,
+                        cudaStream_t stream);
+int hpb_launch_multiview(hpb_ctx *ctx, const float *TCO, const float *tCR, int b, const float *positions_host,
+                         int n_extra, int n_views, int keep_tco, float *out, cudaStream_t stream);
+int hpb_launch_normalize_depth(hpb_ctx *ctx, float *depth, int64_t bstride, const int32_t *chans, int n_planes,
+                               const float *tCR, int b, int h, int w, int kind, cudaStream_t stream);
+int hpb_launch_topk(hpb_ctx *ctx, const float *scores, const int32_t *groups, int n, int n_groups, int K,
+                    int64_t *out_idx, int32_t *out_count, cudaStream_t stream);
+
+static thread_local char g_err[512] = "";
+
+void hpb_set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" {
+
+int hpb_version(void) { return HPB_VERSION; }
+const char *hpb_last_error(void) { return g_err; }
+
+int hpb_create(int device, hpb_ctx **out) {
+    HPB_REQUIRE(out != nullptr, "out is NULL");
+    int n_dev = 0;
+    HPB_CUDA_OK(cudaGetDeviceCount(&n_dev));
+    HPB_REQUIRE(device >= 0 && device < n_dev, "no such CUDA device");
+    HpbDeviceGuard guard(device);
+    hpb_ctx *ctx = new (std::nothrow) hpb_ctx();
+    if (!ctx) {
+        hpb_set_error("hpb_create: out of host memory");
+        return HPB_ENOMEM;
+    }
+    ctx->device = device;
+    cudaDeviceProp prop;
+    HPB_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    if (prop.major < 10) {
+        hpb_set_error("hpb_create: device %d is sm_%d%d; this library is built for sm_100a (B200) only", device,
+                      prop.major, prop.minor);
+        delete ctx;
+        return HPB_EINVAL;
+    }
+    *out = ctx;
+    return HPB_OK;
+}
+
+int hpb_destroy(hpb_ctx *ctx) {
+    if (!ctx) return HPB_OK;
+    HpbDeviceGuard guard(ctx->device);
+    for (auto &m : ctx->meshes) {
+        cudaFree(m.pos); cudaFree(m.nrm); cudaFree(m.uv); cudaFree(m.vcol); cudaFree(m.faces); cudaFree(m.tex);
+    }
+    cudaFree(ctx->meshes_dev);
+    cudaFree(ctx->vis);
+    cudaFree(ctx->vert_scratch);
+    cudaFree(ctx->topk_ws);
+    delete ctx;
+    return HPB_OK;
+}
+
+int64_t hpb_launch_count(const hpb_ctx *ctx) { return ctx ? ctx->launches : 0; }
+int hpb_mesh_count(const hpb_ctx *ctx) { return ctx ? (int)ctx->meshes.size() : 0; }
+
+int hpb_mesh_upload(hpb_ctx *ctx, const float *verts_xyz, const float *normals, const float *uv,
+                    const uint8_t *vcolor, int64_t n_verts, const int32_t *faces, int64_t n_faces,
+                    const uint8_t *tex, int tex_h, int tex_w, int tex_c, int32_t *mesh_id) {
+    HPB_REQUIRE(ctx && verts_xyz && faces && mesh_id, "NULL argument");
+    HPB_REQUIRE(n_verts > 0 && n_verts < (1ll << 31) && n_faces > 0 && n_faces < (1ll << 31), "bad mesh size");
+    HPB_REQUIRE(!tex || (tex_h > 0 && tex_w > 0 && (tex_c == 3 || tex_c == 4)), "bad texture shape");
+    for (int64_t i = 0; i < 3 * n_faces; ++i) HPB_REQUIRE(faces[i] >= 0 && faces[i] < n_verts, "face index out of range");
+    HpbDeviceGuard guard(ctx->device);
+    HpbMeshHost m;
+    memset(&m.dev, 0, sizeof(m.dev));
+    const size_t nv = (size_t)n_verts, nf = (size_t)n_faces;
+
+    HPB_CUDA_OK(cudaMalloc(&m.pos, nv * 3 * sizeof(float)));
+    HPB_CUDA_OK(cudaMemcpy(m.pos, verts_xyz, nv * 3 * sizeof(float), cudaMemcpyHostToDevice));
+
+    std::vector<float> gen;
+    if (!normals) {  // area-weighted smooth normals in float64 (a mesh file without normals)
+        std::vector<double> acc(nv * 3, 0.0);
+        for (size_t t = 0; t < nf; ++t) {
+            const int32_t *f = faces + 3 * t;
+            double a[3], b[3];
+            for (int k = 0; k < 3; ++k) {
+                a[k] = (double)verts_xyz[3 * f[1] + k] - (double)verts_xyz[3 * f[0] + k];
+                b[k] = (double)verts_xyz[3 * f[2] + k] - (double)verts_xyz[3 * f[0] + k];
+            }
+            const double c[3] = {a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]};
+            for (int v = 0; v < 3; ++v)
+                for (int k = 0; k < 3; ++k) acc[3 * (size_t)f[v] + k] += c[k];
+        }
+        gen.resize(nv * 3);
+        for (size_t i = 0; i < nv; ++i) {
+            const double l = std::sqrt(acc[3 * i] * acc[3 * i] + acc[3 * i + 1] * acc[3 * i + 1] + acc[3 * i + 2] * acc[3 * i + 2]);
+            for (int k = 0; k < 3; ++k) gen[3 * i + k] = l > 0 ? (float)(acc[3 * i + k] / l) : 0.0f;
+        }
+        normals = gen.data();
+    }
+    HPB_CUDA_OK(cudaMalloc(&m.nrm, nv * 3 * sizeof(float)));
+    HPB_CUDA_OK(cudaMemcpy(m.nrm, normals, nv * 3 * sizeof(float), cudaMemcpyHostToDevice));
+    if (uv) {
+        HPB_CUDA_OK(cudaMalloc(&m.uv, nv * 2 * sizeof(float)));
+        HPB_CUDA_OK(cudaMemcpy(m.uv, uv, nv * 2 * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    if (vcolor) {
+        HPB_CUDA_OK(cudaMalloc(&m.vcol, nv * 4));
+        HPB_CUDA_OK(cudaMemcpy(m.vcol, vcolor, nv * 4, cudaMemcpyHostToDevice));
+    }
+    {
+        std::vector<int32_t> f4(nf * 4);
+        for (size_t t = 0; t < nf; ++t) {
+            f4[4 * t] = faces[3 * t]; f4[4 * t + 1] = faces[3 * t + 1]; f4[4 * t + 2] = faces[3 * t + 2]; f4[4 * t + 3] = 0;
+        }
+        HPB_CUDA_OK(cudaMalloc(&m.faces, nf * 16));
+        HPB_CUDA_OK(cudaMemcpy(m.faces, f4.data(), nf * 16, cudaMemcpyHostToDevice));
+    }
+    m.dev.pos = (const float *)m.pos;
+    m.dev.nrm = (const float *)m.nrm;
+    m.dev.uv = (const float *)m.uv;
+    m.dev.vcol = (const uchar4 *)m.vcol;
+    m.dev.faces = (const int4 *)m.faces;
+    m.dev.nv = (int)n_verts;
+    m.dev.nf = (int)n_faces;
+    if (tex && uv) {
+        // RGBA8 mip chain: level l+1 = max(1, size/2), rounded 2x2 box filter, built on the device
+        int w = tex_w, h = tex_h, levels = 0;
+        long long total = 0;
+        while (true) {
+            HPB_REQUIRE(levels < HPB_MAX_MIPS, "texture too large");
+            m.dev.tex_w[levels] = w; m.dev.tex_h[levels] = h; m.dev.tex_off[levels] = total;
+            total += (long long)w * h;
+            ++levels;
+            if (w == 1 && h == 1) break;
+            w = w > 1 ? w / 2 : 1;
+            h = h > 1 ? h / 2 : 1;
+        }
+        m.dev.tex_levels = levels;
+        HPB_CUDA_OK(cudaMalloc(&m.tex, (size_t)total * 4));
+        uint8_t *staging = nullptr;
+        const size_t raw = (size_t)tex_w * tex_h * tex_c;
+        HPB_CUDA_OK(cudaMalloc(&staging, raw));
+        HPB_CUDA_OK(cudaMemcpy(staging, tex, raw, cudaMemcpyHostToDevice));
+        int rc = hpb_launch_tex_expand(staging, tex_w * tex_h, tex_c, (uchar4 *)m.tex, 0);
+        for (int l = 1; l < levels && rc == HPB_OK; ++l)
+            rc = hpb_launch_mip((const uchar4 *)m.tex + m.dev.tex_off[l - 1], m.dev.tex_w[l - 1], m.dev.tex_h[l - 1],
+                                (uchar4 *)m.tex + m.dev.tex_off[l], m.dev.tex_w[l], m.dev.tex_h[l], 0);
+        cudaError_t e = cudaDeviceSynchronize();
+        cudaFree(staging);
+        if (rc != HPB_OK) return rc;
+        HPB_CUDA_OK(e);
+        m.dev.tex = (const uchar4 *)m.tex;
+    }
+    ctx->meshes.push_back(m);
+    if ((int)n_verts > ctx->max_nv) ctx->max_nv = (int)n_verts;
+    // refresh the device-side table
+    const int n = (int)ctx->meshes.size();
+    if (n > ctx->meshes_dev_cap) {
+        const int cap = n * 2 + 8;
+        HpbMeshDev *nd = nullptr;
+        HPB_CUDA_OK(cudaMalloc(&nd, sizeof(HpbMeshDev) * cap));
+        HPB_CUDA_OK(cudaDeviceSynchronize());
+        if (ctx->meshes_dev) cudaFree(ctx->meshes_dev);
+        ctx->meshes_dev = nd;
+        ctx->meshes_dev_cap = cap;
+        std::vector<HpbMeshDev> all(n);
+        for (int i = 0; i < n; ++i) all[i] = ctx->meshes[i].dev;
+        HPB_CUDA_OK(cudaMemcpy(ctx->meshes_dev, all.data(), sizeof(HpbMeshDev) * n, cudaMemcpyHostToDevice));
+    } else {
+        HPB_CUDA_OK(cudaMemcpy(ctx->meshes_dev + (n - 1), &ctx->meshes[n - 1].dev, sizeof(HpbMeshDev), cudaMemcpyHostToDevice));
+    }
+    *mesh_id = n - 1;
+    return HPB_OK;
+}
+
+int hpb_mesh_get_mip(hpb_ctx *ctx, int32_t mesh_id, int level, uint8_t *out_host, int *w, int *h, int *levels) {
+    HPB_REQUIRE(ctx, "NULL ctx");
+    if (mesh_id < 0 || mesh_id >= (int)ctx->meshes.size()) {
+        hpb_set_error("hpb_mesh_get_mip: unknown mesh id %d", mesh_id);
+        return HPB_ENOTFOUND;
+    }
+    const HpbMeshDev &d = ctx->meshes[mesh_id].dev;
+    if (levels) *levels = d.tex_levels;
+    if (d.tex_levels == 0) return HPB_OK;
+    HPB_REQUIRE(level >= 0 && level < d.tex_levels, "no such mip level");
+    if (w) *w = d.tex_w[level];
+    if (h) *h = d.tex_h[level];
+    if (out_host) {
+        HpbDeviceGuard guard(ctx->device);
+        HPB_CUDA_OK(cudaMemcpy(out_host, d.tex + d.tex_off[level], (size_t)d.tex_w[level] * d.tex_h[level] * 4, cudaMemcpyDeviceToHost));
+    }
+    return HPB_OK;
+}
+
+int hpb_render(hpb_ctx *ctx, const int32_t *mesh_ids_dev, const float *TCO_dev, const float *K_dev,
+               const float *ambient_dev, int b, int h, int w, float z_near, float z_far, uint32_t flags,
+               float *rgb_dev, int64_t rgb_bstride, float *normals_dev, int64_t normals_bstride, float *depth_dev,
+               int64_t depth_bstride, uint8_t *mask_dev, int64_t mask_bstride, void *stream) {
+    HPB_REQUIRE(ctx, "NULL ctx");
+    HPB_REQUIRE(b >= 0 && h > 0 && w > 0 && (long long)h * w < (1ll << 30), "bad batch / resolution");
+    if (b == 0) return HPB_OK;
+    HPB_REQUIRE(mesh_ids_dev && TCO_dev && K_dev, "NULL input");
+    HPB_REQUIRE(z_near > 0.f && z_far > z_near, "bad near/far");
+    HPB_REQUIRE(!ctx->meshes.empty(), "no mesh uploaded");
+    HPB_REQUIRE(!(flags & HPB_RENDER_RGB) || rgb_dev, "rgb requested but NULL");
+    HPB_REQUIRE(!(flags & HPB_RENDER_NORMALS) || normals_dev, "normals requested but NULL");
+    HPB_REQUIRE(!(flags & HPB_RENDER_DEPTH) || depth_dev, "depth requested but NULL");
+    HPB_REQUIRE(!(flags & HPB_RENDER_MASK) || mask_dev, "mask requested but NULL");
+    HPB_REQUIRE(flags != 0, "nothing to render");
+    HpbDeviceGuard guard(ctx->device);
+    return hpb_launch_raster(ctx, mesh_ids_dev, TCO_dev, K_dev, ambient_dev, b, h, w, z_near, z_far, flags, rgb_dev,
+                             rgb_bstride, normals_dev, normals_bstride, depth_dev, depth_bstride, mask_dev,
+                             mask_bstride, (cudaStream_t)stream);
+}
+
+int hpb_crop_boxes(hpb_ctx *ctx, int H, int W, const float *points_dev, int n_obj, int n_pts,
+                   const int32_t *obj_ids_dev, const float *K_dev, const float *TCO_dev, const float *tCR_dev, int b,
+                   int h, int w, float lamb, float *K_crop_dev, float *boxes_rend_dev, float *boxes_crop_dev,
+                   void *stream) {
+    HPB_REQUIRE(ctx, "NULL ctx");
+    HPB_REQUIRE(b >= 0 && H > 0 && W > 0 && h > 0 && w > 0 && n_obj > 0 && n_pts > 0, "bad sizes");
+    if (b == 0) return HPB_OK;
+    HPB_REQUIRE(points_dev && obj_ids_dev && K_dev && TCO_dev && tCR_dev, "NULL input");
+    HPB_REQUIRE(K_crop_dev && boxes_rend_dev && boxes_crop_dev, "NULL output");
+    HpbDeviceGuard guard(ctx->device);
+    return hpb_launch_crop_boxes(ctx, H, W, points_dev, n_pts, obj_ids_dev, K_dev, TCO_dev, tCR_dev, b, h, w, lamb,
+                                 K_crop_dev, boxes_rend_dev, boxes_crop_dev, (cudaStream_t)stream);
+}
+
+int hpb_crop(hpb_ctx *ctx, const float *images_dev, int n_im, int C, int H, int W, const int32_t *im_ids_dev,
+             const float *points_dev, int n_obj, int n_pts, const int32_t *obj_ids_dev, const float *K_dev,
+             const float *TCO_dev, const float *tCR_dev, int b, int h, int w, float lamb, float *crops_dev,
+             int64_t crops_bstride, float *K_crop_dev, float *boxes_rend_dev, float *boxes_crop_dev, void *stream) {
+    HPB_REQUIRE(ctx, "NULL ctx");
+    HPB_REQUIRE(C == 3 || C == 4, "images must have 3 or 4 channels");  // cropping.py:161
+    HPB_REQUIRE(n_im > 0 && images_dev && im_ids_dev && crops_dev, "NULL image input/output");
+    int rc = hpb_crop_boxes(ctx, H, W, points_dev, n_obj, n_pts, obj_ids_dev, K_dev, TCO_dev, tCR_dev, b, h, w, lamb,
+                            K_crop_dev, boxes_rend_dev, boxes_crop_dev, stream);
+    if (rc != HPB_OK || b == 0) return rc;
+    HpbDeviceGuard guard(ctx->device);
+    for (int s = 0; s < b; s += 32768) {  // grid.y limit
+        const int nb = b - s < 32768 ? b - s : 32768;
+        rc = hpb_launch_crop_pixels(ctx, images_dev, n_im, C, H, W, im_ids_dev + s, boxes_crop_dev + (size_t)s * 4, nb,
+                                    h, w, crops_dev + (size_t)s * crops_bstride, crops_bstride, (cudaStream_t)stream);
+        if (rc != HPB_OK) return rc;
+    }
+    return HPB_OK;
+}
+
+int hpb_normalize_T(hpb_ctx *ctx, const float *T_dev, int b, float *T_out_dev, void *stream) {
+    HPB_REQUIRE(ctx && b >= 0, "bad argument");
+    if (b == 0) return HPB_OK;
+    HPB_REQUIRE(T_dev && T_out_dev, "NULL pointer");
+    HpbDeviceGuard guard(ctx->device);
+    return hpb_launch_normalize_T(ctx, T_dev, b, T_out_dev, (cudaStream_t)stream);
+}
+
+int hpb_pose_update(hpb_ctx *ctx, const float *TCO_dev, const float *K_crop_dev, const float *out_dev,
+                    const float *tCR_dev, int b, int variant, float *TCO_out_dev, void *stream) {
+    HPB_REQUIRE(ctx && b >= 0, "bad argument");
+    HPB_REQUIRE(variant >= 0 && variant <= 2, "unknown variant");
+    if (b == 0) return HPB_OK;
+    HPB_REQUIRE(TCO_dev && K_crop_dev && out_dev && TCO_out_dev, "NULL pointer");
+    HPB_REQUIRE(variant != HPB_POSE_MEGAPOSE || tCR_dev, "tCR required by the MegaPose variant");
+    HpbDeviceGuard guard(ctx->device);
+    return hpb_launch_pose_update(ctx, TCO_dev, K_crop_dev, out_dev, tCR_dev, b, variant, TCO_out_dev, (cudaStream_t)stream);
+}
+
+int hpb_tco_init(hpb_ctx *ctx, int variant, const float *boxes_dev, const float *points_dev, int n_obj, int n_pts,
+                 const int32_t *obj_ids_dev, const float *K_dev, const float *R_dev, float z_mean, int b,
+                 float *TCO_out_dev, void *stream) {
+    HPB_REQUIRE(ctx && b >= 0, "bad argument");
+    HPB_REQUIRE(variant >= 0 && variant <= 2, "unknown variant");
+    if (b == 0) return HPB_OK;
+    HPB_REQUIRE(boxes_dev && K_dev && TCO_out_dev, "NULL pointer");
+    if (variant != HPB_TCO_INIT_FROM_BOXES)
+        HPB_REQUIRE(points_dev && obj_ids_dev && n_obj > 0 && n_pts > 0, "points required");
+    HPB_REQUIRE(variant != HPB_TCO_INIT_AUTODEPTH_WITH_R || R_dev, "R required");
+    HpbDeviceGuard guard(ctx->device);
+    return hpb_launch_tco_init(ctx, variant, boxes_dev, points_dev, n_pts, obj_ids_dev, K_dev, R_dev, z_mean, b,
+                               TCO_out_dev, (cudaStream_t)stream);
+}
+
+int hpb_multiview(hpb_ctx *ctx, const float *TCO_dev, const float *tCR_dev, int b, int mv_type, int n_views,
+                  int remove_tco_rendering, float *TCV_O_dev, void *stream) {
+    HPB_REQUIRE(ctx && b >= 0 && n_views >= 1, "bad argument");
+    if (b == 0) return HPB_OK;
+    HPB_REQUIRE(TCO_dev && tCR_dev && TCV_O_dev, "NULL pointer");
+    float pos[26 * 3];
+    int n_extra = 0, keep = 1;
+    if (n_views == 1) {  // multiview.py:190-197: identity view only
+        n_extra = 0;
+        keep = 1;
+    } else {
+        keep = remove_tco_rendering ? 0 : 1;
+        if (mv_type == HPB_MV_TCO_FRONT_1VIEW) {
+            const float q[3] = {0, 0, 0};
+            memcpy(pos, q, sizeof(q));
+            n_extra = 1;
+        } else if (mv_type == HPB_MV_TCO_FRONT_3VIEWS) {
+            const float q[9] = {0, 0, 0, 1, 0, 0, -1, 0, 0};
+            memcpy(pos, q, sizeof(q));
+            n_extra = 3;
+        } else if (mv_type == HPB_MV_SPHERE_26VIEWS) {
+            const int ys[3] = {0, 1, 2}, xs[3] = {0, -1, 1}, zs[3] = {0, 1, -1};
+            for (int yi = 0; yi < 3; ++yi)
+                for (int xi = 0; xi < 3; ++xi)
+                    for (int zi = 0; zi < 3; ++zi) {
+                        if (xs[xi] == 0 && ys[yi] == 1 && zs[zi] == 0) continue;
+                        pos[3 * n_extra] = (float)xs[xi]; pos[3 * n_extra + 1] = (float)ys[yi]; pos[3 * n_extra + 2] = (float)zs[zi];
+                        ++n_extra;
+                    }
+        } else {
+            hpb_set_error("hpb_multiview: unknown multiview type %d", mv_type);
+            return HPB_EINVAL;
+        }
+        HPB_REQUIRE(n_views == n_extra + keep, "n_views does not match the multiview type");
+    }
+    HpbDeviceGuard guard(ctx->device);
+    return hpb_launch_multiview(ctx, TCO_dev, tCR_dev, b, pos, n_extra, n_views, keep, TCV_O_dev, (cudaStream_t)stream);
+}
+
+int hpb_normalize_depth(hpb_ctx *ctx, float *depth_dev, int64_t bstride, const int32_t *plane_channels_host,
+                        int n_planes, const float *tCR_dev, int b, int h, int w, int kind, void *stream) {
+    HPB_REQUIRE(ctx && b >= 0 && n_planes >= 0 && n_planes <= 8, "bad argument (at most 8 depth planes)");
+    HPB_REQUIRE(kind >= 0 && kind <= 3, "unknown depth normalisation");
+    if (b == 0 || n_planes == 0) return HPB_OK;
+    HPB_REQUIRE(depth_dev && plane_channels_host && tCR_dev, "NULL pointer");
+    HpbDeviceGuard guard(ctx->device);
+    return hpb_launch_normalize_depth(ctx, depth_dev, bstride, plane_channels_host, n_planes, tCR_dev, b, h, w, kind,
+                                      (cudaStream_t)stream);
+}
+
+int hpb_topk_segmented(hpb_ctx *ctx, const float *scores_dev, const int32_t *group_ids_dev, int n, int n_groups,
+                       int K, int64_t *out_idx_dev, int32_t *out_count_dev, void *stream) {
+    HPB_REQUIRE(ctx && n >= 0 && n_groups >= 0, "bad argument");
+    HPB_REQUIRE(out_count_dev, "NULL out_count");
+    HPB_REQUIRE(n == 0 || (scores_dev && group_ids_dev && out_idx_dev), "NULL pointer");
+    HpbDeviceGuard guard(ctx->device);
+    return hpb_launch_topk(ctx, scores_dev, group_ids_dev, n, n_groups, K, out_idx_dev, out_count_dev, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,99 @@
+// Internal definitions shared by the kernels and the C-ABI layer of libhpb200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/hpb200.h"
+
+#define HPB_MAX_MIPS 16
+#define HPB_SUBPIX_BITS 8
+#define HPB_SUBPIX 256
+#define HPB_GUARD 4194304.0f  // 2^22 fixed-point units (16384 px) guard band for snapped vertices
+#define HPB_VIS_EMPTY 0xffffffffffffffffull
+
+// Device-side mesh record (array indexed by mesh id lives in device memory).
+struct HpbMeshDev {
+    const float *pos;    // [nv,3] metres
+    const float *nrm;    // [nv,3] unit, object frame
+    const float *uv;     // [nv,2] or nullptr
+    const uchar4 *vcol;  // [nv] RGBA or nullptr
+    const int4 *faces;   // [nf] (i0,i1,i2,0): padded to 16 B so one thread loads a triangle in one LDG.128
+    const uchar4 *tex;   // RGBA8 mip chain or nullptr
+    int nv, nf;
+    int tex_levels;
+    int tex_w[HPB_MAX_MIPS];
+    int tex_h[HPB_MAX_MIPS];
+    long long tex_off[HPB_MAX_MIPS];  // texel offset of each level
+};
+
+// Screen-space vertex produced by phase A of the rasteriser (12 B; iz == 0 marks a near-clipped vertex).
+struct HpbSVert {
+    int x, y;  // 24.8 fixed point
+    float iz;  // 1 / Z_cam
+};
+
+struct HpbMeshHost {
+    void *pos = nullptr, *nrm = nullptr, *uv = nullptr, *vcol = nullptr, *faces = nullptr, *tex = nullptr;
+    HpbMeshDev dev;
+};
+
+struct hpb_ctx {
+    int device = 0;
+    int sm_count = 0;
+    int max_smem_optin = 0;
+    std::vector<HpbMeshHost> meshes;
+    HpbMeshDev *meshes_dev = nullptr;  // device copy of all HpbMeshDev records
+    int meshes_dev_cap = 0;
+    int max_nv = 0;
+    // rasteriser workspace: one visibility buffer (+ vertex scratch for big meshes) per resident CTA
+    unsigned long long *vis = nullptr;
+    size_t vis_elems = 0;
+    HpbSVert *vert_scratch = nullptr;
+    size_t vert_scratch_elems = 0;
+    // top-k workspace
+    void *topk_ws = nullptr;
+    size_t topk_ws_bytes = 0;
+    int64_t launches = 0;
+};
+
+void hpb_set_error(const char *fmt, ...);
+
+#define HPB_CUDA_OK(expr)                                                                      \
+    do {                                                                                        \
+        cudaError_t _e = (expr);                                                                \
+        if (_e != cudaSuccess) {                                                                \
+            hpb_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+            return HPB_ECUDA;                                                                   \
+        }                                                                                       \
+    } while (0)
+
+#define HPB_REQUIRE(cond, msg)                                        \
+    do {                                                              \
+        if (!(cond)) {                                                \
+            hpb_set_error("%s: %s (%s)", __func__, msg, #cond);       \
+            return HPB_EINVAL;                                        \
+        }                                                             \
+    } while (0)
+
+struct HpbDeviceGuard {
+    int prev = -1;
+    explicit HpbDeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~HpbDeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+// kernel launchers implemented in the .cu files
+int hpb_launch_raster(hpb_ctx *ctx, const int32_t *mesh_ids, const float *TCO, const float *K, const float *ambient,
+                      int b, int h, int w, float z_near, float z_far, uint32_t flags, float *rgb, int64_t rgb_bs,
+                      float *nrm, int64_t nrm_bs, float *depth, int64_t depth_bs, uint8_t *mask, int64_t mask_bs,
+                      cudaStream_t stream);
+int hpb_launch_mip(const uchar4 *src, int sw, int sh, uchar4 *dst, int dw, int dh, cudaStream_t stream);
+int hpb_launch_tex_expand(const uint8_t *src, int n, int c, uchar4 *dst, cudaStream_t stream);
+int hpb_launch_vertex_normals(const float *pos, const int4 *faces, int nv, int nf, float *nrm, cudaStream_t stream);

@@ -1,0 +1,310 @@
+// Perspective crop + resize of the observed frame (PosePredictor.crop_inputs) for sm_100a.
+//
+// Replaces happypose/pose_estimators/megapose/models/pose_rigid.py:199-277:
+//   project_points_robust + boxes_from_uv      toolbox/lib3d/camera_geometry.py:40-67
+//   deepim_boxes / deepim_crops_robust          toolbox/lib3d/cropping.py:27-75,113-152
+//   crop_images -> torchvision.ops.roi_align    toolbox/lib3d/cropping.py:155-197 (sampling_ratio=4, aligned=False)
+//   get_K_crop_resize                           toolbox/lib3d/camera_geometry.py:70-122
+//
+// Two kernels:
+//   hpb_crop_boxes_kernel   one CTA per hypothesis: projects the object's point set, reduces min/max, builds
+//                           boxes_rend, boxes_crop and K_crop on the device.
+//   hpb_crop_pixels_kernel  one CTA per (hypothesis, band of output rows).  roi_align's 4x4 bilinear samples per
+//                           output pixel are separable: the 4 row samples and the 4 column samples of a bin are
+//                           folded into dense per-row / per-column tap weights in shared memory (a 2-3 tap span
+//                           when up-sampling, the usual case), so a pixel costs span_y*span_x loads per channel
+//                           instead of 64.  The frame is indexed by im_id: no per-hypothesis copy of the frame
+//                           (the reference materialises images[batch_im_ids], pose_estimator.py:390).
+//                           Stores are coalesced along x.  RGB-D frames also resample the depth-validity map and
+//                           zero depth where validity < 0.99 (cropping.py:181-195).
+#include "hpb_common.cuh"
+
+namespace {
+
+constexpr int CROP_SPAN = 4;       // dense tap span handled by the fast path
+constexpr int CROP_BAND = 16;      // output rows per CTA
+constexpr int CROP_THREADS = 256;
+
+struct CropBoxParams {
+    const float *points;
+    const int32_t *obj_ids;
+    const float *K, *TCO, *tCR;
+    int n_pts, b;
+    int H, W, h, w;
+    float lamb;
+    float *K_crop, *boxes_rend, *boxes_crop;
+};
+
+__global__ void __launch_bounds__(256) hpb_crop_boxes_kernel(const CropBoxParams p) {
+    const int n = blockIdx.x;
+    const int tid = threadIdx.x;
+    __shared__ float sP[12];
+    __shared__ float red[4][8];
+    const float *K = p.K + (size_t)n * 9;
+    const float *T = p.TCO + (size_t)n * 16;
+    if (tid < 12) {
+        const int i = tid / 4, j = tid % 4;  // P = K @ TCO[:3]
+        sP[tid] = fmaf(K[i * 3 + 2], T[8 + j], fmaf(K[i * 3 + 1], T[4 + j], K[i * 3] * T[j]));
+    }
+    __syncthreads();
+    const float *pts = p.points + (size_t)p.obj_ids[n] * p.n_pts * 3;
+    float mnx = INFINITY, mny = INFINITY, mxx = -INFINITY, mxy = -INFINITY;
+    for (int i = tid; i < p.n_pts; i += blockDim.x) {
+        const float x = __ldg(pts + 3 * i), y = __ldg(pts + 3 * i + 1), z = __ldg(pts + 3 * i + 2);
+        const float su = fmaf(sP[2], z, fmaf(sP[1], y, fmaf(sP[0], x, sP[3])));
+        const float sv = fmaf(sP[6], z, fmaf(sP[5], y, fmaf(sP[4], x, sP[7])));
+        float sz = fmaf(sP[10], z, fmaf(sP[9], y, fmaf(sP[8], x, sP[11])));
+        sz = fmaxf(0.1f, sz);  // project_points_robust z_min (camera_geometry.py:53-54)
+        const float u = su / sz, v = sv / sz;
+        mnx = fminf(mnx, u); mxx = fmaxf(mxx, u);
+        mny = fminf(mny, v); mxy = fmaxf(mxy, v);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        mnx = fminf(mnx, __shfl_xor_sync(0xffffffffu, mnx, o));
+        mny = fminf(mny, __shfl_xor_sync(0xffffffffu, mny, o));
+        mxx = fmaxf(mxx, __shfl_xor_sync(0xffffffffu, mxx, o));
+        mxy = fmaxf(mxy, __shfl_xor_sync(0xffffffffu, mxy, o));
+    }
+    if ((tid & 31) == 0) {
+        red[0][tid >> 5] = mnx; red[1][tid >> 5] = mny; red[2][tid >> 5] = mxx; red[3][tid >> 5] = mxy;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const int nw = blockDim.x >> 5;
+        for (int k = 1; k < nw; ++k) {
+            mnx = fminf(mnx, red[0][k]); mny = fminf(mny, red[1][k]);
+            mxx = fmaxf(mxx, red[2][k]); mxy = fmaxf(mxy, red[3][k]);
+        }
+        // reference point projection: TCR = TCO with translation tCR, point (0,0,0) (cropping.py:131-137)
+        const float *c = p.tCR + (size_t)n * 3;
+        const float su = fmaf(K[2], c[2], fmaf(K[1], c[1], K[0] * c[0]));
+        const float sv = fmaf(K[5], c[2], fmaf(K[4], c[1], K[3] * c[0]));
+        float sz = fmaf(K[8], c[2], fmaf(K[7], c[1], K[6] * c[0]));
+        sz = fmaxf(0.1f, sz);
+        const float xc = su / sz, yc = sv / sz;
+        // deepim_boxes (cropping.py:27-75); obs box == rend box on this path
+        const float r = (float)max(p.H, p.W) / (float)min(p.H, p.W);
+        const float xdist = fmaxf(fabsf(mnx - xc), fabsf(mxx - xc));
+        const float ydist = fmaxf(fabsf(mny - yc), fabsf(mxy - yc));
+        const float width = fmaxf(xdist, ydist * r) * 2.0f * p.lamb;
+        const float height = fmaxf(xdist / r, ydist) * 2.0f * p.lamb;
+        const float x1 = xc - width / 2.0f, y1 = yc - height / 2.0f, x2 = xc + width / 2.0f, y2 = yc + height / 2.0f;
+        float *br = p.boxes_rend + (size_t)n * 4;
+        br[0] = mnx; br[1] = mny; br[2] = mxx; br[3] = mxy;
+        float *bc = p.boxes_crop + (size_t)n * 4;
+        bc[0] = x1; bc[1] = y1; bc[2] = x2; bc[3] = y2;
+        // get_K_crop_resize (camera_geometry.py:70-122)
+        const float final_w = (float)max(p.h, p.w), final_h = (float)min(p.h, p.w);
+        const float cw = x2 - x1, ch = y2 - y1;
+        const float ccj = (x1 + x2) / 2.0f, cci = (y1 + y2) / 2.0f;
+        const float cx = K[2] + (cw - 1.0f) / 2.0f - ccj;
+        const float cy = K[5] + (ch - 1.0f) / 2.0f - cci;
+        const float dcx = cx - (cw - 1.0f) / 2.0f, dcy = cy - (ch - 1.0f) / 2.0f;
+        const float sx = final_w / cw, sy = final_h / ch;
+        float *ko = p.K_crop + (size_t)n * 9;
+        for (int k = 0; k < 9; ++k) ko[k] = K[k];
+        ko[0] = sx * K[0];
+        ko[4] = sy * K[4];
+        ko[2] = (final_w - 1.0f) / 2.0f + sx * dcx;
+        ko[5] = (final_h - 1.0f) / 2.0f + sy * dcy;
+    }
+}
+
+struct CropPixParams {
+    const float *images;
+    const int32_t *im_ids;
+    const float *boxes;  // [b,4]
+    int n_im, C, H, W, b, h, w;
+    float *crops;
+    long long crops_bs;
+};
+
+// One roi_align sample coordinate along one axis (torchvision roi_align bilinear_interpolate, aligned=False).
+struct AxisTap {
+    int lo, hi;
+    float wlo, whi;
+    bool valid;
+};
+
+__device__ __forceinline__ AxisTap axis_tap(float c, int n) {
+    AxisTap t;
+    t.valid = !(c < -1.0f || c > (float)n);
+    if (c <= 0.0f) c = 0.0f;
+    int lo = (int)c;
+    int hi;
+    if (lo >= n - 1) {
+        lo = hi = n - 1;
+        c = (float)lo;
+    } else {
+        hi = lo + 1;
+    }
+    const float l = c - (float)lo;
+    t.lo = lo; t.hi = hi; t.whi = l; t.wlo = 1.0f - l;
+    return t;
+}
+
+// Dense tap weights of the 4 samples of output bin `i` along one axis.  Returns false when the span exceeds
+// CROP_SPAN (heavy down-sampling): the caller then takes the generic path.
+__device__ __forceinline__ bool axis_weights(float start, float bin, int i, int n, int &base, float (&wt)[CROP_SPAN]) {
+#pragma unroll
+    for (int k = 0; k < CROP_SPAN; ++k) wt[k] = 0.0f;
+    AxisTap taps[4];
+    int lo_min = 0x7fffffff, hi_max = -1;
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        const float c = start + (float)i * bin + ((float)s + 0.5f) * bin / 4.0f;
+        taps[s] = axis_tap(c, n);
+        if (taps[s].valid) {
+            lo_min = min(lo_min, taps[s].lo);
+            hi_max = max(hi_max, taps[s].hi);
+        }
+    }
+    if (hi_max < 0) {  // no valid sample: all-zero weights
+        base = 0;
+        return true;
+    }
+    if (hi_max - lo_min >= CROP_SPAN) return false;
+    base = lo_min;
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        if (!taps[s].valid) continue;
+#pragma unroll
+        for (int k = 0; k < CROP_SPAN; ++k) {
+            if (taps[s].lo - lo_min == k) wt[k] += 0.25f * taps[s].wlo;
+            if (taps[s].hi - lo_min == k) wt[k] += 0.25f * taps[s].whi;
+        }
+    }
+    return true;
+}
+
+__global__ void __launch_bounds__(CROP_THREADS) hpb_crop_pixels_kernel(const CropPixParams p) {
+    const int n = blockIdx.y;
+    const int row0 = blockIdx.x * CROP_BAND;
+    const int tid = threadIdx.x;
+    extern __shared__ float sm[];
+    float *sWX = sm;                                  // [w][CROP_SPAN]
+    int *sBX = reinterpret_cast<int *>(sWX + (size_t)p.w * CROP_SPAN);  // [w]
+    float *sWY = reinterpret_cast<float *>(sBX + p.w);  // [CROP_BAND][CROP_SPAN]
+    int *sBY = reinterpret_cast<int *>(sWY + CROP_BAND * CROP_SPAN);  // [CROP_BAND]
+    __shared__ int sGeneric;
+
+    const float *bx = p.boxes + (size_t)n * 4;
+    const float x1 = bx[0], y1 = bx[1], x2 = bx[2], y2 = bx[3];
+    const float roi_w = fmaxf(x2 - x1, 1.0f), roi_h = fmaxf(y2 - y1, 1.0f);
+    const float bin_w = roi_w / (float)p.w, bin_h = roi_h / (float)p.h;
+    if (tid == 0) sGeneric = 0;
+    __syncthreads();
+    for (int j = tid; j < p.w; j += blockDim.x) {
+        float wt[CROP_SPAN];
+        int base;
+        if (!axis_weights(x1, bin_w, j, p.W, base, wt)) sGeneric = 1;
+        sBX[j] = base;
+#pragma unroll
+        for (int k = 0; k < CROP_SPAN; ++k) sWX[j * CROP_SPAN + k] = wt[k];
+    }
+    for (int i = tid; i < CROP_BAND; i += blockDim.x) {
+        float wt[CROP_SPAN];
+        int base = 0;
+        if (row0 + i < p.h) {
+            if (!axis_weights(y1, bin_h, row0 + i, p.H, base, wt)) sGeneric = 1;
+        } else {
+#pragma unroll
+            for (int k = 0; k < CROP_SPAN; ++k) wt[k] = 0.0f;
+        }
+        sBY[i] = base;
+#pragma unroll
+        for (int k = 0; k < CROP_SPAN; ++k) sWY[i * CROP_SPAN + k] = wt[k];
+    }
+    __syncthreads();
+    const bool generic = sGeneric != 0;
+    const int im = p.im_ids[n];
+    const float *img = p.images + (size_t)im * p.C * p.H * p.W;
+    float *out = p.crops + (size_t)n * p.crops_bs;
+    const size_t plane_in = (size_t)p.H * p.W, plane_out = (size_t)p.h * p.w;
+    const int rows = min(CROP_BAND, p.h - row0);
+    const int npx = rows * p.w;
+
+    for (int q = tid; q < npx; q += blockDim.x) {
+        const int i = q / p.w, j = q - i * p.w;
+        const int oy = row0 + i;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        float accv = 0.f;
+        if (!generic) {
+            const int by = sBY[i], bxx = sBX[j];
+#pragma unroll
+            for (int ky = 0; ky < CROP_SPAN; ++ky) {
+                const float wy = sWY[i * CROP_SPAN + ky];
+                if (wy == 0.0f) continue;
+                const int yy = min(by + ky, p.H - 1);
+#pragma unroll
+                for (int kx = 0; kx < CROP_SPAN; ++kx) {
+                    const float wx = sWX[j * CROP_SPAN + kx];
+                    if (wx == 0.0f) continue;
+                    const int xx = min(bxx + kx, p.W - 1);
+                    const float wgt = wy * wx;
+                    const float *src = img + (size_t)yy * p.W + xx;
+                    for (int c = 0; c < p.C; ++c) {
+                        const float v = __ldg(src + c * plane_in);
+                        acc[c] = fmaf(wgt, v, acc[c]);
+                        if (c == 3) accv = fmaf(wgt, v > 0.0f ? 1.0f : 0.0f, accv);
+                    }
+                }
+            }
+        } else {
+            // generic roi_align: 4x4 samples, 4 taps each (heavy down-sampling; rare on this path)
+            for (int sy = 0; sy < 4; ++sy) {
+                const AxisTap ty = axis_tap(y1 + (float)oy * bin_h + ((float)sy + 0.5f) * bin_h / 4.0f, p.H);
+                if (!ty.valid) continue;
+                for (int sx = 0; sx < 4; ++sx) {
+                    const AxisTap tx = axis_tap(x1 + (float)j * bin_w + ((float)sx + 0.5f) * bin_w / 4.0f, p.W);
+                    if (!tx.valid) continue;
+                    const float w1 = ty.wlo * tx.wlo, w2 = ty.wlo * tx.whi, w3 = ty.whi * tx.wlo, w4 = ty.whi * tx.whi;
+                    for (int c = 0; c < p.C; ++c) {
+                        const float *pl = img + c * plane_in;
+                        const float v1 = __ldg(pl + (size_t)ty.lo * p.W + tx.lo), v2 = __ldg(pl + (size_t)ty.lo * p.W + tx.hi);
+                        const float v3 = __ldg(pl + (size_t)ty.hi * p.W + tx.lo), v4 = __ldg(pl + (size_t)ty.hi * p.W + tx.hi);
+                        acc[c] += 0.0625f * (w1 * v1 + w2 * v2 + w3 * v3 + w4 * v4);
+                        if (c == 3)
+                            accv += 0.0625f * (w1 * (v1 > 0.f) + w2 * (v2 > 0.f) + w3 * (v3 > 0.f) + w4 * (v4 > 0.f));
+                    }
+                }
+            }
+        }
+        if (p.C == 4 && accv < 0.99f) acc[3] = 0.0f;  // cropping.py:191-195
+        float *o = out + (size_t)oy * p.w + j;
+        for (int c = 0; c < p.C; ++c) __stcs(o + c * plane_out, acc[c]);
+    }
+}
+
+}  // namespace
+
+int hpb_launch_crop_boxes(hpb_ctx *ctx, int H, int W, const float *points, int n_pts, const int32_t *obj_ids,
+                          const float *K, const float *TCO, const float *tCR, int b, int h, int w, float lamb,
+                          float *K_crop, float *boxes_rend, float *boxes_crop, cudaStream_t stream) {
+    if (b == 0) return HPB_OK;
+    CropBoxParams p;
+    p.points = points; p.obj_ids = obj_ids; p.K = K; p.TCO = TCO; p.tCR = tCR;
+    p.n_pts = n_pts; p.b = b; p.H = H; p.W = W; p.h = h; p.w = w; p.lamb = lamb;
+    p.K_crop = K_crop; p.boxes_rend = boxes_rend; p.boxes_crop = boxes_crop;
+    hpb_crop_boxes_kernel<<<b, 256, 0, stream>>>(p);
+    HPB_CUDA_OK(cudaGetLastError());
+    ctx->launches++;
+    return HPB_OK;
+}
+
+int hpb_launch_crop_pixels(hpb_ctx *ctx, const float *images, int n_im, int C, int H, int W, const int32_t *im_ids,
+                           const float *boxes, int b, int h, int w, float *crops, int64_t crops_bs,
+                           cudaStream_t stream) {
+    if (b == 0) return HPB_OK;
+    CropPixParams p;
+    p.images = images; p.im_ids = im_ids; p.boxes = boxes;
+    p.n_im = n_im; p.C = C; p.H = H; p.W = W; p.b = b; p.h = h; p.w = w;
+    p.crops = crops; p.crops_bs = crops_bs;
+    const size_t smem = (size_t)w * CROP_SPAN * sizeof(float) + (size_t)w * sizeof(int) +
+                        CROP_BAND * CROP_SPAN * sizeof(float) + CROP_BAND * sizeof(int);
+    dim3 grid((h + CROP_BAND - 1) / CROP_BAND, b);
+    hpb_crop_pixels_kernel<<<grid, CROP_THREADS, smem, stream>>>(p);
+    HPB_CUDA_OK(cudaGetLastError());
+    ctx->launches++;
+    return HPB_OK;
+}

@@ -1,0 +1,348 @@
+// Small per-hypothesis pose kernels for sm_100a (one launch each; they replace chains of ~10-30 eager torch ops
+// and, for the multiview placement, a per-sample CPU loop over Panda3D scene-graph nodes).
+//
+//   hpb_normalize_T_kernel   toolbox/lib3d/transform_ops.py:107-120 (normalize_T) + rotations.py:22-36 (ortho6d)
+//   hpb_pose_update_kernel   megapose/models/pose_rigid.py:339-350 -> toolbox/lib3d/cosypose_ops.py:34-62;
+//                            cosypose/lib3d/cosypose_ops.py:18-42 + cosypose/models/pose.py:95-106
+//   hpb_tco_init_kernel      toolbox/lib3d/cosypose_ops.py:159-181,184-238,241-283
+//   hpb_multiview_kernel     toolbox/lib3d/multiview.py:28-92,166-251 (Panda3D NodePath.lookAt in closed form)
+//   hpb_normalize_depth_kernel  megapose/models/pose_rigid.py:510-544
+#include "hpb_common.cuh"
+
+namespace {
+
+// columns (x, y, z) of R from the 6-D representation (a = first column, b = second column)
+__device__ __forceinline__ void ortho6d(const float a[3], const float bb[3], float R[9]) {
+    const float na = sqrtf(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
+    const float x0 = a[0] / na, x1 = a[1] / na, x2 = a[2] / na;
+    float z0 = x1 * bb[2] - x2 * bb[1], z1 = x2 * bb[0] - x0 * bb[2], z2 = x0 * bb[1] - x1 * bb[0];
+    const float nz = sqrtf(z0 * z0 + z1 * z1 + z2 * z2);
+    z0 /= nz; z1 /= nz; z2 /= nz;
+    const float y0 = z1 * x2 - z2 * x1, y1 = z2 * x0 - z0 * x2, y2 = z0 * x1 - z1 * x0;
+    R[0] = x0; R[1] = y0; R[2] = z0;
+    R[3] = x1; R[4] = y1; R[5] = z1;
+    R[6] = x2; R[7] = y2; R[8] = z2;
+}
+
+__global__ void hpb_normalize_T_kernel(const float *T, int b, float *out) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= b) return;
+    const float *t = T + (size_t)n * 16;
+    const float a[3] = {t[0], t[4], t[8]}, c[3] = {t[1], t[5], t[9]};
+    const float tr[3] = {t[3], t[7], t[11]};
+    float R[9];
+    ortho6d(a, c, R);
+    float *o = out + (size_t)n * 16;
+    o[0] = R[0]; o[1] = R[1]; o[2] = R[2]; o[3] = tr[0];
+    o[4] = R[3]; o[5] = R[4]; o[6] = R[5]; o[7] = tr[1];
+    o[8] = R[6]; o[9] = R[7]; o[10] = R[8]; o[11] = tr[2];
+    o[12] = 0.f; o[13] = 0.f; o[14] = 0.f; o[15] = 1.f;
+}
+
+// xyzw quaternion -> R through the angle-axis route of the reference (rotations.py:196-229: quat2mat ->
+// quaternion_to_angle_axis -> angle_axis_to_rotation_matrix); algebraically the standard unit-quaternion matrix.
+__device__ __forceinline__ void quat_to_R(const float q[4], float R[9]) {
+    const float nq = sqrtf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+    const float x = q[0] / nq, y = q[1] / nq, z = q[2] / nq, w = q[3] / nq;
+    R[0] = 1.f - 2.f * (y * y + z * z); R[1] = 2.f * (x * y - z * w); R[2] = 2.f * (x * z + y * w);
+    R[3] = 2.f * (x * y + z * w); R[4] = 1.f - 2.f * (x * x + z * z); R[5] = 2.f * (y * z - x * w);
+    R[6] = 2.f * (x * z - y * w); R[7] = 2.f * (y * z + x * w); R[8] = 1.f - 2.f * (x * x + y * y);
+}
+
+__global__ void hpb_pose_update_kernel(const float *TCO, const float *K_crop, const float *outv, const float *tCR,
+                                       int b, int variant, float *TCO_out) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= b) return;
+    float T[16];
+    for (int k = 0; k < 16; ++k) T[k] = TCO[(size_t)n * 16 + k];
+    const float fx = K_crop[(size_t)n * 9], fy = K_crop[(size_t)n * 9 + 4];
+    float dR[9], vx, vy, vz;
+    if (variant == HPB_POSE_COSYPOSE_QUAT) {
+        const float *o = outv + (size_t)n * 7;
+        const float q[4] = {o[0], o[1], o[2], o[3]};
+        quat_to_R(q, dR);
+        vx = o[4]; vy = o[5]; vz = o[6];
+    } else {
+        const float *o = outv + (size_t)n * 9;
+        const float a[3] = {o[0], o[1], o[2]}, c[3] = {o[3], o[4], o[5]};
+        ortho6d(a, c, dR);
+        vx = o[6]; vy = o[7]; vz = o[8];
+    }
+    float ref[3];  // reference point in the camera frame
+    if (variant == HPB_POSE_MEGAPOSE) {
+        ref[0] = tCR[(size_t)n * 3]; ref[1] = tCR[(size_t)n * 3 + 1]; ref[2] = tCR[(size_t)n * 3 + 2];
+    } else {
+        ref[0] = T[3]; ref[1] = T[7]; ref[2] = T[11];
+    }
+    const float zsrc = ref[2];
+    const float ztgt = vz * zsrc;
+    const float rx = (vx / fx + ref[0] / zsrc) * ztgt;
+    const float ry = (vy / fy + ref[1] / zsrc) * ztgt;
+    float tn[3];
+    if (variant == HPB_POSE_MEGAPOSE) {
+        const float d0 = T[3] - ref[0], d1 = T[7] - ref[1], d2 = T[11] - ref[2];
+        tn[0] = dR[0] * d0 + dR[1] * d1 + dR[2] * d2 + rx;
+        tn[1] = dR[3] * d0 + dR[4] * d1 + dR[5] * d2 + ry;
+        tn[2] = dR[6] * d0 + dR[7] * d1 + dR[8] * d2 + ztgt;
+    } else {
+        tn[0] = rx; tn[1] = ry; tn[2] = ztgt;
+    }
+    float *o = TCO_out + (size_t)n * 16;
+    float Rn[9];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j)
+            Rn[i * 3 + j] = dR[i * 3] * T[j] + dR[i * 3 + 1] * T[4 + j] + dR[i * 3 + 2] * T[8 + j];
+    o[0] = Rn[0]; o[1] = Rn[1]; o[2] = Rn[2]; o[3] = tn[0];
+    o[4] = Rn[3]; o[5] = Rn[4]; o[6] = Rn[5]; o[7] = tn[1];
+    o[8] = Rn[6]; o[9] = Rn[7]; o[10] = Rn[8]; o[11] = tn[2];
+    o[12] = T[12]; o[13] = T[13]; o[14] = T[14]; o[15] = T[15];  // TCO.clone(): last row carried over
+}
+
+struct TcoInitParams {
+    int variant;
+    const float *boxes, *points;
+    const int32_t *obj_ids;
+    const float *K, *R;
+    float z_mean;
+    int n_pts, b;
+    float *out;
+};
+
+__global__ void __launch_bounds__(256) hpb_tco_init_kernel(const TcoInitParams p) {
+    const int n = blockIdx.x, tid = threadIdx.x;
+    __shared__ float red[4][8];
+    const float *K = p.K + (size_t)n * 9;
+    const float *bx = p.boxes + (size_t)n * 4;
+    const float fx = K[0], fy = K[4], cx = K[2], cy = K[5];
+    const float ucx = (bx[0] + bx[2]) / 2.0f, ucy = (bx[1] + bx[3]) / 2.0f;
+    float R[9] = {0.f, 1.f, 0.f, 0.f, 0.f, -1.f, -1.f, 0.f, 0.f};
+    if (p.variant == HPB_TCO_INIT_AUTODEPTH_WITH_R)
+        for (int k = 0; k < 9; ++k) R[k] = p.R[(size_t)n * 9 + k];
+    float *o = p.out + (size_t)n * 16;
+    if (p.variant == HPB_TCO_INIT_FROM_BOXES) {
+        if (tid == 0) {
+            const float z = p.z_mean;
+            o[0] = 1.f; o[1] = 0.f; o[2] = 0.f; o[3] = ((ucx - cx) * z) / fx;
+            o[4] = 0.f; o[5] = 1.f; o[6] = 0.f; o[7] = ((ucy - cy) * z) / fy;
+            o[8] = 0.f; o[9] = 0.f; o[10] = 1.f; o[11] = z;
+            o[12] = 0.f; o[13] = 0.f; o[14] = 0.f; o[15] = 1.f;
+        }
+        return;
+    }
+    // z_guess = 1: translation (tx, ty, 1); only the x/y extents of the transformed points are needed
+    const float tx = ((ucx - cx) * 1.0f) / fx, ty = ((ucy - cy) * 1.0f) / fy;
+    const float *pts = p.points + (size_t)p.obj_ids[n] * p.n_pts * 3;
+    float mnx = INFINITY, mny = INFINITY, mxx = -INFINITY, mxy = -INFINITY;
+    for (int i = tid; i < p.n_pts; i += blockDim.x) {
+        const float x = __ldg(pts + 3 * i), y = __ldg(pts + 3 * i + 1), z = __ldg(pts + 3 * i + 2);
+        const float X = R[0] * x + R[1] * y + R[2] * z + tx;
+        const float Y = R[3] * x + R[4] * y + R[5] * z + ty;
+        mnx = fminf(mnx, X); mxx = fmaxf(mxx, X);
+        mny = fminf(mny, Y); mxy = fmaxf(mxy, Y);
+    }
+    for (int s = 16; s > 0; s >>= 1) {
+        mnx = fminf(mnx, __shfl_xor_sync(0xffffffffu, mnx, s));
+        mny = fminf(mny, __shfl_xor_sync(0xffffffffu, mny, s));
+        mxx = fmaxf(mxx, __shfl_xor_sync(0xffffffffu, mxx, s));
+        mxy = fmaxf(mxy, __shfl_xor_sync(0xffffffffu, mxy, s));
+    }
+    if ((tid & 31) == 0) {
+        red[0][tid >> 5] = mnx; red[1][tid >> 5] = mny; red[2][tid >> 5] = mxx; red[3][tid >> 5] = mxy;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        for (int k = 1; k < (int)(blockDim.x >> 5); ++k) {
+            mnx = fminf(mnx, red[0][k]); mny = fminf(mny, red[1][k]);
+            mxx = fmaxf(mxx, red[2][k]); mxy = fmaxf(mxy, red[3][k]);
+        }
+        const float dx3 = mxx - mnx, dy3 = mxy - mny;
+        const float bdx = (bx[2] - bx[0]) + 1.0f, bdy = (bx[3] - bx[1]) + 1.0f;
+        const float z = ((fy * dy3 / bdy) + (fx * dx3 / bdx)) / 2.0f;
+        o[0] = R[0]; o[1] = R[1]; o[2] = R[2]; o[3] = ((ucx - cx) * z) / fx;
+        o[4] = R[3]; o[5] = R[4]; o[6] = R[5]; o[7] = ((ucy - cy) * z) / fy;
+        o[8] = R[6]; o[9] = R[7]; o[10] = R[8]; o[11] = z;
+        o[12] = 0.f; o[13] = 0.f; o[14] = 0.f; o[15] = 1.f;
+    }
+}
+
+// ---- multiview camera placement (float64 like the reference's numpy path, cast to float32 at the end) ----
+struct M4 { double m[16]; };
+
+__device__ __forceinline__ M4 m4_mul(const M4 &a, const M4 &b) {
+    M4 r;
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) {
+            double s = 0;
+            for (int k = 0; k < 4; ++k) s += a.m[i * 4 + k] * b.m[k * 4 + j];
+            r.m[i * 4 + j] = s;
+        }
+    return r;
+}
+__device__ __forceinline__ M4 m4_rigid_inv(const M4 &a) {  // (R, t) -> (R^T, -R^T t)
+    M4 r;
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) r.m[i * 4 + j] = a.m[j * 4 + i];
+    for (int i = 0; i < 3; ++i) r.m[i * 4 + 3] = -(r.m[i * 4] * a.m[3] + r.m[i * 4 + 1] * a.m[7] + r.m[i * 4 + 2] * a.m[11]);
+    r.m[12] = r.m[13] = r.m[14] = 0;
+    r.m[15] = 1;
+    return r;
+}
+// Panda3D look_at(): +Y exactly at the target, +Z as close to `up` as possible, +X = Y x Z; node axes as columns.
+__device__ __forceinline__ void look_at(const double pos[3], const double tgt[3], const double up[3], double R[9]) {
+    double f[3] = {tgt[0] - pos[0], tgt[1] - pos[1], tgt[2] - pos[2]};
+    const double nf = sqrt(f[0] * f[0] + f[1] * f[1] + f[2] * f[2]);
+    f[0] /= nf; f[1] /= nf; f[2] /= nf;
+    double r[3] = {f[1] * up[2] - f[2] * up[1], f[2] * up[0] - f[0] * up[2], f[0] * up[1] - f[1] * up[0]};
+    const double nr = sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+    r[0] /= nr; r[1] /= nr; r[2] /= nr;
+    const double u[3] = {r[1] * f[2] - r[2] * f[1], r[2] * f[0] - r[0] * f[2], r[0] * f[1] - r[1] * f[0]};
+    R[0] = r[0]; R[1] = f[0]; R[2] = u[0];
+    R[3] = r[1]; R[4] = f[1]; R[5] = u[1];
+    R[6] = r[2]; R[7] = f[2]; R[8] = u[2];
+}
+
+__constant__ float c_mv_pos[26 * 3];
+
+__global__ void hpb_multiview_kernel(const float *TCO, const float *tCR, int b, int n_extra, int n_views,
+                                     int keep_tco, float *out) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= b) return;
+    const float *Tf = TCO + (size_t)n * 16;
+    float *o = out + (size_t)n * n_views * 16;
+    int v0 = 0;
+    if (keep_tco) {
+        for (int k = 0; k < 16; ++k) o[k] = Tf[k];
+        v0 = 1;
+    }
+    if (n_extra == 0) return;
+    M4 T;
+    for (int k = 0; k < 16; ++k) T.m[k] = (double)Tf[k];
+    double c[3] = {(double)tCR[(size_t)n * 3], (double)tCR[(size_t)n * 3 + 1], (double)tCR[(size_t)n * 3 + 2]};
+    T.m[12] = T.m[13] = T.m[14] = 0; T.m[15] = 1;
+    M4 TOC = m4_rigid_inv(T);
+    bool fin = true;
+    for (int k = 0; k < 12; ++k) fin = fin && isfinite(TOC.m[k]);
+    if (!fin) {  // multiview.py:44-46
+        for (int k = 0; k < 16; ++k) TOC.m[k] = (k % 5 == 0) ? 1.0 : 0.0;
+        c[0] = c[1] = c[2] = 0;
+    }
+    const M4 CCGL = {{1, 0, 0, 0, 0, 0, -1, 0, 0, 1, 0, 0, 0, 0, 0, 1}};
+    const M4 CCGLi = {{1, 0, 0, 0, 0, 0, 1, 0, 0, -1, 0, 0, 0, 0, 0, 1}};
+    const M4 WC0 = m4_mul(TOC, CCGL);
+    const double ref[3] = {TOC.m[0] * c[0] + TOC.m[1] * c[1] + TOC.m[2] * c[2] + TOC.m[3],
+                           TOC.m[4] * c[0] + TOC.m[5] * c[1] + TOC.m[6] * c[2] + TOC.m[7],
+                           TOC.m[8] * c[0] + TOC.m[9] * c[1] + TOC.m[10] * c[2] + TOC.m[11]};
+    const double radius = sqrt(c[0] * c[0] + c[1] * c[1] + c[2] * c[2]);
+    const double up[3] = {WC0.m[2], WC0.m[6], WC0.m[10]};
+    const double c0[3] = {WC0.m[3], WC0.m[7], WC0.m[11]};
+    double Rp[9];
+    look_at(c0, ref, up, Rp);
+    const M4 C0W = m4_rigid_inv(WC0);
+    for (int e = 0; e < n_extra; ++e) {
+        const double q[3] = {c_mv_pos[3 * e] * radius, c_mv_pos[3 * e + 1] * radius, c_mv_pos[3 * e + 2] * radius};
+        const double pos[3] = {c0[0] + Rp[0] * q[0] + Rp[1] * q[1] + Rp[2] * q[2],
+                               c0[1] + Rp[3] * q[0] + Rp[4] * q[1] + Rp[5] * q[2],
+                               c0[2] + Rp[6] * q[0] + Rp[7] * q[1] + Rp[8] * q[2]};
+        double Rn[9];
+        look_at(pos, ref, up, Rn);
+        M4 WN;
+        for (int i = 0; i < 3; ++i) {
+            for (int j = 0; j < 3; ++j) WN.m[i * 4 + j] = Rn[i * 3 + j];
+            WN.m[i * 4 + 3] = pos[i];
+        }
+        WN.m[12] = WN.m[13] = WN.m[14] = 0; WN.m[15] = 1;
+        const M4 TC0_CV = m4_mul(m4_mul(CCGL, m4_mul(C0W, WN)), CCGLi);
+        // cast to float32, invert as a rigid transform and compose with TCO in float32
+        // (invert_transform_matrices(TC0_CV) @ TCO, multiview.py:236)
+        float A[16];
+        for (int k = 0; k < 16; ++k) A[k] = (float)TC0_CV.m[k];
+        float Ai[12];
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) Ai[i * 4 + j] = A[j * 4 + i];
+        for (int i = 0; i < 3; ++i) Ai[i * 4 + 3] = -(Ai[i * 4] * A[3] + Ai[i * 4 + 1] * A[7] + Ai[i * 4 + 2] * A[11]);
+        float *ov = o + (size_t)(v0 + e) * 16;
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 4; ++j)
+                ov[i * 4 + j] = Ai[i * 4] * Tf[j] + Ai[i * 4 + 1] * Tf[4 + j] + Ai[i * 4 + 2] * Tf[8 + j] + Ai[i * 4 + 3] * Tf[12 + j];
+        for (int j = 0; j < 4; ++j)
+            ov[12 + j] = A[12] * Tf[j] + A[13] * Tf[4 + j] + A[14] * Tf[8 + j] + A[15] * Tf[12 + j];
+    }
+}
+
+__global__ void hpb_normalize_depth_kernel(float *depth, long long bstride, int c0, int c1, int c2, int c3, int c4,
+                                           int c5, int c6, int c7, int n_planes, const float *tCR, int b, int hw,
+                                           int kind) {
+    const int chans[8] = {c0, c1, c2, c3, c4, c5, c6, c7};
+    const long long total = (long long)b * n_planes * hw;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int pix = (int)(i % hw);
+        const long long r = i / hw;
+        const int pl = (int)(r % n_planes), n = (int)(r / n_planes);
+        float *d = depth + (size_t)n * bstride + (size_t)chans[pl] * hw + pix;
+        const float z = tCR[(size_t)n * 3 + 2];
+        float v = *d;
+        if (kind == HPB_DEPTH_NORM_TCR_SCALE) v = v / z;
+        else if (kind == HPB_DEPTH_NORM_TCR_SCALE_CLAMP_CENTER) v = fminf(fmaxf(v / z, 0.0f), 2.0f) - 1.0f;
+        else if (kind == HPB_DEPTH_NORM_TCR_CENTER_CLAMP) v = fminf(fmaxf(v - z, -2.0f), 2.0f);
+        *d = v;
+    }
+}
+
+}  // namespace
+
+int hpb_launch_normalize_T(hpb_ctx *ctx, const float *T, int b, float *out, cudaStream_t stream) {
+    if (b == 0) return HPB_OK;
+    hpb_normalize_T_kernel<<<(b + 127) / 128, 128, 0, stream>>>(T, b, out);
+    HPB_CUDA_OK(cudaGetLastError());
+    ctx->launches++;
+    return HPB_OK;
+}
+
+int hpb_launch_pose_update(hpb_ctx *ctx, const float *TCO, const float *K_crop, const float *outv, const float *tCR,
+                           int b, int variant, float *TCO_out, cudaStream_t stream) {
+    if (b == 0) return HPB_OK;
+    hpb_pose_update_kernel<<<(b + 127) / 128, 128, 0, stream>>>(TCO, K_crop, outv, tCR, b, variant, TCO_out);
+    HPB_CUDA_OK(cudaGetLastError());
+    ctx->launches++;
+    return HPB_OK;
+}
+
+int hpb_launch_tco_init(hpb_ctx *ctx, int variant, const float *boxes, const float *points, int n_pts,
+                        const int32_t *obj_ids, const float *K, const float *R, float z_mean, int b, float *out,
+                        cudaStream_t stream) {
+    if (b == 0) return HPB_OK;
+    TcoInitParams p;
+    p.variant = variant; p.boxes = boxes; p.points = points; p.obj_ids = obj_ids; p.K = K; p.R = R;
+    p.z_mean = z_mean; p.n_pts = n_pts; p.b = b; p.out = out;
+    hpb_tco_init_kernel<<<b, 256, 0, stream>>>(p);
+    HPB_CUDA_OK(cudaGetLastError());
+    ctx->launches++;
+    return HPB_OK;
+}
+
+int hpb_launch_multiview(hpb_ctx *ctx, const float *TCO, const float *tCR, int b, const float *positions_host,
+                         int n_extra, int n_views, int keep_tco, float *out, cudaStream_t stream) {
+    if (b == 0) return HPB_OK;
+    if (n_extra > 0)
+        HPB_CUDA_OK(cudaMemcpyToSymbolAsync(c_mv_pos, positions_host, sizeof(float) * 3 * n_extra, 0,
+                                            cudaMemcpyHostToDevice, stream));
+    hpb_multiview_kernel<<<(b + 63) / 64, 64, 0, stream>>>(TCO, tCR, b, n_extra, n_views, keep_tco, out);
+    HPB_CUDA_OK(cudaGetLastError());
+    ctx->launches++;
+    return HPB_OK;
+}
+
+int hpb_launch_normalize_depth(hpb_ctx *ctx, float *depth, int64_t bstride, const int32_t *chans, int n_planes,
+                               const float *tCR, int b, int h, int w, int kind, cudaStream_t stream) {
+    if (b == 0 || n_planes == 0 || kind == HPB_DEPTH_NORM_NONE) return HPB_OK;
+    int c[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < n_planes; ++i) c[i] = chans[i];
+    const long long total = (long long)b * n_planes * h * w;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > ctx->sm_count * 16) blocks = ctx->sm_count * 16;
+    hpb_normalize_depth_kernel<<<blocks, 256, 0, stream>>>(depth, bstride, c[0], c[1], c[2], c[3], c[4], c[5], c[6],
+                                                           c[7], n_planes, tCR, b, h * w, kind);
+    HPB_CUDA_OK(cudaGetLastError());
+    ctx->launches++;
+    return HPB_OK;
+}

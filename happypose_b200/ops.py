@@ -1,0 +1,293 @@
+"""Torch-tensor front end of the C ABI (include/hpb200.h): one Python function per entry point.
+
+All functions enqueue on torch's current CUDA stream and never synchronise the host.  Inputs are cast to
+contiguous float32 / int32 on the context's device; outputs are freshly allocated torch tensors owned by the
+caller (the reference returns fresh tensors too, panda3d_batch_renderer.py:245-286).
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _capi
+from ._capi import Context, ptr, stream_ptr
+
+
+def _f32(t, device) -> torch.Tensor:
+    return torch.as_tensor(t).to(device=device, dtype=torch.float32).contiguous()
+
+
+def _i32(t, device) -> torch.Tensor:
+    return torch.as_tensor(t).to(device=device, dtype=torch.int32).contiguous()
+
+
+# ------------------------------------------------------------------------------------------------
+# meshes
+# ------------------------------------------------------------------------------------------------
+def mesh_upload(ctx: Context, verts_m, faces, normals=None, uv=None, vcolor=None, texture=None) -> int:
+    """verts_m: [nv,3] float32 METRES.  Returns the dense mesh id."""
+    v = np.ascontiguousarray(np.asarray(verts_m, np.float32))
+    f = np.ascontiguousarray(np.asarray(faces, np.int32))
+    if v.ndim != 2 or v.shape[1] != 3 or f.ndim != 2 or f.shape[1] != 3:
+        raise ValueError("verts must be [nv,3] and faces [nf,3] (triangles only)")
+    n = None if normals is None else np.ascontiguousarray(np.asarray(normals, np.float32))
+    t = None if uv is None else np.ascontiguousarray(np.asarray(uv, np.float32))
+    c = None
+    if vcolor is not None:
+        c = np.asarray(vcolor, np.uint8)
+        if c.shape[1] == 3:
+            c = np.concatenate([c, np.full((len(c), 1), 255, np.uint8)], 1)
+        c = np.ascontiguousarray(c)
+    tex = None if texture is None else np.ascontiguousarray(np.asarray(texture, np.uint8))
+    for a, name, width in ((n, "normals", 3), (t, "uv", 2), (c, "vcolor", 4)):
+        if a is not None and a.shape != (len(v), width):
+            raise ValueError(f"{name} must be [nv,{width}]")
+    th, tw, tc = (tex.shape[0], tex.shape[1], tex.shape[2]) if tex is not None else (0, 0, 0)
+    mid = ctypes.c_int32(-1)
+    rc = ctx.lib.hpb_mesh_upload(
+        ctx.handle, v.ctypes.data, None if n is None else n.ctypes.data, None if t is None else t.ctypes.data,
+        None if c is None else c.ctypes.data, len(v), f.ctypes.data, len(f),
+        None if tex is None else tex.ctypes.data, th, tw, tc, ctypes.byref(mid))
+    ctx.check(rc, "hpb_mesh_upload")
+    return int(mid.value)
+
+
+def mesh_get_mip(ctx: Context, mesh_id: int, level: int) -> Optional[np.ndarray]:
+    w, h, levels = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_int(0)
+    ctx.check(ctx.lib.hpb_mesh_get_mip(ctx.handle, mesh_id, level, None, ctypes.byref(w), ctypes.byref(h), ctypes.byref(levels)), "hpb_mesh_get_mip")
+    if levels.value == 0:
+        return None
+    out = np.empty((h.value, w.value, 4), np.uint8)
+    ctx.check(ctx.lib.hpb_mesh_get_mip(ctx.handle, mesh_id, level, out.ctypes.data, None, None, None), "hpb_mesh_get_mip")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# rasteriser
+# ------------------------------------------------------------------------------------------------
+def render(
+    ctx: Context,
+    mesh_ids: torch.Tensor,
+    TCO: torch.Tensor,
+    K: torch.Tensor,
+    resolution: Tuple[int, int],
+    ambient: Optional[torch.Tensor] = None,
+    render_rgb: bool = True,
+    render_normals: bool = False,
+    render_depth: bool = False,
+    render_binary_mask: bool = False,
+    z_near: float = 0.1,
+    z_far: float = 10.0,
+    out: Optional[torch.Tensor] = None,
+    out_channel_offset: int = 0,
+):
+    """Renders b scenes.  Returns (rgb, normals, depth, mask) tensors (None when not requested).
+
+    If `out` ([b, C_total, h, w] float32, contiguous) is given, rgb / normals / depth are written into consecutive
+    channels of `out` starting at `out_channel_offset` (rgb 3, then normals 3, then depth 1) and the returned
+    tensors are views of it -- the rasteriser then writes the network input in place (no torch.cat).
+    """
+    dev = ctx.device
+    h, w = int(resolution[0]), int(resolution[1])
+    TCO = _f32(TCO, dev).reshape(-1, 16)
+    K = _f32(K, dev).reshape(-1, 9)
+    b = TCO.shape[0]
+    assert K.shape[0] == b, "K and TCO batch sizes differ"
+    mesh_ids = _i32(mesh_ids, dev)
+    assert mesh_ids.numel() == b, "Need same number of labels as TCO/K batch size"
+    amb = None if ambient is None else _f32(ambient, dev).reshape(b, 3)
+    flags = (1 if render_rgb else 0) | (2 if render_normals else 0) | (4 if render_depth else 0) | (8 if render_binary_mask else 0)
+    rgb = nrm = dep = msk = None
+    if out is not None:
+        assert out.is_contiguous() and out.dtype == torch.float32 and out.shape[0] == b and tuple(out.shape[2:]) == (h, w)
+        c, bs = out_channel_offset, out.stride(0)
+        if render_rgb:
+            rgb = out[:, c:c + 3]; c += 3
+        if render_normals:
+            nrm = out[:, c:c + 3]; c += 3
+        if render_depth:
+            dep = out[:, c:c + 1]; c += 1
+        assert c <= out.shape[1]
+        strides = (bs, bs, bs)
+    else:
+        if render_rgb:
+            rgb = torch.empty((b, 3, h, w), dtype=torch.float32, device=dev)
+        if render_normals:
+            nrm = torch.empty((b, 3, h, w), dtype=torch.float32, device=dev)
+        if render_depth:
+            dep = torch.empty((b, 1, h, w), dtype=torch.float32, device=dev)
+        strides = (3 * h * w, 3 * h * w, h * w)
+    if render_binary_mask:
+        msk = torch.empty((b, 1, h, w), dtype=torch.bool, device=dev)
+    if b > 0:
+        rc = ctx.lib.hpb_render(
+            ctx.handle, ptr(mesh_ids), ptr(TCO), ptr(K), ptr(amb), b, h, w, z_near, z_far, flags,
+            ptr(rgb), strides[0], ptr(nrm), strides[1], ptr(dep), strides[2], ptr(msk), h * w, stream_ptr(dev))
+        ctx.check(rc, "hpb_render")
+    return rgb, nrm, dep, msk
+
+
+# ------------------------------------------------------------------------------------------------
+# crop
+# ------------------------------------------------------------------------------------------------
+def crop(
+    ctx: Context,
+    images: torch.Tensor,
+    im_ids: torch.Tensor,
+    points: torch.Tensor,
+    obj_ids: torch.Tensor,
+    K: torch.Tensor,
+    TCO: torch.Tensor,
+    tCR: torch.Tensor,
+    render_size: Tuple[int, int],
+    lamb: float = 1.4,
+    out: Optional[torch.Tensor] = None,
+):
+    """crop_inputs: returns (images_cropped [b,C,h,w], K_crop [b,3,3], boxes_rend [b,4], boxes_crop [b,4]).
+
+    images [n_im,C,H,W] float32 (not expanded per hypothesis), im_ids [b]; points [n_obj,n_pts,3], obj_ids [b].
+    With `out` ([b,C_total,h,w]) the crop is written into channels [0,C) of it.
+    """
+    dev = ctx.device
+    images = _f32(images, dev)
+    n_im, C, H, W = images.shape
+    h, w = int(render_size[0]), int(render_size[1])
+    K = _f32(K, dev).reshape(-1, 9)
+    TCO = _f32(TCO, dev).reshape(-1, 16)
+    tCR = _f32(tCR, dev).reshape(-1, 3)
+    b = TCO.shape[0]
+    assert K.shape[0] == b and tCR.shape[0] == b
+    im_ids = _i32(im_ids, dev)
+    obj_ids = _i32(obj_ids, dev)
+    points = _f32(points, dev)
+    assert points.dim() == 3 and points.shape[2] == 3
+    if out is not None:
+        assert out.is_contiguous() and out.dtype == torch.float32 and out.shape[0] == b and tuple(out.shape[2:]) == (h, w)
+        crops, bs = out[:, :C], out.stride(0)
+    else:
+        crops = torch.empty((b, C, h, w), dtype=torch.float32, device=dev)
+        bs = C * h * w
+    K_crop = torch.empty((b, 3, 3), dtype=torch.float32, device=dev)
+    boxes_rend = torch.empty((b, 4), dtype=torch.float32, device=dev)
+    boxes_crop = torch.empty((b, 4), dtype=torch.float32, device=dev)
+    rc = ctx.lib.hpb_crop(
+        ctx.handle, ptr(images), n_im, C, H, W, ptr(im_ids), ptr(points), points.shape[0], points.shape[1], ptr(obj_ids),
+        ptr(K), ptr(TCO), ptr(tCR), b, h, w, lamb, ptr(crops), bs, ptr(K_crop), ptr(boxes_rend), ptr(boxes_crop),
+        stream_ptr(dev))
+    ctx.check(rc, "hpb_crop")
+    return crops, K_crop, boxes_rend, boxes_crop
+
+
+def crop_boxes(ctx: Context, image_size, points, obj_ids, K, TCO, tCR, render_size, lamb: float = 1.4):
+    """compute_crops_multiview maths: (K_crop, boxes_rend, boxes_crop) without resampling any pixels."""
+    dev = ctx.device
+    H, W = int(image_size[0]), int(image_size[1])
+    h, w = int(render_size[0]), int(render_size[1])
+    K = _f32(K, dev).reshape(-1, 9)
+    TCO = _f32(TCO, dev).reshape(-1, 16)
+    tCR = _f32(tCR, dev).reshape(-1, 3)
+    b = TCO.shape[0]
+    obj_ids = _i32(obj_ids, dev)
+    points = _f32(points, dev)
+    K_crop = torch.empty((b, 3, 3), dtype=torch.float32, device=dev)
+    boxes_rend = torch.empty((b, 4), dtype=torch.float32, device=dev)
+    boxes_crop = torch.empty((b, 4), dtype=torch.float32, device=dev)
+    rc = ctx.lib.hpb_crop_boxes(
+        ctx.handle, H, W, ptr(points), points.shape[0], points.shape[1], ptr(obj_ids), ptr(K), ptr(TCO), ptr(tCR),
+        b, h, w, lamb, ptr(K_crop), ptr(boxes_rend), ptr(boxes_crop), stream_ptr(dev))
+    ctx.check(rc, "hpb_crop_boxes")
+    return K_crop, boxes_rend, boxes_crop
+
+
+# ------------------------------------------------------------------------------------------------
+# pose maths
+# ------------------------------------------------------------------------------------------------
+def normalize_T(ctx: Context, T: torch.Tensor) -> torch.Tensor:
+    dev = ctx.device
+    shape = T.shape
+    Tf = _f32(T, dev).reshape(-1, 16)
+    out = torch.empty_like(Tf)
+    ctx.check(ctx.lib.hpb_normalize_T(ctx.handle, ptr(Tf), Tf.shape[0], ptr(out), stream_ptr(dev)), "hpb_normalize_T")
+    return out.reshape(shape)
+
+
+def pose_update(ctx: Context, TCO, K_crop, pose_outputs, tCR=None, variant: int = _capi.POSE_MEGAPOSE) -> torch.Tensor:
+    dev = ctx.device
+    TCO = _f32(TCO, dev).reshape(-1, 16)
+    b = TCO.shape[0]
+    K_crop = _f32(K_crop, dev).reshape(-1, 9)
+    width = 7 if variant == _capi.POSE_COSYPOSE_QUAT else 9
+    o = _f32(pose_outputs, dev)
+    assert o.shape == (b, width), f"pose outputs must be [b,{width}]"
+    t = None if tCR is None else _f32(tCR, dev).reshape(b, 3)
+    out = torch.empty_like(TCO)
+    ctx.check(ctx.lib.hpb_pose_update(ctx.handle, ptr(TCO), ptr(K_crop), ptr(o), ptr(t), b, variant, ptr(out), stream_ptr(dev)), "hpb_pose_update")
+    return out.reshape(b, 4, 4)
+
+
+def tco_init(ctx: Context, variant: int, boxes, K, points=None, obj_ids=None, R=None, z_mean: float = 1.0) -> torch.Tensor:
+    dev = ctx.device
+    boxes = _f32(boxes, dev)
+    assert boxes.dim() == 2 and boxes.shape[-1] == 4
+    b = boxes.shape[0]
+    K = _f32(K, dev).reshape(-1, 9)
+    pts = None if points is None else _f32(points, dev)
+    ids = None if obj_ids is None else _i32(obj_ids, dev)
+    Rm = None if R is None else _f32(R, dev).reshape(-1, 9)
+    out = torch.empty((b, 16), dtype=torch.float32, device=dev)
+    n_obj, n_pts = (pts.shape[0], pts.shape[1]) if pts is not None else (0, 0)
+    rc = ctx.lib.hpb_tco_init(ctx.handle, variant, ptr(boxes), ptr(pts), n_obj, n_pts, ptr(ids), ptr(K), ptr(Rm), float(z_mean), b, ptr(out), stream_ptr(dev))
+    ctx.check(rc, "hpb_tco_init")
+    return out.reshape(b, 4, 4)
+
+
+def multiview(ctx: Context, TCO, tCR, multiview_type: str, n_views: int, remove_TCO_rendering: bool = False) -> torch.Tensor:
+    dev = ctx.device
+    TCO = _f32(TCO, dev).reshape(-1, 16)
+    b = TCO.shape[0]
+    tCR = _f32(tCR, dev).reshape(b, 3)
+    if n_views > 1 and multiview_type not in _capi.MV_TYPES:
+        raise ValueError(multiview_type)
+    mv = _capi.MV_TYPES.get(multiview_type, 0)
+    out = torch.empty((b, n_views, 4, 4), dtype=torch.float32, device=dev)
+    rc = ctx.lib.hpb_multiview(ctx.handle, ptr(TCO), ptr(tCR), b, mv, n_views, int(remove_TCO_rendering), ptr(out), stream_ptr(dev))
+    ctx.check(rc, "hpb_multiview")
+    return out
+
+
+def normalize_depth_(ctx: Context, x: torch.Tensor, channels: Sequence[int], tCR, kind: str) -> torch.Tensor:
+    """In place on x [b,C,h,w] float32 contiguous: normalises the listed depth channels by tCR_z."""
+    if kind not in _capi.DEPTH_NORM:
+        raise ValueError(f"Unknown depth_normalization_type = {kind}")
+    if kind == "none" or len(channels) == 0:
+        return x
+    dev = ctx.device
+    assert x.is_contiguous() and x.dtype == torch.float32
+    b, C, h, w = x.shape
+    tCR = _f32(tCR, dev).reshape(b, 3)
+    ch = (ctypes.c_int32 * len(channels))(*[int(c) for c in channels])
+    rc = ctx.lib.hpb_normalize_depth(ctx.handle, ptr(x), x.stride(0), ctypes.addressof(ch), len(channels), ptr(tCR), b, h, w, _capi.DEPTH_NORM[kind], stream_ptr(dev))
+    ctx.check(rc, "hpb_normalize_depth")
+    return x
+
+
+# ------------------------------------------------------------------------------------------------
+# top-K
+# ------------------------------------------------------------------------------------------------
+def topk_segmented(ctx: Context, scores, group_ids, n_groups: int, K: int) -> torch.Tensor:
+    """Row indices (int64, on device) kept by filter_top_pose_estimates, in global descending score order.
+    The single host sync is reading the survivor count, which sizes the result."""
+    dev = ctx.device
+    s = _f32(scores, dev).reshape(-1)
+    g = _i32(group_ids, dev).reshape(-1)
+    n = s.numel()
+    assert g.numel() == n
+    cap = max(1, min(n, max(0, n_groups) * max(0, K)))
+    out = torch.empty((cap,), dtype=torch.int64, device=dev)
+    cnt = torch.zeros((1,), dtype=torch.int32, device=dev)
+    rc = ctx.lib.hpb_topk_segmented(ctx.handle, ptr(s), ptr(g), n, n_groups, K, ptr(out), ptr(cnt), stream_ptr(dev))
+    ctx.check(rc, "hpb_topk_segmented")
+    return out[: int(cnt.item())]

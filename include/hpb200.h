@@ -1,0 +1,181 @@
+/*
+ * hpb200.h -- C ABI of libhpb200.so: the B200-native (sm_100a) MegaPose / CosyPose
+ * render-and-compare hot path (batched rasteriser, perspective crop, image-space pose update,
+ * segmented top-K) behind happypose's PosePredictor / PoseEstimator / Panda3dBatchRenderer API.
+ *
+ * Conventions
+ *   - every entry point returns 0 on success and a negative HPB_E* code on failure;
+ *     hpb_last_error() returns a thread-local, NUL-terminated description of the last failure.
+ *   - pointers named *_dev are DEVICE pointers on the context's device, *_host are host pointers.
+ *   - matrices are row-major float32: TCO = 16 floats (4x4), K = 9 floats (3x3).
+ *   - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream).  Nothing
+ *     synchronises the host unless stated; work is ordered on `stream`.
+ *   - images are planar CHW float32 with a caller-chosen batch stride (in elements), so a caller can
+ *     have the kernels write straight into a slice of a larger [b, C_total, h, w] network input.
+ *
+ * Reference interfaces replaced (paths relative to the happypose repo root):
+ *   hpb_render            happypose/toolbox/renderer/panda3d_batch_renderer.py:194-286 (render) with
+ *                         :144-192 (make_scene_data), :62-125 (worker_loop) and
+ *                         panda3d_scene_renderer.py:320-390 (render_scene)
+ *   hpb_mesh_upload       panda3d_scene_renderer.py:206-219 (get_object_node: load, scale, hpr)
+ *   hpb_crop              happypose/pose_estimators/megapose/models/pose_rigid.py:199-277 (crop_inputs):
+ *                         toolbox/lib3d/camera_geometry.py:40-67,70-122 and
+ *                         toolbox/lib3d/cropping.py:27-75,113-152,155-197 (roi_align, sampling_ratio 4)
+ *   hpb_crop_boxes        pose_rigid.py:279-337 (compute_crops_multiview, return_crops=False)
+ *   hpb_normalize_T       toolbox/lib3d/transform_ops.py:107-120 + rotations.py:22-36
+ *   hpb_pose_update       pose_rigid.py:339-350 -> toolbox/lib3d/cosypose_ops.py:34-62;
+ *                         cosypose/lib3d/cosypose_ops.py:18-42 (apply_imagespace_predictions)
+ *   hpb_tco_init          toolbox/lib3d/cosypose_ops.py:159-181,184-238,241-283
+ *   hpb_multiview         toolbox/lib3d/multiview.py:28-92,166-251
+ *   hpb_topk_segmented    toolbox/utils/tensor_collection.py:201-230 (filter_top_pose_estimates)
+ *   hpb_normalize_depth   pose_rigid.py:455-544
+ */
+#ifndef HPB200_H
+#define HPB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HPB_VERSION 100
+
+/* error codes */
+#define HPB_OK 0
+#define HPB_EINVAL (-1)  /* bad argument (shape, NULL, range)            */
+#define HPB_ECUDA (-2)   /* a CUDA runtime call failed                    */
+#define HPB_ENOMEM (-3)  /* host or device allocation failed              */
+#define HPB_ENOTFOUND (-4) /* unknown mesh id                             */
+
+/* hpb_render output selection (rgb is always produced by the reference; here it is a flag too) */
+#define HPB_RENDER_RGB 1u
+#define HPB_RENDER_NORMALS 2u
+#define HPB_RENDER_DEPTH 4u
+#define HPB_RENDER_MASK 8u
+
+/* hpb_pose_update variants */
+#define HPB_POSE_MEGAPOSE 0      /* pose_update_with_reference_point, 9-D output (6-D rot + vxvyvz) */
+#define HPB_POSE_COSYPOSE_6D 1   /* apply_imagespace_predictions, 9-D output                        */
+#define HPB_POSE_COSYPOSE_QUAT 2 /* apply_imagespace_predictions, 7-D output (xyzw quaternion)       */
+
+/* hpb_tco_init variants */
+#define HPB_TCO_INIT_AUTODEPTH_WITH_R 0 /* TCO_init_from_boxes_autodepth_with_R (MegaPose coarse) */
+#define HPB_TCO_INIT_ZUP_AUTODEPTH 1    /* TCO_init_from_boxes_zup_autodepth (CosyPose)           */
+#define HPB_TCO_INIT_FROM_BOXES 2       /* TCO_init_from_boxes(z_range) (CosyPose)                */
+
+/* hpb_normalize_depth kinds (PosePredictor.depth_normalization_type) */
+#define HPB_DEPTH_NORM_NONE 0
+#define HPB_DEPTH_NORM_TCR_SCALE 1
+#define HPB_DEPTH_NORM_TCR_SCALE_CLAMP_CENTER 2
+#define HPB_DEPTH_NORM_TCR_CENTER_CLAMP 3
+
+/* hpb_multiview types (PosePredictor.multiview_type) */
+#define HPB_MV_TCO_FRONT_1VIEW 0
+#define HPB_MV_TCO_FRONT_3VIEWS 1
+#define HPB_MV_SPHERE_26VIEWS 2
+
+typedef struct hpb_ctx hpb_ctx;
+
+int hpb_version(void);
+const char *hpb_last_error(void);
+
+/* One context per (process, device).  Owns mesh/texture device buffers and the rasteriser workspace. */
+int hpb_create(int device, hpb_ctx **out);
+int hpb_destroy(hpb_ctx *ctx);
+
+/* Number of kernels this library has launched since the context was created (bench.py gpu_launches). */
+int64_t hpb_launch_count(const hpb_ctx *ctx);
+
+/*
+ * Upload one mesh (HOST pointers; synchronous, not on the hot path).
+ *   verts_xyz  [n_verts,3] vertex positions already in METRES and with any ypr offset applied
+ *   normals    [n_verts,3] unit normals, or NULL (area-weighted smooth normals are generated)
+ *   uv         [n_verts,2] texture coordinates (v up, GL convention), or NULL
+ *   vcolor     [n_verts,4] RGBA8 vertex colours, or NULL
+ *   faces      [n_faces,3] int32 vertex indices (triangles only)
+ *   tex        [tex_h,tex_w,tex_c] uint8 texture (tex_c = 3 or 4), or NULL; a box-filter mip chain is
+ *              built on the device
+ * Returns the mesh id in *mesh_id (dense, starting at 0).
+ */
+int hpb_mesh_upload(hpb_ctx *ctx, const float *verts_xyz, const float *normals, const float *uv,
+                    const uint8_t *vcolor, int64_t n_verts, const int32_t *faces, int64_t n_faces,
+                    const uint8_t *tex, int tex_h, int tex_w, int tex_c, int32_t *mesh_id);
+int hpb_mesh_count(const hpb_ctx *ctx);
+/* Copies the mip level `level` (RGBA8, tex_w*tex_h*4 bytes) back to the host; for tests. */
+int hpb_mesh_get_mip(hpb_ctx *ctx, int32_t mesh_id, int level, uint8_t *out_host, int *w, int *h, int *levels);
+
+/*
+ * Batched rasteriser: renders b single-object scenes in ONE launch.
+ *   mesh_ids_dev [b] int32, TCO_dev [b,16], K_dev [b,9] float32 (device)
+ *   ambient_dev  [b,3] summed ambient light colour per scene, or NULL (= 1,1,1)
+ *   flags        HPB_RENDER_* ; outputs not selected may be NULL
+ *   rgb/normals  [b,3,h,w] float32 in {k/255};  depth [b,1,h,w] float32 metres (0 = background);
+ *   mask         [b,1,h,w] uint8 0/1.   *_bstride = elements between consecutive scenes.
+ * A non-finite TCO or K yields all-zero images for that scene (panda3d_batch_renderer.py:81-111).
+ */
+int hpb_render(hpb_ctx *ctx, const int32_t *mesh_ids_dev, const float *TCO_dev, const float *K_dev,
+               const float *ambient_dev, int b, int h, int w, float z_near, float z_far, uint32_t flags,
+               float *rgb_dev, int64_t rgb_bstride, float *normals_dev, int64_t normals_bstride,
+               float *depth_dev, int64_t depth_bstride, uint8_t *mask_dev, int64_t mask_bstride,
+               void *stream);
+
+/*
+ * Perspective crop + resize of the observed frame(s) (crop_inputs).
+ *   images_dev [n_im,C,H,W] float32 (C = 3 or 4; channel 3 = depth), im_ids_dev [b] int32 selects the
+ *   frame of each row (replaces the reference's images[batch_im_ids] expansion, pose_estimator.py:390)
+ *   points_dev [n_obj,n_pts,3] float32 point sets (mesh_db.select(labels).sample_points(2000)),
+ *   obj_ids_dev [b] int32 row of points_dev per hypothesis
+ *   K_dev [b,9], TCO_dev [b,16], tCR_dev [b,3]
+ *   outputs: crops_dev [b,C,h,w] (batch stride crops_bstride elements), K_crop_dev [b,9],
+ *            boxes_rend_dev [b,4], boxes_crop_dev [b,4]  (x1,y1,x2,y2)
+ */
+int hpb_crop(hpb_ctx *ctx, const float *images_dev, int n_im, int C, int H, int W, const int32_t *im_ids_dev,
+             const float *points_dev, int n_obj, int n_pts, const int32_t *obj_ids_dev, const float *K_dev,
+             const float *TCO_dev, const float *tCR_dev, int b, int h, int w, float lamb, float *crops_dev,
+             int64_t crops_bstride, float *K_crop_dev, float *boxes_rend_dev, float *boxes_crop_dev,
+             void *stream);
+
+/* Boxes and K_crop only (compute_crops_multiview: return_crops=False, 200 points). H,W = source frame size. */
+int hpb_crop_boxes(hpb_ctx *ctx, int H, int W, const float *points_dev, int n_obj, int n_pts,
+                   const int32_t *obj_ids_dev, const float *K_dev, const float *TCO_dev, const float *tCR_dev,
+                   int b, int h, int w, float lamb, float *K_crop_dev, float *boxes_rend_dev,
+                   float *boxes_crop_dev, void *stream);
+
+/* T -> normalize_T(T): Gram-Schmidt on columns 0,1 of R, translation kept, last row (0,0,0,1). In place allowed. */
+int hpb_normalize_T(hpb_ctx *ctx, const float *T_dev, int b, float *T_out_dev, void *stream);
+
+/* Image-space pose update.  out_dev [b,9] (variants 0,1) or [b,7] (variant 2); tCR_dev [b,3] is only read by
+ * variant 0.  TCO_out_dev may alias TCO_dev. */
+int hpb_pose_update(hpb_ctx *ctx, const float *TCO_dev, const float *K_crop_dev, const float *out_dev,
+                    const float *tCR_dev, int b, int variant, float *TCO_out_dev, void *stream);
+
+/* Initial poses from 2-D boxes.  boxes_dev [b,4]; points_dev [n_obj,n_pts,3] + obj_ids_dev [b] (all mesh points,
+ * variants 0,1); K_dev [b,9]; R_dev [b,9] (variant 0); z_mean (variant 2). */
+int hpb_tco_init(hpb_ctx *ctx, int variant, const float *boxes_dev, const float *points_dev, int n_obj, int n_pts,
+                 const int32_t *obj_ids_dev, const float *K_dev, const float *R_dev, float z_mean, int b,
+                 float *TCO_out_dev, void *stream);
+
+/* Extra refiner viewpoints: TCV_O_dev [b,V,16] with V = n_views; view 0 = TCO unless remove_tco_rendering. */
+int hpb_multiview(hpb_ctx *ctx, const float *TCO_dev, const float *tCR_dev, int b, int mv_type, int n_views,
+                  int remove_tco_rendering, float *TCV_O_dev, void *stream);
+
+/* depth_out = normalize_depth(depth, tCR_z) on `n_planes` [h*w] planes per row; plane p of row n lives at
+ * depth_dev + n*bstride + plane_offsets_host[p]*h*w (host array of channel indices). In place. */
+int hpb_normalize_depth(hpb_ctx *ctx, float *depth_dev, int64_t bstride, const int32_t *plane_channels_host,
+                        int n_planes, const float *tCR_dev, int b, int h, int w, int kind, void *stream);
+
+/*
+ * Segmented top-K (filter_top_pose_estimates): keeps, for every group, the K rows with the largest score and
+ * returns the surviving row indices in GLOBAL descending-score order (groups interleaved), exactly the order of
+ * df.sort_values(field, ascending=False).groupby(cols).head(K).index.  Ties: lowest row index first; NaN last.
+ *   scores_dev [n] float32, group_ids_dev [n] int32 in [0,n_groups)
+ *   out_idx_dev [min(n, n_groups*K)] int64, out_count_dev [1] int32 (device)
+ */
+int hpb_topk_segmented(hpb_ctx *ctx, const float *scores_dev, const int32_t *group_ids_dev, int n, int n_groups,
+                       int K, int64_t *out_idx_dev, int32_t *out_count_dev, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HPB200_H */

@@ -1,0 +1,392 @@
+"""GPU parity tests proper: every kernel called through the C ABI (happypose_b200.ops -> libhpb200.so) and compared
+with the CPU oracle on the same seeded inputs, plus the golden vectors produced by the real reference functions."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import np_oracle as O
+from oracle import raster as oraster
+from tests.scenes import icosphere, random_crop_scene, random_rotations, reference_test_scene
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from happypose_b200._capi import Context
+
+    return Context.get("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def can(ctx, can_mesh_arrays):
+    from happypose_b200 import ops
+
+    d = can_mesh_arrays
+    om = oraster.OracleMesh(d["verts"], d["faces"], d["normals"], d["uv"], texture=d["texture"], scale=0.001)
+    mid = ops.mesh_upload(ctx, om.pos, d["faces"], d["normals"], d["uv"], texture=d["texture"])
+    return om, mid
+
+
+def _render_both(ctx, om, mid, T, K, res, ambient=None, **kw):
+    from happypose_b200 import ops
+
+    b = len(T)
+    ref = oraster.render([om], [0] * b, T, K, res, ambient=ambient, render_normals=True, render_depth=True, render_binary_mask=True, n_threads=8, **kw)
+    rgb, nrm, dep, msk = ops.render(ctx, torch.full((b,), mid), torch.as_tensor(T), torch.as_tensor(K), res,
+                                    ambient=None if ambient is None else torch.as_tensor(ambient),
+                                    render_normals=True, render_depth=True, render_binary_mask=True, **kw)
+    torch.cuda.synchronize()
+    return ref, (rgb.cpu().numpy(), nrm.cpu().numpy(), dep.cpu().numpy(), msk.cpu().numpy())
+
+
+def _check_render_parity(ref, got, name=""):
+    rgb, nrm, dep, msk = got
+    # mask / coverage: bit-exact is expected (same integer edge functions); BASELINE bar: <= 0.5 % silhouette mismatches
+    mism = (msk != ref["mask"]).mean()
+    assert mism <= 0.005, f"{name}: mask mismatch {mism}"
+    both = msk & ref["mask"]
+    rel = np.abs(dep - ref["depth"])[both] / ref["depth"][both]
+    assert rel.size > 0
+    # BASELINE bar: depth within 1e-4 relative on interior pixels
+    assert (rel > 1e-4).mean() <= 0.005, f"{name}: depth rel err max {rel.max()}"
+    # colour / normals: 8-bit values; allow one quantisation step on <= 0.5 % of the pixels
+    for a, r, tag in ((rgb, ref["rgb"], "rgb"), (nrm, ref["normals"], "normals")):
+        d = np.abs(a - r) * 255
+        assert (d > 0.5).mean() <= 0.005, f"{name}: {tag} differs on {(d > 0.5).mean():.4%} of values (max {d.max():.1f}/255)"
+    return mism, rel.max()
+
+
+def test_mip_chain_matches_oracle(ctx, can):
+    from happypose_b200 import ops
+
+    om, mid = can
+    for lvl in range(len(om.tex_w)):
+        got = ops.mesh_get_mip(ctx, mid, lvl)
+        w, h, off = int(om.tex_w[lvl]), int(om.tex_h[lvl]), int(om.tex_off[lvl])
+        ref = om.tex[off:off + w * h].reshape(h, w, 4)
+        assert got.shape == ref.shape
+        assert (got == ref).all(), f"mip level {lvl} differs"
+
+
+def test_render_reference_scene_bit_exact(ctx, can):
+    """The reference's own renderer test scene (tests/test_batch_renderer_panda3d.py:43-91), f64 TCO / K inputs."""
+    om, mid = can
+    T, K, res = reference_test_scene()
+    ref, got = _render_both(ctx, om, mid, np.stack([T] * 4), np.stack([K] * 4), res)
+    rgb, nrm, dep, msk = got
+    assert rgb.shape == (4, 3, 480, 640) and dep.shape == (4, 1, 480, 640) and msk.dtype == bool
+    assert (msk == ref["mask"]).all()
+    assert (dep == ref["depth"]).all(), "depth must be bit-identical to the oracle"
+    assert (nrm == ref["normals"]).all()
+    assert (rgb == ref["rgb"]).all()
+    for a in got:
+        assert (a[0] == a[1]).all() and (a[0] == a[3]).all()
+    assert rgb[0, :, 0, 0].max() == 0 and rgb[0, :, 240, 320].max() > 0
+    assert dep[0, 0, 0, 0] == 0 and 0 < dep[0, 0, 240, 320] < 0.3
+    assert not msk[0, 0, 0, 0] and msk[0, 0, 240, 320]
+
+
+def test_render_random_poses_parity(ctx, can):
+    om, mid = can
+    rs = np.random.RandomState(7)
+    T, K = random_crop_scene(rs, 24)
+    ref, got = _render_both(ctx, om, mid, T, K, (240, 320), ambient=rs.uniform(0.7, 1.0, (24, 1)).repeat(3, 1))
+    mism, relmax = _check_render_parity(ref, got, "random")
+    assert (got[3] == ref["mask"]).all() and (got[2] == ref["depth"]).all()  # stronger than the bar: bit-exact
+    assert got[3].mean() > 0.1
+
+
+def test_render_more_scenes_than_sms(ctx, can):
+    """Persistent CTAs loop over scenes: 320 scenes > 148 SMs; the visibility buffer must be re-armed correctly."""
+    om, mid = can
+    rs = np.random.RandomState(8)
+    T, K = random_crop_scene(rs, 320, res=(60, 80))
+    ref, got = _render_both(ctx, om, mid, T, K, (60, 80))
+    assert (got[3] == ref["mask"]).all() and (got[2] == ref["depth"]).all()
+    _check_render_parity(ref, got, "many")
+
+
+def test_render_edge_cases(ctx, can):
+    """non-finite pose -> zero images; object behind / across the near plane; far rule; off-screen; empty batch."""
+    from happypose_b200 import ops
+
+    om, mid = can
+    T0, K0, _ = reference_test_scene()
+    K0 = K0.copy()
+    K0[:2] /= 4
+    T = np.stack([T0] * 7)
+    T[1, 0, 3] = np.nan
+    T[2, 2, 3] = -0.5    # behind the camera
+    T[3, 2, 3] = 0.12    # straddles the near plane (triangles with a vertex closer than z_near are dropped)
+    T[4, 2, 3] = 9.6     # d > 0.999: colour drawn, depth/mask 0
+    T[5, 2, 3] = 12.0    # beyond far: clipped
+    T[6, 0, 3] = 5.0     # off screen
+    K = np.stack([K0] * 7)
+    K[4, 0, 0] = K[4, 1, 1] = K[5, 0, 0] = K[5, 1, 1] = 3000
+    ref, got = _render_both(ctx, om, mid, T, K, (120, 160))
+    rgb, nrm, dep, msk = got
+    assert (msk == ref["mask"]).all() and (dep == ref["depth"]).all()
+    assert (rgb == ref["rgb"]).all() and (nrm == ref["normals"]).all()
+    assert rgb[1].max() == 0 and dep[1].max() == 0 and nrm[1].max() == 0
+    assert rgb[2].max() == 0 and rgb[5].max() == 0 and rgb[6].max() == 0
+    assert rgb[4].max() > 0 and dep[4].max() == 0 and not msk[4].any()
+    Kn = K.copy()
+    Kn[0, 1, 1] = np.inf
+    _, got2 = _render_both(ctx, om, mid, T[:1], Kn[:1], (120, 160))
+    assert got2[0].max() == 0
+    out = ops.render(ctx, torch.zeros(0, dtype=torch.int32), torch.zeros(0, 4, 4), torch.zeros(0, 3, 3), (120, 160), render_depth=True)
+    assert out[0].shape == (0, 3, 120, 160) and out[2].shape == (0, 1, 120, 160)
+
+
+def test_render_untextured_and_two_meshes(ctx, can):
+    from happypose_b200 import ops
+
+    om, mid = can
+    v, f, n = icosphere(3, 0.05)
+    sph = oraster.OracleMesh(v, f, None)  # normals generated (area-weighted) on both sides
+    sid = ops.mesh_upload(ctx, sph.pos, f)
+    colors = (np.random.RandomState(0).rand(len(v), 3) * 255).astype(np.uint8)
+    sphc = oraster.OracleMesh(v, f, n, vcolor=colors)
+    cid = ops.mesh_upload(ctx, sphc.pos, f, n, vcolor=colors)
+    rs = np.random.RandomState(9)
+    T, K = random_crop_scene(rs, 6, res=(120, 160))
+    ids_o = [0, 1, 2, 1, 0, 2]
+    ids_g = torch.tensor([mid, sid, cid, sid, mid, cid])
+    ref = oraster.render([om, sph, sphc], ids_o, T, K, (120, 160), render_normals=True, render_depth=True, render_binary_mask=True)
+    rgb, nrm, dep, msk = ops.render(ctx, ids_g, torch.as_tensor(T), torch.as_tensor(K), (120, 160), render_normals=True, render_depth=True, render_binary_mask=True)
+    got = (rgb.cpu().numpy(), nrm.cpu().numpy(), dep.cpu().numpy(), msk.cpu().numpy())
+    assert (got[3] == ref["mask"]).all() and (got[2] == ref["depth"]).all()
+    _check_render_parity(ref, got, "mixed meshes")
+    assert (got[0][1][:, got[3][1, 0]] == 1.0).all()  # untextured, uncoloured mesh is white under ambient 1
+
+
+def test_render_big_triangles_int64_path(ctx):
+    """A 2-triangle quad filling the screen exercises the 64-bit edge-function path and the guard band."""
+    from happypose_b200 import ops
+
+    v = np.array([[-1, -1, 0], [1, -1, 0], [1, 1, 0], [-1, 1, 0]], np.float32)
+    f = np.array([[0, 1, 2], [0, 2, 3]], np.int32)
+    n = np.tile(np.array([[0, 0, -1]], np.float32), (4, 1))
+    om = oraster.OracleMesh(v, f, n)
+    mid = ops.mesh_upload(ctx, om.pos, f, n)
+    T = np.tile(np.eye(4, dtype=np.float32), (3, 1, 1))
+    T[:, 2, 3] = [0.5, 1.0, 0.2]
+    T[1, :3, :3] = random_rotations(np.random.RandomState(3), 1)[0] @ np.diag([1, 1, 1])
+    T[1, 2, 3] = 3.0
+    K = np.tile(np.array([[300, 0, 160.3], [0, 300, 120.1], [0, 0, 1]], np.float32), (3, 1, 1))
+    ref = oraster.render([om], [0, 0, 0], T, K, (240, 320), render_normals=True, render_depth=True, render_binary_mask=True)
+    rgb, nrm, dep, msk = ops.render(ctx, torch.full((3,), mid), torch.as_tensor(T), torch.as_tensor(K), (240, 320), render_normals=True, render_depth=True, render_binary_mask=True)
+    assert (msk.cpu().numpy() == ref["mask"]).all() and (dep.cpu().numpy() == ref["depth"]).all()
+    assert msk[0].all()  # the quad covers the whole frame at z = 0.5
+    assert (nrm.cpu().numpy() == ref["normals"]).all() and (rgb.cpu().numpy() == ref["rgb"]).all()
+
+
+def test_render_into_network_input_slice(ctx, can):
+    from happypose_b200 import ops
+
+    om, mid = can
+    rs = np.random.RandomState(10)
+    T, K = random_crop_scene(rs, 5, res=(120, 160))
+    x = torch.full((5, 9, 120, 160), -7.0, device="cuda")
+    rgb, nrm, _, _ = ops.render(ctx, torch.full((5,), mid), torch.as_tensor(T), torch.as_tensor(K), (120, 160), render_normals=True, out=x, out_channel_offset=3)
+    rgb2, nrm2, _, _ = ops.render(ctx, torch.full((5,), mid), torch.as_tensor(T), torch.as_tensor(K), (120, 160), render_normals=True)
+    assert (x[:, :3] == -7.0).all()
+    assert torch.equal(x[:, 3:6], rgb2) and torch.equal(x[:, 6:9], nrm2)
+    assert rgb.data_ptr() == x[:, 3:6].data_ptr()
+
+
+# ------------------------------------------------------------------------------------------------------------
+def _mesh_points(can_mesh_arrays):
+    return (can_mesh_arrays["verts"].astype(np.float64) * 0.001).astype(np.float32)
+
+
+def test_crop_matches_reference_golden_small(ctx, golden, can_mesh_arrays):
+    from happypose_b200 import ops
+
+    g = golden("ref_crop_small.npz")
+    pts = _mesh_points(can_mesh_arrays)[g["point_ids"]]
+    b = len(g["TCO"])
+    for C, tag in ((4, "rgbd"), (3, "rgb")):
+        crops, K_crop, boxes_rend, boxes_crop = ops.crop(
+            ctx, torch.as_tensor(g["images"][:, :C].copy()), torch.as_tensor(g["im_ids"]), torch.as_tensor(pts[None]),
+            torch.zeros(b, dtype=torch.int32), g["K"], g["TCO"], g["tCR"], (60, 80))
+        np.testing.assert_allclose(boxes_rend.cpu().numpy(), g["boxes_rend"], atol=2e-3)
+        np.testing.assert_allclose(boxes_crop.cpu().numpy(), g["boxes_crop"], atol=5e-3)
+        np.testing.assert_allclose(K_crop.cpu().numpy(), g["K_crop"], rtol=2e-5, atol=2e-3)
+        ref = g[f"crops_{tag}"]
+        got = crops.cpu().numpy()
+        np.testing.assert_allclose(got[:, :3], ref[:, :3], atol=1e-3)  # BASELINE bar: crops within 1e-3 absolute
+        if C == 4:
+            assert (np.abs(got[:, 3] - ref[:, 3]) > 1e-3).mean() < 2e-3  # validity threshold flips (cropping.py:191-193)
+
+
+def test_crop_full_size_matches_reference_golden(ctx, golden, can_mesh_arrays):
+    from happypose_b200 import ops
+
+    g = golden("ref_crop_full.npz")
+    pts = _mesh_points(can_mesh_arrays)[O.sample_point_ids(9951, 2000)]
+    b = len(g["TCO"])
+    image = np.random.RandomState(int(g["image_seed"])).rand(1, 3, 480, 640).astype(np.float32)
+    crops, K_crop, boxes_rend, boxes_crop = ops.crop(
+        ctx, torch.as_tensor(image), torch.zeros(b, dtype=torch.int32), torch.as_tensor(pts[None]), torch.zeros(b, dtype=torch.int32),
+        g["K"], g["TCO"], g["tCR"], (240, 320))
+    np.testing.assert_allclose(boxes_crop.cpu().numpy(), g["boxes_crop"], atol=1e-2)
+    np.testing.assert_allclose(K_crop.cpu().numpy(), g["K_crop"], rtol=3e-5, atol=5e-3)
+    got = crops.cpu().numpy()
+    np.testing.assert_allclose(got[:, :, ::5, ::5], g["crops_sub"], atol=1e-3)
+    np.testing.assert_allclose(got.astype(np.float64).sum((1, 2, 3)), g["crops_sum"], rtol=1e-5)
+
+
+def test_crop_vs_oracle_downsampling_and_out_of_frame(ctx, can_mesh_arrays):
+    """Boxes much larger than the frame (generic roi_align path) and boxes hanging off the frame (zero padding rule)."""
+    from happypose_b200 import ops
+
+    rs = np.random.RandomState(11)
+    pts = _mesh_points(can_mesh_arrays)[O.sample_point_ids(9951, 2000)]
+    b = 6
+    images = rs.rand(2, 4, 96, 128).astype(np.float32)
+    images[:, 3] *= rs.rand(2, 96, 128) > 0.2
+    K = np.tile(np.array([[120.0, 0, 64], [0, 120, 48], [0, 0, 1]], np.float32), (b, 1, 1))
+    TCO = np.tile(np.eye(4, dtype=np.float32), (b, 1, 1))
+    TCO[:, :3, :3] = random_rotations(rs, b)
+    TCO[:, :3, 3] = [[0, 0, 0.15], [0.3, 0.2, 0.5], [-0.4, 0.0, 0.6], [0, 0, 0.11], [0.0, -0.35, 0.7], [0.01, 0.01, 2.5]]
+    tCR = TCO[:, :3, 3].copy()
+    im_ids = np.array([0, 1, 0, 1, 1, 0])
+    points = np.tile(pts[None], (b, 1, 1))
+    ref_crops, ref_K, ref_br, ref_bc = O.crop_inputs(images, K, TCO, tCR, points, (48, 64), im_ids=im_ids)
+    crops, K_crop, boxes_rend, boxes_crop = ops.crop(ctx, torch.as_tensor(images), torch.as_tensor(im_ids), torch.as_tensor(pts[None]),
+                                                     torch.zeros(b, dtype=torch.int32), K, TCO, tCR, (48, 64))
+    np.testing.assert_allclose(boxes_crop.cpu().numpy(), ref_bc, rtol=1e-5, atol=5e-3)
+    np.testing.assert_allclose(K_crop.cpu().numpy(), ref_K, rtol=3e-5, atol=5e-3)
+    # resample with the oracle on the GPU's own boxes so that only the roi_align arithmetic is compared
+    rois = np.concatenate([im_ids[:, None].astype(np.float32), boxes_crop.cpu().numpy()], 1)
+    ref2 = O.crop_images(images, rois, (48, 64), 4)
+    got = crops.cpu().numpy()
+    np.testing.assert_allclose(got[:, :3], ref2[:, :3], atol=2e-5)
+    assert (np.abs(got[:, 3] - ref2[:, 3]) > 1e-3).mean() < 2e-3
+
+
+def test_crop_boxes_multiview_200_points(ctx, can_mesh_arrays):
+    from happypose_b200 import ops
+
+    rs = np.random.RandomState(12)
+    pts = _mesh_points(can_mesh_arrays)[O.sample_point_ids(9951, 200)]
+    T, K = random_crop_scene(rs, 16, res=(480, 640))
+    tCR = T[:, :3, 3].copy()
+    points = np.tile(pts[None], (16, 1, 1))
+    uv = O.project_points_robust(points, K, T)
+    br = O.boxes_from_uv(uv)
+    bc, _ = O.deepim_crops_robust(np.zeros((1, 3, 480, 640), np.float32), br, K, T, tCR, points, (240, 320), return_crops=False)
+    Kc = O.get_K_crop_resize(K, bc, (480, 640), (240, 320))
+    K_crop, boxes_rend, boxes_crop = ops.crop_boxes(ctx, (480, 640), torch.as_tensor(pts[None]), torch.zeros(16, dtype=torch.int32), K, T, tCR, (240, 320))
+    np.testing.assert_allclose(boxes_rend.cpu().numpy(), br, atol=5e-3)
+    np.testing.assert_allclose(boxes_crop.cpu().numpy(), bc, atol=1e-2)
+    np.testing.assert_allclose(K_crop.cpu().numpy(), Kc, rtol=3e-5, atol=5e-3)
+
+
+# ------------------------------------------------------------------------------------------------------------
+def test_pose_kernels_match_reference_golden(ctx, golden):
+    from happypose_b200 import _capi, ops
+
+    g = golden("ref_pose.npz")
+    Tn = ops.normalize_T(ctx, torch.as_tensor(g["TCO"]))
+    np.testing.assert_allclose(Tn.cpu().numpy(), g["normalize_T"], atol=1e-6)
+    # BASELINE bar: pose updates within 1e-5
+    up = ops.pose_update(ctx, Tn, g["K_crop"], g["out9"], g["tCR"], _capi.POSE_MEGAPOSE)
+    np.testing.assert_allclose(up.cpu().numpy(), g["pose_update_megapose"], atol=1e-5)
+    up = ops.pose_update(ctx, Tn, g["K_crop"], g["out9"], None, _capi.POSE_COSYPOSE_6D)
+    np.testing.assert_allclose(up.cpu().numpy(), g["pose_update_cosypose6d"], atol=1e-5)
+    up = ops.pose_update(ctx, Tn, g["K_crop"], g["out7"], None, _capi.POSE_COSYPOSE_QUAT)
+    np.testing.assert_allclose(up.cpu().numpy(), g["pose_update_cosyposequat"], atol=1e-5)
+    with pytest.raises(ValueError):
+        ops.pose_update(ctx, Tn, g["K_crop"], g["out9"], None, _capi.POSE_MEGAPOSE)  # tCR missing
+
+
+def test_tco_init_matches_reference_golden(ctx, golden, can_mesh_arrays):
+    from happypose_b200 import _capi, ops
+
+    g = golden("ref_pose.npz")
+    pts = torch.as_tensor(_mesh_points(can_mesh_arrays)[None])
+    b = len(g["boxes"])
+    ids = torch.zeros(b, dtype=torch.int32)
+    out = ops.tco_init(ctx, _capi.TCO_INIT_AUTODEPTH_WITH_R, g["boxes"], g["K_init"], pts, ids, g["R_init"])
+    np.testing.assert_allclose(out.cpu().numpy(), g["tco_init_autodepth_with_R"], atol=1e-5)
+    out = ops.tco_init(ctx, _capi.TCO_INIT_ZUP_AUTODEPTH, g["boxes"], g["K_init"], pts, ids)
+    np.testing.assert_allclose(out.cpu().numpy(), g["tco_init_zup_autodepth"], atol=1e-5)
+    out = ops.tco_init(ctx, _capi.TCO_INIT_FROM_BOXES, g["boxes"], g["K_init"], z_mean=1.0)
+    np.testing.assert_allclose(out.cpu().numpy(), g["tco_init_from_boxes"], atol=1e-6)
+
+
+def test_multiview_matches_oracle(ctx):
+    from happypose_b200 import ops
+
+    rs = np.random.RandomState(13)
+    T, _ = random_crop_scene(rs, 32)
+    T[:, :2, 3] += rs.uniform(-0.2, 0.2, (32, 2)).astype(np.float32)
+    T = O.normalize_T(T)
+    tCR = T[:, :3, 3].copy()
+    for mv, nv in (("TCO+front_3views", 4), ("TCO+front_1view", 2), ("sphere_26views", 27)):
+        ref = O.make_TCO_multiview(T, tCR, mv, nv)
+        got = ops.multiview(ctx, torch.as_tensor(T), torch.as_tensor(tCR), mv, nv).cpu().numpy()
+        np.testing.assert_allclose(got, ref, atol=1e-5)
+    got = ops.multiview(ctx, torch.as_tensor(T), torch.as_tensor(tCR), "TCO+front_3views", 3, remove_TCO_rendering=True).cpu().numpy()
+    np.testing.assert_allclose(got, O.make_TCO_multiview(T, tCR, "TCO+front_3views", 3, remove_TCO_rendering=True), atol=1e-5)
+    one = ops.multiview(ctx, torch.as_tensor(T), torch.as_tensor(tCR), "TCO+front_3views", 1).cpu().numpy()
+    assert (one[:, 0] == T).all()
+    bad = T.copy()
+    bad[0, 1, 1] = np.nan
+    got = ops.multiview(ctx, torch.as_tensor(bad), torch.as_tensor(tCR), "TCO+front_3views", 4).cpu().numpy()
+    assert np.isfinite(got[1:]).all()
+
+
+def test_normalize_depth(ctx):
+    from happypose_b200 import ops
+
+    rs = np.random.RandomState(14)
+    x = rs.rand(3, 9, 20, 30).astype(np.float32) * 2
+    tCR = rs.uniform(0.3, 1.0, (3, 3)).astype(np.float32)
+    for kind in ("tCR_scale", "tCR_scale_clamp_center", "tCR_center_clamp", "none"):
+        t = torch.as_tensor(x.copy()).cuda()
+        ops.normalize_depth_(ctx, t, [3, 8], tCR, kind)
+        ref = x.copy()
+        ref[:, [3, 8]] = O.normalize_depth(x[:, [3, 8]], tCR[:, 2], kind)
+        np.testing.assert_allclose(t.cpu().numpy(), ref, atol=1e-6)
+    with pytest.raises(ValueError):
+        ops.normalize_depth_(ctx, torch.zeros(1, 4, 2, 2).cuda(), [3], tCR[:1], "bogus")
+
+
+# ------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["c1", "k5", "multi", "kbig"])
+def test_topk_matches_pandas_golden(ctx, golden, name):
+    from happypose_b200 import ops
+
+    g = golden("ref_topk.npz")
+    groups = g[f"{name}_groups"]
+    idx = ops.topk_segmented(ctx, g[f"{name}_scores"], groups, int(groups.max()) + 1, int(g[f"{name}_K"]))
+    assert idx.dtype == torch.int64
+    assert (idx.cpu().numpy() == g[f"{name}_idx"]).all()  # bit-exact indices
+
+
+def test_topk_large_and_ties(ctx):
+    from happypose_b200 import ops
+
+    rs = np.random.RandomState(15)
+    n_groups, M = 240, 576  # BASELINE config #4: 240 detections x 576 hypotheses
+    scores = rs.randn(n_groups * M).astype(np.float32)
+    scores[rs.randint(0, len(scores), 5000)] = 0.25   # many exact ties
+    scores[rs.randint(0, len(scores), 50)] = np.nan
+    scores[:7] = [0.0, -0.0, np.inf, -np.inf, 0.0, -0.0, np.inf]
+    groups = rs.permutation(np.repeat(np.arange(n_groups), M)).astype(np.int32)  # interleaved, not contiguous
+    for K in (1, 5):
+        idx = ops.topk_segmented(ctx, scores, groups, n_groups, K).cpu().numpy()
+        assert (idx == O.filter_top_k(scores, groups, K)).all()
+    s = np.array([1.0, 3.0, 3.0, 2.0, 3.0, np.nan], np.float32)
+    g = np.array([0, 0, 1, 1, 0, 0], np.int32)
+    assert ops.topk_segmented(ctx, s, g, 2, 2).tolist() == [1, 2, 4, 3]
+    assert ops.topk_segmented(ctx, s, g, 2, 10).tolist() == [1, 2, 4, 3, 0, 5]
+    assert ops.topk_segmented(ctx, s[:0], g[:0], 0, 3).tolist() == []
+    # a group bigger than the rank kernel's shared-memory tile (SO(3) grid 4608)
+    big = rs.randn(4608 * 2).astype(np.float32)
+    gb = np.repeat(np.arange(2), 4608).astype(np.int32)
+    assert (ops.topk_segmented(ctx, big, gb, 2, 7).cpu().numpy() == O.filter_top_k(big, gb, 7)).all()
