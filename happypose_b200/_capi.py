@@ -34,7 +34,7 @@ SIGNATURES = {
     "hpb_mesh_count": (c_int, [c_void_p]),
     "hpb_mesh_get_mip": (c_int, [c_void_p, c_int32, c_int, c_void_p, ctypes.POINTER(c_int), ctypes.POINTER(c_int), ctypes.POINTER(c_int)]),
     "hpb_render": (c_int, [c_void_p] * 5 + [c_int, c_int, c_int, c_float, c_float, c_uint32,
-                           c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p]),
+                           c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int64, c_void_p]),
     "hpb_crop": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p,
                          c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_int64, c_void_p,
                          c_void_p, c_void_p, c_void_p]),

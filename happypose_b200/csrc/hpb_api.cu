@@ -217,9 +217,11 @@ int hpb_mesh_get_mip(hpb_ctx *ctx, int32_t mesh_id, int level, uint8_t *out_host
 int hpb_render(hpb_ctx *ctx, const int32_t *mesh_ids_dev, const float *TCO_dev, const float *K_dev,
                const float *ambient_dev, int b, int h, int w, float z_near, float z_far, uint32_t flags,
                float *rgb_dev, int64_t rgb_bstride, float *normals_dev, int64_t normals_bstride, float *depth_dev,
-               int64_t depth_bstride, uint8_t *mask_dev, int64_t mask_bstride, void *stream) {
+               int64_t depth_bstride, uint8_t *mask_dev, int64_t mask_bstride, int views, int64_t view_stride,
+               void *stream) {
     HPB_REQUIRE(ctx, "NULL ctx");
     HPB_REQUIRE(b >= 0 && h > 0 && w > 0 && (long long)h * w < (1ll << 30), "bad batch / resolution");
+    HPB_REQUIRE(views >= 1 && b % views == 0, "b must be a multiple of views");
     if (b == 0) return HPB_OK;
     HPB_REQUIRE(mesh_ids_dev && TCO_dev && K_dev, "NULL input");
     HPB_REQUIRE(z_near > 0.f && z_far > z_near, "bad near/far");
@@ -232,7 +234,7 @@ int hpb_render(hpb_ctx *ctx, const int32_t *mesh_ids_dev, const float *TCO_dev, 
     HpbDeviceGuard guard(ctx->device);
     return hpb_launch_raster(ctx, mesh_ids_dev, TCO_dev, K_dev, ambient_dev, b, h, w, z_near, z_far, flags, rgb_dev,
                              rgb_bstride, normals_dev, normals_bstride, depth_dev, depth_bstride, mask_dev,
-                             mask_bstride, (cudaStream_t)stream);
+                             mask_bstride, views, view_stride, (cudaStream_t)stream);
 }
 
 int hpb_crop_boxes(hpb_ctx *ctx, int H, int W, const float *points_dev, int n_obj, int n_pts,

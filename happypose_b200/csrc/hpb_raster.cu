@@ -35,6 +35,8 @@ struct RasterParams {
     float *depth;
     uint8_t *mask;
     long long rgb_bs, nrm_bs, depth_bs, mask_bs;
+    int views;            // scene i writes at base + (i / views) * bstride + (i % views) * view_stride
+    long long view_stride;
     unsigned long long *vis;   // [gridDim.x][h*w]
     HpbSVert *vert_scratch;    // [gridDim.x][max_nv] when vertices do not fit in shared memory
     int max_nv;
@@ -279,10 +281,11 @@ __global__ void __launch_bounds__(1024, 1) hpb_raster_kernel(const RasterParams 
         }
 
         // ---------------- phase C: resolve ----------------
-        float *rgb = (p.flags & HPB_RENDER_RGB) ? p.rgb + (size_t)hyp * p.rgb_bs : nullptr;
-        float *nrm = (p.flags & HPB_RENDER_NORMALS) ? p.nrm + (size_t)hyp * p.nrm_bs : nullptr;
-        float *dep = (p.flags & HPB_RENDER_DEPTH) ? p.depth + (size_t)hyp * p.depth_bs : nullptr;
-        uint8_t *msk = (p.flags & HPB_RENDER_MASK) ? p.mask + (size_t)hyp * p.mask_bs : nullptr;
+        const size_t oi = (size_t)(hyp / p.views), ov = (size_t)(hyp % p.views) * p.view_stride;
+        float *rgb = (p.flags & HPB_RENDER_RGB) ? p.rgb + oi * p.rgb_bs + ov : nullptr;
+        float *nrm = (p.flags & HPB_RENDER_NORMALS) ? p.nrm + oi * p.nrm_bs + ov : nullptr;
+        float *dep = (p.flags & HPB_RENDER_DEPTH) ? p.depth + oi * p.depth_bs + ov : nullptr;
+        uint8_t *msk = (p.flags & HPB_RENDER_MASK) ? p.mask + (size_t)hyp * p.mask_bs : nullptr;  // never view-interleaved
         for (int pix = tid; pix < npix; pix += nthr) {
             unsigned long long key = HPB_VIS_EMPTY;
             if (finite) {
@@ -443,7 +446,7 @@ int hpb_launch_tex_expand(const uint8_t *src, int n, int c, uchar4 *dst, cudaStr
 int hpb_launch_raster(hpb_ctx *ctx, const int32_t *mesh_ids, const float *TCO, const float *K, const float *ambient,
                       int b, int h, int w, float z_near, float z_far, uint32_t flags, float *rgb, int64_t rgb_bs,
                       float *nrm, int64_t nrm_bs, float *depth, int64_t depth_bs, uint8_t *mask, int64_t mask_bs,
-                      cudaStream_t stream) {
+                      int views, int64_t view_stride, cudaStream_t stream) {
     if (b == 0) return HPB_OK;
     const int npix = h * w;
     // persistent grid: one CTA per SM (1024 threads, vertices in shared memory), never more CTAs than scenes
@@ -494,6 +497,7 @@ int hpb_launch_raster(hpb_ctx *ctx, const int32_t *mesh_ids, const float *TCO, c
     p.flags = flags;
     p.rgb = rgb; p.nrm = nrm; p.depth = depth; p.mask = mask;
     p.rgb_bs = rgb_bs; p.nrm_bs = nrm_bs; p.depth_bs = depth_bs; p.mask_bs = mask_bs;
+    p.views = views; p.view_stride = view_stride;
     p.vis = ctx->vis;
     p.vert_scratch = ctx->vert_scratch;
     p.max_nv = ctx->max_nv;

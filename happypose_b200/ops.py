@@ -83,12 +83,16 @@ def render(
     z_far: float = 10.0,
     out: Optional[torch.Tensor] = None,
     out_channel_offset: int = 0,
+    views: int = 1,
 ):
     """Renders b scenes.  Returns (rgb, normals, depth, mask) tensors (None when not requested).
 
     If `out` ([b, C_total, h, w] float32, contiguous) is given, rgb / normals / depth are written into consecutive
     channels of `out` starting at `out_channel_offset` (rgb 3, then normals 3, then depth 1) and the returned
     tensors are views of it -- the rasteriser then writes the network input in place (no torch.cat).
+    With views = V > 1 (multi-view refiner), the b = n*V scenes are hypothesis-major and `out` is [n, C_total, h, w]:
+    view v of hypothesis i lands in channels offset + v*C_r ... of out[i] (C_r = channels of one render), i.e. the
+    layout of render_images_multiview (pose_rigid.py:447-452).  The returned tensors are then None.
     """
     dev = ctx.device
     h, w = int(resolution[0]), int(resolution[1])
@@ -101,8 +105,10 @@ def render(
     amb = None if ambient is None else _f32(ambient, dev).reshape(b, 3)
     flags = (1 if render_rgb else 0) | (2 if render_normals else 0) | (4 if render_depth else 0) | (8 if render_binary_mask else 0)
     rgb = nrm = dep = msk = None
+    view_stride = 0
     if out is not None:
-        assert out.is_contiguous() and out.dtype == torch.float32 and out.shape[0] == b and tuple(out.shape[2:]) == (h, w)
+        assert b % views == 0
+        assert out.is_contiguous() and out.dtype == torch.float32 and out.shape[0] == b // views and tuple(out.shape[2:]) == (h, w)
         c, bs = out_channel_offset, out.stride(0)
         if render_rgb:
             rgb = out[:, c:c + 3]; c += 3
@@ -110,9 +116,12 @@ def render(
             nrm = out[:, c:c + 3]; c += 3
         if render_depth:
             dep = out[:, c:c + 1]; c += 1
-        assert c <= out.shape[1]
+        view_stride = (c - out_channel_offset) * h * w
+        assert out_channel_offset + views * (c - out_channel_offset) <= out.shape[1]
         strides = (bs, bs, bs)
     else:
+        assert views == 1, "views > 1 needs an `out` tensor"
+
         if render_rgb:
             rgb = torch.empty((b, 3, h, w), dtype=torch.float32, device=dev)
         if render_normals:
@@ -125,8 +134,11 @@ def render(
     if b > 0:
         rc = ctx.lib.hpb_render(
             ctx.handle, ptr(mesh_ids), ptr(TCO), ptr(K), ptr(amb), b, h, w, z_near, z_far, flags,
-            ptr(rgb), strides[0], ptr(nrm), strides[1], ptr(dep), strides[2], ptr(msk), h * w, stream_ptr(dev))
+            ptr(rgb), strides[0], ptr(nrm), strides[1], ptr(dep), strides[2], ptr(msk), h * w,
+            views, view_stride if views > 1 else 0, stream_ptr(dev))
         ctx.check(rc, "hpb_render")
+    if views > 1:
+        return None, None, None, msk
     return rgb, nrm, dep, msk
 
 

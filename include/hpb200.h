@@ -111,14 +111,19 @@ int hpb_mesh_get_mip(hpb_ctx *ctx, int32_t mesh_id, int level, uint8_t *out_host
  *   ambient_dev  [b,3] summed ambient light colour per scene, or NULL (= 1,1,1)
  *   flags        HPB_RENDER_* ; outputs not selected may be NULL
  *   rgb/normals  [b,3,h,w] float32 in {k/255};  depth [b,1,h,w] float32 metres (0 = background);
- *   mask         [b,1,h,w] uint8 0/1.   *_bstride = elements between consecutive scenes.
+ *   mask         [b,1,h,w] uint8 0/1.
+ *   addressing   scene i writes its planes at  base + (i / views) * bstride + (i % views) * view_stride  (elements).
+ *                views = 1 is the plain batched layout.  views = V with view_stride = C_r*h*w lets the V renders of
+ *                one hypothesis land side by side in the channels of a [b/V, C_in, h, w] network input
+ *                (render_images_multiview's view(bsz, n_views, C, h, w).flatten(1, 2), pose_rigid.py:447-452).
+ *                The mask is never view-interleaved: scene i writes at mask_dev + i * mask_bstride.
  * A non-finite TCO or K yields all-zero images for that scene (panda3d_batch_renderer.py:81-111).
  */
 int hpb_render(hpb_ctx *ctx, const int32_t *mesh_ids_dev, const float *TCO_dev, const float *K_dev,
                const float *ambient_dev, int b, int h, int w, float z_near, float z_far, uint32_t flags,
                float *rgb_dev, int64_t rgb_bstride, float *normals_dev, int64_t normals_bstride,
                float *depth_dev, int64_t depth_bstride, uint8_t *mask_dev, int64_t mask_bstride,
-               void *stream);
+               int views, int64_t view_stride, void *stream);
 
 /*
  * Perspective crop + resize of the observed frame(s) (crop_inputs).
