@@ -1,0 +1,405 @@
+#!/usr/bin/env python
+"""bench.py -- MegaPose poses/sec on BASELINE config #1 (1 object per GPU, 640x480 synthetic frame, 576 coarse hypotheses
++ top-1 + 5 refiner iterations x 4 views + 1 scoring pass, random-init ResNet-34 coarse/refiner in bf16).
+
+    python bench.py --gpus N --steps K --warmup W                 this repo (CUDA kernels behind libhpb200.so)
+    python bench.py --impl reference --gpus N --steps K --warmup W  the reference's CPU path (oracle port) on host cores
+
+One "step" = one PoseEstimator.run_inference_pipeline call = D poses per GPU (D = --dets, default 1).  With N > 1 (one
+process per GPU, torchrun) the N*D detections of the frame form one hypothesis table whose rows are sharded across the
+ranks; the only collective is the all-gather of the coarse / scoring logits (happypose_b200/distributed.py).
+Per-GPU work is fixed as N grows ("weak").  Rank 0 prints ONE JSON line.
+
+Reported (see DESIGN.md "Measurement"):
+  value      poses/s, frame and detections already resident in HBM, CUDA-event timed, max over ranks
+  e2e        same metric through the public API from pinned HOST buffers (H2D of frame/K/boxes and D2H of the final poses
+             inside the timed region)
+  roofline   hpb_raster_kernel (dominant kernel of this library): algorithmic bytes / CUDA-event duration measured
+             live around every launch of the timed region, against MEASURED_PEAKS.json hbm_gbs
+  kernels    the same live figures for every bracketed kernel (rasteriser, crop)
+  hyps       rendered hyps/s (render + crop of 576 hypotheses into the 9-channel network input, no network)
+  cpu_baseline  the CPU oracle pipeline (C rasteriser port + torch-CPU ResNet + torchvision roi_align) on a bounded
+             sample, extrapolated to one pose, on all host cores (N=1, rank 0 only)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+K_BBQ = np.array([[605.95, 0, 319.03], [0, 605.01, 249.68], [0, 0, 1]], np.float32)  # docs/book/megapose/inference.md:33
+BBOX_BBQ = np.array([384, 234, 522, 455], np.float32)                               # docs/book/megapose/inference.md:37
+MESH = os.path.join(ROOT, "tests", "golden", "obj_000001.npz")
+LABEL = "obj_000001"
+M_GRID, N_REFINER_ITERS, N_VIEWS = 576, 5, 4
+H_IM, W_IM, H_R, W_R = 480, 640, 240, 320
+METRIC, UNIT = "megapose_poses_per_sec", "poses/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--dets", type=int, default=1, help="detections (poses) per GPU per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graphs", action="store_true")
+    return ap.parse_args()
+
+
+def config_dict(args, world):
+    return {
+        "workload": "BASELINE configs[0]: MegaPose barbecue-sauce-style example, 1 object per GPU, 640x480 synthetic RGB frame, "
+                    "576 coarse hypotheses + top-1 + 5 refiner iterations x 4 views + 1 scoring pass, random-init ResNet-34 (bf16)",
+        "mesh": "tests/golden/obj_000001.npz (reference tests/data/obj_000001.ply: 9951 verts, 15728 faces, 512^2 texture)",
+        "detections_per_gpu": args.dets, "coarse_hypotheses": M_GRID, "refiner_iterations": N_REFINER_ITERS, "refiner_views": N_VIEWS,
+        "render_size": [H_R, W_R], "frame": [H_IM, W_IM], "bsz_images": 576, "bsz_objects": 16,
+        "parallelism": f"hypothesis-sharded x{world}",
+        "l2": "no explicit flush: every step writes/reads 1.6 GB of network input per pose (> 126 MB L2)",
+    }
+
+
+def detections_arrays(n_det):
+    """Seeded synthetic detections of frame 0: the barbecue-sauce bbox, jittered for rows > 0."""
+    rs = np.random.RandomState(1)
+    boxes = np.tile(BBOX_BBQ, (n_det, 1)) + rs.uniform(-25, 25, (n_det, 4)).astype(np.float32)
+    boxes[0] = BBOX_BBQ
+    return boxes.astype(np.float32)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# clocks (B200_PROFILING.md): sampled during the timed region
+# ----------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.proc = None
+        self.path = f"/tmp/hpb_clocks_{os.getpid()}.csv"
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(index)],
+                                         stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            p = [x.strip() for x in line.split(",")]
+            if len(p) < 7:
+                continue
+            try:
+                sm.append(float(p[0])); mx.append(float(p[1])); power.append(float(p[2]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, p[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        try:
+            os.remove(self.path)
+        except OSError:
+            pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "power_w_max": max(power), "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peak_gbs():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# CPU side: the oracle pipeline = the reference's algorithm on host cores
+# ----------------------------------------------------------------------------------------------------------------
+def _torchvision_roi_align():
+    """The reference crops with torchvision.ops.roi_align (toolbox/lib3d/cropping.py:167); use the real (C++, CPU) op in
+    the baseline when it is importable so the baseline is not slowed down by the numpy restatement."""
+    try:
+        from torchvision.ops import roi_align as tv_roi_align
+    except Exception:
+        return None
+
+    def roi_align(images, rois, output_size, sampling_ratio=4):
+        out = tv_roi_align(torch.as_tensor(np.asarray(images, np.float32)), torch.as_tensor(np.asarray(rois, np.float32)),
+                           output_size=tuple(output_size), spatial_scale=1.0, sampling_ratio=int(sampling_ratio))
+        return out.numpy()
+
+    return roi_align
+
+
+class CpuPipeline:
+    """Bounded sample of the pose workload on the CPU: n_coarse coarse hypotheses (crop + raster + ResNet-34 9ch) and one
+    refiner iteration of one hypothesis (crop + 4 rasters + ResNet-34 27ch); pose time = 577/n_coarse * t_c + 5 * t_r."""
+
+    def __init__(self, n_coarse=8):
+        from oracle import np_oracle as O
+        from oracle import pipeline_oracle as P
+        from happypose_b200.megapose.backbones import make_backbone
+        from types import SimpleNamespace
+
+        self.O, self.P = O, P
+        tv = _torchvision_roi_align()
+        self.roi_kind = "torchvision.ops.roi_align (CPU)" if tv is not None else "numpy restatement"
+        if tv is not None:
+            O.roi_align = tv
+        self.cores = len(os.sched_getaffinity(0))
+        torch.set_num_threads(self.cores)
+        d = np.load(MESH)
+        self.scene = P.make_scene([{k: d[k] for k in d.files}], [0.001])
+        torch.manual_seed(0)
+
+        def cpu_model(n_in, n_views, head, out_dim):
+            bb = make_backbone("vanilla_resnet34", n_in).float().eval()
+            return SimpleNamespace(backbone=bb, heads={head: torch.nn.Linear(bb.n_features, out_dim).eval()}, render_size=(H_R, W_R),
+                                   input_depth=False, render_normals=True, render_depth=False, n_rendered_views=n_views,
+                                   multiview_type="TCO+front_3views", remove_TCO_rendering=False, depth_normalization_type="none", pose_dim=9)
+
+        self.coarse = cpu_model(9, 1, "renderings_logits", 1)
+        self.refiner = cpu_model(27, 4, "pose", 9)
+        with torch.no_grad():
+            self.refiner.heads["pose"].weight.mul_(1e-2)
+            self.refiner.heads["pose"].bias.copy_(torch.tensor([1.0, 0, 0, 0, 1, 0, 0, 0, 1]))
+        self.n_coarse = n_coarse
+        rs = np.random.RandomState(0)
+        self.image = rs.rand(1, 3, H_IM, W_IM).astype(np.float32)
+        quats = np.load(os.path.join(ROOT, "happypose_b200", "data", "so3_grid_576.npy"))
+        R = O.unitquat_to_rotmat(quats[:: M_GRID // n_coarse][:n_coarse]).astype(np.float32)
+        self.K_rows = np.tile(K_BBQ, (n_coarse, 1, 1))
+        boxes = np.tile(BBOX_BBQ, (n_coarse, 1))
+        self.zeros = np.zeros(n_coarse, int)
+        self.TCO0 = O.TCO_init_from_boxes_autodepth_with_R(boxes, self.scene.points[self.zeros], self.K_rows, R)
+
+    def sample(self):
+        """-> seconds per pose extrapolated from one bounded sample."""
+        P, n = self.P, self.n_coarse
+        t0 = time.perf_counter()
+        P.forward_coarse(self.coarse, self.scene, self.image, self.K_rows, self.zeros, self.zeros, self.TCO0, n_threads=self.cores)
+        t1 = time.perf_counter()
+        P.forward_refiner(self.refiner, self.scene, self.image, self.K_rows[:1], self.zeros[:1], self.zeros[:1], self.TCO0[:1], 1, n_threads=self.cores)
+        t2 = time.perf_counter()
+        return (t1 - t0) / n * (M_GRID + 1) + (t2 - t1) * N_REFINER_ITERS
+
+    def describe(self):
+        return (f"{self.n_coarse} of 577 coarse/scoring hypotheses + 1 of 5 refiner iterations (1 hypothesis x 4 views) per sample, "
+                f"extrapolated linearly to one pose; C rasteriser port (oracle/raster_oracle.c) + {self.roi_kind} + torch-CPU fp32 ResNet-34")
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    pipe = CpuPipeline(n_coarse=8)
+    for _ in range(max(args.warmup, 1)):
+        pipe.sample()
+    times = [pipe.sample() for _ in range(args.steps)]
+    t_pose = sum(times) / len(times)
+    value = args.dets / (t_pose * args.dets)  # a CPU box processes the detections one after another
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": t_pose * args.dets * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": config_dict(args, args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": pipe.cores, "kind": "port", "sample": pipe.describe()},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "Panda3D/OpenGL cannot be installed offline, so the reference arm is the CPU oracle port of the same path "
+                "(it omits the reference's worker-process IPC and GL read-back, i.e. it is a faster baseline than the real one)",
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# this repo
+# ----------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+    import pandas as pd
+    from happypose_b200 import distributed as hdist, ops
+    from happypose_b200.datasets.object_dataset import RigidObject, RigidObjectDataset
+    from happypose_b200.inference.types import ObservationTensor
+    from happypose_b200.megapose.pose_estimator import PoseEstimator
+    from happypose_b200.megapose.pose_models_cfg import make_pose_models
+    from happypose_b200.utils.tensor_collection import PandasTensorCollection
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    rank, local_rank, world = hdist.init_distributed_mode()
+    assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+    dev = torch.device("cuda", local_rank)
+    torch.backends.cudnn.benchmark = True
+
+    ds = RigidObjectDataset([RigidObject(label=LABEL, mesh_path=MESH, mesh_units="mm")])
+    coarse, refiner, mesh_db = make_pose_models(ds, device=dev, seed=0)
+    with torch.no_grad():  # identity-biased pose head: random weights must not throw the object out of the frame
+        refiner.pose_fc.weight.mul_(1e-2)
+        refiner.pose_fc.bias.copy_(torch.tensor([1.0, 0, 0, 0, 1, 0, 0, 0, 1]))
+    est = PoseEstimator(refiner_model=refiner, coarse_model=coarse, bsz_objects=16, bsz_images=576, SO3_grid_size=M_GRID)
+    if hasattr(est, "use_cuda_graphs"):
+        est.use_cuda_graphs = not args.no_graphs
+    ctx = coarse._ctx()
+
+    n_det = args.dets * world
+    boxes_np = detections_arrays(n_det)
+    rs = np.random.RandomState(0)
+    image_host = torch.as_tensor(rs.rand(1, 3, H_IM, W_IM).astype(np.float32)).pin_memory()
+    K_host = torch.as_tensor(K_BBQ[None]).pin_memory()
+    boxes_host = torch.as_tensor(boxes_np).pin_memory()
+
+    def make_detections(boxes_dev):
+        infos = pd.DataFrame({"label": [LABEL] * n_det, "batch_im_id": [0] * n_det, "score": [1.0] * n_det})
+        return PandasTensorCollection(infos=infos, bboxes=boxes_dev)
+
+    obs_dev = ObservationTensor(image_host.to(dev), K_host.to(dev))
+    boxes_dev = boxes_host.to(dev)
+
+    def step_resident():
+        final, _ = est.run_inference_pipeline(obs_dev, detections=make_detections(boxes_dev), n_refiner_iterations=N_REFINER_ITERS, n_pose_hypotheses=1)
+        return final
+
+    h2d = image_host.numel() * 4 + K_host.numel() * 4 + boxes_host.numel() * 4
+
+    def step_e2e():
+        obs = ObservationTensor(image_host.to(dev, non_blocking=True), K_host.to(dev, non_blocking=True))
+        det = make_detections(boxes_host.to(dev, non_blocking=True))
+        final, _ = est.run_inference_pipeline(obs, detections=det, n_refiner_iterations=N_REFINER_ITERS, n_pose_hypotheses=1)
+        poses = final.poses.cpu()
+        return poses, final.infos["pose_score"].to_numpy()
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    def timed(fn, steps):
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        sync_all()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    for _ in range(2):
+        step_e2e()
+
+    # ---- timed region 1: resident inputs (value), kernels bracketed with events, clocks sampled ------------------
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    timer = ops.KernelTimer()
+    ops.set_kernel_timer(timer)
+    l0 = ctx.launch_count()
+    ms_total = timed(step_resident, args.steps)
+    launches = ctx.launch_count() - l0
+    ops.set_kernel_timer(None)
+    ksum = timer.summary()
+    # ---- timed region 2: end to end from pinned host buffers -----------------------------------------------------
+    ms_e2e = timed(step_e2e, args.steps)
+    clocks = sampler.stop() if sampler is not None else None
+    poses, scores = step_e2e()
+    assert poses.shape == (n_det, 4, 4) and torch.isfinite(poses).all(), "pipeline produced non-finite poses"
+
+    # ---- render+crop throughput (BASELINE's second metric), no network -------------------------------------------
+    b = M_GRID
+    grid = est._SO3_grid.to(dev)
+    from happypose_b200 import _capi
+    obj0 = torch.zeros(b, dtype=torch.int32, device=dev)
+    mesh_ids = coarse.renderer.mesh_ids([LABEL] * b)
+    K_rows = obs_dev.K.expand(b, 3, 3).contiguous()
+    TCO = ops.tco_init(ctx, _capi.TCO_INIT_AUTODEPTH_WITH_R, boxes_dev[:1].expand(b, 4).contiguous(), K_rows, mesh_db.points, obj0, grid)
+    x = torch.empty((b, 9, H_R, W_R), device=dev)
+    pts = mesh_db.points_subset(2000)
+
+    def render_crop():
+        _, K_crop, _, _ = ops.crop(ctx, obs_dev.images, obj0, pts, obj0, K_rows, TCO, TCO[:, :3, 3].contiguous(), (H_R, W_R), out=x)
+        ops.render(ctx, mesh_ids, TCO, K_crop, (H_R, W_R), render_normals=True, out=x, out_channel_offset=3)
+
+    for _ in range(3):
+        render_crop()
+    hyp_iters = 20
+    ms_hyp = timed(render_crop, hyp_iters)
+    hyps_per_s = world * b * hyp_iters / (ms_hyp / 1e3)
+
+    if rank != 0:
+        return
+    poses_per_step = n_det
+    value = poses_per_step * args.steps / (ms_total / 1e3)
+    e2e_value = poses_per_step * args.steps / (ms_e2e / 1e3)
+    peak, peak_src = measured_peak_gbs()
+    rk = ksum.get("hpb_raster_kernel", {"gbps": 0.0, "ms_avg": 0.0, "launches": 0, "bytes_avg": 0, "ms_total": 0.0})
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16 (networks) / f32 (rasteriser, crop, pose kernels)", "data": "synthetic", "config": config_dict(args, world),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(poses.numel() * 4 + scores.size * 8),
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "kernel": "hpb_raster_kernel", "achieved": rk["gbps"], "peak": peak, "unit": "GB/s",
+                     "frac": rk["gbps"] / peak, "peak_source": peak_src, "traffic": None,
+                     "launches_timed": rk["launches"], "avg_launch_ms": rk["ms_avg"], "algorithmic_bytes_per_launch": rk["bytes_avg"],
+                     "share_of_step": rk["ms_total"] / ms_total if ms_total > 0 else None},
+        "kernels": {k: {"gbps": v["gbps"], "frac": v["gbps"] / peak, "avg_launch_ms": v["ms_avg"], "launches": v["launches"],
+                        "share_of_step": v["ms_total"] / ms_total} for k, v in ksum.items()},
+        "hyps": {"metric": "rendered_hyps_per_sec", "value": hyps_per_s, "unit": "hyps/s", "b": b, "ms_per_launch_pair": ms_hyp / hyp_iters,
+                 "gbps": b * 9 * H_R * W_R * 4 / 1e9 / (ms_hyp / hyp_iters / 1e3), "frac": b * 9 * H_R * W_R * 4 / 1e9 / (ms_hyp / hyp_iters / 1e3) / peak},
+    }
+    traffic_file = os.path.join(ROOT, "profiles", "raster_traffic.json")
+    if os.path.exists(traffic_file):
+        try:
+            line["roofline"]["traffic"] = json.load(open(traffic_file)).get("traffic_bytes_per_launch")
+        except Exception:
+            pass
+    if world == 1 and not args.no_cpu_baseline:
+        pipe = CpuPipeline(n_coarse=8)
+        pipe.sample()
+        t_pose = min(pipe.sample() for _ in range(2))
+        line["cpu_baseline"] = {"value": 1.0 / t_pose, "unit": UNIT, "cores": pipe.cores, "kind": "port", "sample": pipe.describe()}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+        import torch.distributed as dist
+
+        if dist.is_available() and dist.is_initialized():
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

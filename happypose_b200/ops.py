@@ -16,6 +16,38 @@ from . import _capi
 from ._capi import Context, ptr, stream_ptr
 
 
+class KernelTimer:
+    """Optional CUDA-event bracket around individual C-ABI launches (bench.py's live roofline measurement).
+    Events are recorded on torch's current stream -- the stream the kernels are launched on."""
+
+    def __init__(self):
+        self.records = {}
+
+    def bracket(self, name: str, algorithmic_bytes: int):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.records.setdefault(name, []).append((e0, e1, int(algorithmic_bytes)))
+        return e0, e1
+
+    def summary(self):
+        """name -> dict(launches, ms_total, ms_avg, bytes_avg, gbps); call after torch.cuda.synchronize()."""
+        out = {}
+        for name, recs in self.records.items():
+            ms = [a.elapsed_time(b) for a, b, _ in recs]
+            byts = [c for _, _, c in recs]
+            tot = sum(ms)
+            out[name] = {"launches": len(recs), "ms_total": tot, "ms_avg": tot / len(recs), "bytes_avg": sum(byts) / len(recs),
+                         "gbps": (sum(byts) / 1e9) / (tot / 1e3) if tot > 0 else 0.0}
+        return out
+
+
+_kernel_timer: Optional[KernelTimer] = None
+
+
+def set_kernel_timer(timer: Optional[KernelTimer]) -> None:
+    global _kernel_timer
+    _kernel_timer = timer
+
+
 def _f32(t, device) -> torch.Tensor:
     return torch.as_tensor(t).to(device=device, dtype=torch.float32).contiguous()
 
@@ -132,10 +164,17 @@ def render(
     if render_binary_mask:
         msk = torch.empty((b, 1, h, w), dtype=torch.bool, device=dev)
     if b > 0:
+        ev = None
+        if _kernel_timer is not None:
+            n_planes = (3 if render_rgb else 0) + (3 if render_normals else 0) + (1 if render_depth else 0)
+            ev = _kernel_timer.bracket("hpb_raster_kernel", b * h * w * (4 * n_planes + (1 if render_binary_mask else 0)))
+            ev[0].record()
         rc = ctx.lib.hpb_render(
             ctx.handle, ptr(mesh_ids), ptr(TCO), ptr(K), ptr(amb), b, h, w, z_near, z_far, flags,
             ptr(rgb), strides[0], ptr(nrm), strides[1], ptr(dep), strides[2], ptr(msk), h * w,
             views, view_stride if views > 1 else 0, stream_ptr(dev))
+        if ev is not None:
+            ev[1].record()
         ctx.check(rc, "hpb_render")
     if views > 1:
         return None, None, None, msk
@@ -185,10 +224,16 @@ def crop(
     K_crop = torch.empty((b, 3, 3), dtype=torch.float32, device=dev)
     boxes_rend = torch.empty((b, 4), dtype=torch.float32, device=dev)
     boxes_crop = torch.empty((b, 4), dtype=torch.float32, device=dev)
+    ev = None
+    if _kernel_timer is not None:
+        ev = _kernel_timer.bracket("hpb_crop", b * C * h * w * 4)
+        ev[0].record()
     rc = ctx.lib.hpb_crop(
         ctx.handle, ptr(images), n_im, C, H, W, ptr(im_ids), ptr(points), points.shape[0], points.shape[1], ptr(obj_ids),
         ptr(K), ptr(TCO), ptr(tCR), b, h, w, lamb, ptr(crops), bs, ptr(K_crop), ptr(boxes_rend), ptr(boxes_crop),
         stream_ptr(dev))
+    if ev is not None:
+        ev[1].record()
     ctx.check(rc, "hpb_crop")
     return crops, K_crop, boxes_rend, boxes_crop
 

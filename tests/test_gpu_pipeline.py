@@ -20,6 +20,13 @@ K_BBQ = np.array([[605.95, 0, 319.03], [0, 605.01, 249.68], [0, 0, 1]], np.float
 BBOX_BBQ = np.array([384, 234, 522, 455], np.float32)                               # docs/book/megapose/inference.md:37
 
 
+@pytest.fixture(autouse=True)
+def _inference_mode():
+    """The reference's callers run these modules under @torch.no_grad() (pose_estimator.py:104,222,327)."""
+    with torch.no_grad():
+        yield
+
+
 @pytest.fixture(scope="module")
 def object_dataset():
     from happypose_b200.datasets.object_dataset import RigidObject, RigidObjectDataset
