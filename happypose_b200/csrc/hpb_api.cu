@@ -158,6 +158,7 @@ int hpb_mesh_upload(hpb_ctx *ctx, const float *verts_xyz, const float *normals, 
             h = h > 1 ? h / 2 : 1;
         }
         m.dev.tex_levels = levels;
+        m.dev.tex_pow2 = ((tex_w & (tex_w - 1)) == 0 && (tex_h & (tex_h - 1)) == 0) ? 1 : 0;
         HPB_CUDA_OK(cudaMalloc(&m.tex, (size_t)total * 4));
         uint8_t *staging = nullptr;
         const size_t raw = (size_t)tex_w * tex_h * tex_c;

@@ -23,16 +23,14 @@ struct HpbMeshDev {
     const uchar4 *tex;   // RGBA8 mip chain or nullptr
     int nv, nf;
     int tex_levels;
+    int tex_pow2;  // 1 when level-0 width and height are powers of two (then every level is): wrap = bit mask
     int tex_w[HPB_MAX_MIPS];
     int tex_h[HPB_MAX_MIPS];
     long long tex_off[HPB_MAX_MIPS];  // texel offset of each level
 };
 
-// Screen-space vertex produced by phase A of the rasteriser (12 B; iz == 0 marks a near-clipped vertex).
-struct HpbSVert {
-    int x, y;  // 24.8 fixed point
-    float iz;  // 1 / Z_cam
-};
+// Screen-space vertices produced by phase A of the rasteriser are kept as two arrays (12 B per vertex):
+//   int2 xy  24.8 fixed-point screen position      float iz  1 / Z_cam (0 marks a near-clipped vertex)
 
 struct HpbMeshHost {
     void *pos = nullptr, *nrm = nullptr, *uv = nullptr, *vcol = nullptr, *faces = nullptr, *tex = nullptr;
@@ -50,8 +48,10 @@ struct hpb_ctx {
     // rasteriser workspace: one visibility buffer (+ vertex scratch for big meshes) per resident CTA
     unsigned long long *vis = nullptr;
     size_t vis_elems = 0;
-    HpbSVert *vert_scratch = nullptr;
-    size_t vert_scratch_elems = 0;
+    unsigned char *vert_scratch = nullptr;  // [resident CTAs][max_nv * 12 B] when a mesh does not fit in shared memory
+    size_t vert_scratch_bytes = 0;
+    int max_clusters[4] = {0, 0, 0, 0};  // co-resident clusters of size 1,2,4,8 (queried once per shared-memory size)
+    size_t max_clusters_smem = (size_t)-1;
     // top-k workspace
     void *topk_ws = nullptr;
     size_t topk_ws_bytes = 0;

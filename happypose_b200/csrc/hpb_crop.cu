@@ -22,7 +22,7 @@
 namespace {
 
 constexpr int CROP_SPAN = 4;       // dense tap span handled by the fast path
-constexpr int CROP_BAND = 16;      // output rows per CTA
+constexpr int CROP_BAND_MAX = 48;  // most output rows one CTA handles (fewer when the batch is small)
 constexpr int CROP_THREADS = 256;
 
 struct CropBoxParams {
@@ -117,6 +117,7 @@ struct CropPixParams {
     int n_im, C, H, W, b, h, w;
     float *crops;
     long long crops_bs;
+    int band;  // output rows per CTA
 };
 
 // One roi_align sample coordinate along one axis (torchvision roi_align bilinear_interpolate, aligned=False).
@@ -177,15 +178,17 @@ __device__ __forceinline__ bool axis_weights(float start, float bin, int i, int 
     return true;
 }
 
+template <int C>
 __global__ void __launch_bounds__(CROP_THREADS) hpb_crop_pixels_kernel(const CropPixParams p) {
     const int n = blockIdx.y;
-    const int row0 = blockIdx.x * CROP_BAND;
+    const int band = p.band;
+    const int row0 = blockIdx.x * band;
     const int tid = threadIdx.x;
     extern __shared__ float sm[];
     float *sWX = sm;                                  // [w][CROP_SPAN]
     int *sBX = reinterpret_cast<int *>(sWX + (size_t)p.w * CROP_SPAN);  // [w]
-    float *sWY = reinterpret_cast<float *>(sBX + p.w);  // [CROP_BAND][CROP_SPAN]
-    int *sBY = reinterpret_cast<int *>(sWY + CROP_BAND * CROP_SPAN);  // [CROP_BAND]
+    float *sWY = reinterpret_cast<float *>(sBX + p.w);  // [band][CROP_SPAN]
+    int *sBY = reinterpret_cast<int *>(sWY + band * CROP_SPAN);  // [band]
     __shared__ int sGeneric;
 
     const float *bx = p.boxes + (size_t)n * 4;
@@ -199,51 +202,53 @@ __global__ void __launch_bounds__(CROP_THREADS) hpb_crop_pixels_kernel(const Cro
         int base;
         if (!axis_weights(x1, bin_w, j, p.W, base, wt)) sGeneric = 1;
         sBX[j] = base;
-#pragma unroll
-        for (int k = 0; k < CROP_SPAN; ++k) sWX[j * CROP_SPAN + k] = wt[k];
+        *reinterpret_cast<float4 *>(sWX + j * CROP_SPAN) = make_float4(wt[0], wt[1], wt[2], wt[3]);
     }
-    for (int i = tid; i < CROP_BAND; i += blockDim.x) {
-        float wt[CROP_SPAN];
+    for (int i = tid; i < band; i += blockDim.x) {
+        float wt[CROP_SPAN] = {0.f, 0.f, 0.f, 0.f};
         int base = 0;
         if (row0 + i < p.h) {
             if (!axis_weights(y1, bin_h, row0 + i, p.H, base, wt)) sGeneric = 1;
-        } else {
-#pragma unroll
-            for (int k = 0; k < CROP_SPAN; ++k) wt[k] = 0.0f;
         }
         sBY[i] = base;
-#pragma unroll
-        for (int k = 0; k < CROP_SPAN; ++k) sWY[i * CROP_SPAN + k] = wt[k];
+        *reinterpret_cast<float4 *>(sWY + i * CROP_SPAN) = make_float4(wt[0], wt[1], wt[2], wt[3]);
     }
     __syncthreads();
     const bool generic = sGeneric != 0;
     const int im = p.im_ids[n];
-    const float *img = p.images + (size_t)im * p.C * p.H * p.W;
+    const float *img = p.images + (size_t)im * C * p.H * p.W;
     float *out = p.crops + (size_t)n * p.crops_bs;
     const size_t plane_in = (size_t)p.H * p.W, plane_out = (size_t)p.h * p.w;
-    const int rows = min(CROP_BAND, p.h - row0);
+    const int rows = min(band, p.h - row0);
     const int npx = rows * p.w;
 
     for (int q = tid; q < npx; q += blockDim.x) {
         const int i = q / p.w, j = q - i * p.w;
         const int oy = row0 + i;
-        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        float acc[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) acc[c] = 0.f;
         float accv = 0.f;
         if (!generic) {
             const int by = sBY[i], bxx = sBX[j];
+            const float4 wy4 = *reinterpret_cast<const float4 *>(sWY + i * CROP_SPAN);
+            const float4 wx4 = *reinterpret_cast<const float4 *>(sWX + j * CROP_SPAN);
+            const float wys[CROP_SPAN] = {wy4.x, wy4.y, wy4.z, wy4.w};
+            const float wxs[CROP_SPAN] = {wx4.x, wx4.y, wx4.z, wx4.w};
 #pragma unroll
             for (int ky = 0; ky < CROP_SPAN; ++ky) {
-                const float wy = sWY[i * CROP_SPAN + ky];
+                const float wy = wys[ky];
                 if (wy == 0.0f) continue;
                 const int yy = min(by + ky, p.H - 1);
 #pragma unroll
                 for (int kx = 0; kx < CROP_SPAN; ++kx) {
-                    const float wx = sWX[j * CROP_SPAN + kx];
+                    const float wx = wxs[kx];
                     if (wx == 0.0f) continue;
                     const int xx = min(bxx + kx, p.W - 1);
                     const float wgt = wy * wx;
                     const float *src = img + (size_t)yy * p.W + xx;
-                    for (int c = 0; c < p.C; ++c) {
+#pragma unroll
+                    for (int c = 0; c < C; ++c) {
                         const float v = __ldg(src + c * plane_in);
                         acc[c] = fmaf(wgt, v, acc[c]);
                         if (c == 3) accv = fmaf(wgt, v > 0.0f ? 1.0f : 0.0f, accv);
@@ -259,7 +264,8 @@ __global__ void __launch_bounds__(CROP_THREADS) hpb_crop_pixels_kernel(const Cro
                     const AxisTap tx = axis_tap(x1 + (float)j * bin_w + ((float)sx + 0.5f) * bin_w / 4.0f, p.W);
                     if (!tx.valid) continue;
                     const float w1 = ty.wlo * tx.wlo, w2 = ty.wlo * tx.whi, w3 = ty.whi * tx.wlo, w4 = ty.whi * tx.whi;
-                    for (int c = 0; c < p.C; ++c) {
+#pragma unroll
+                    for (int c = 0; c < C; ++c) {
                         const float *pl = img + c * plane_in;
                         const float v1 = __ldg(pl + (size_t)ty.lo * p.W + tx.lo), v2 = __ldg(pl + (size_t)ty.lo * p.W + tx.hi);
                         const float v3 = __ldg(pl + (size_t)ty.hi * p.W + tx.lo), v4 = __ldg(pl + (size_t)ty.hi * p.W + tx.hi);
@@ -270,9 +276,10 @@ __global__ void __launch_bounds__(CROP_THREADS) hpb_crop_pixels_kernel(const Cro
                 }
             }
         }
-        if (p.C == 4 && accv < 0.99f) acc[3] = 0.0f;  // cropping.py:191-195
+        if (C == 4 && accv < 0.99f) acc[C - 1] = 0.0f;  // cropping.py:191-195
         float *o = out + (size_t)oy * p.w + j;
-        for (int c = 0; c < p.C; ++c) __stcs(o + c * plane_out, acc[c]);
+#pragma unroll
+        for (int c = 0; c < C; ++c) __stcs(o + c * plane_out, acc[c]);
     }
 }
 
@@ -300,10 +307,19 @@ int hpb_launch_crop_pixels(hpb_ctx *ctx, const float *images, int n_im, int C, i
     p.images = images; p.im_ids = im_ids; p.boxes = boxes;
     p.n_im = n_im; p.C = C; p.H = H; p.W = W; p.b = b; p.h = h; p.w = w;
     p.crops = crops; p.crops_bs = crops_bs;
+    // rows per CTA: enough CTAs to fill the machine for small batches, long bands (column weights amortised) otherwise
+    int band = CROP_BAND_MAX;
+    while (band > 8 && (long long)b * ((h + band - 1) / band) < 2ll * ctx->sm_count) band /= 2;
+    p.band = band;
     const size_t smem = (size_t)w * CROP_SPAN * sizeof(float) + (size_t)w * sizeof(int) +
-                        CROP_BAND * CROP_SPAN * sizeof(float) + CROP_BAND * sizeof(int);
-    dim3 grid((h + CROP_BAND - 1) / CROP_BAND, b);
-    hpb_crop_pixels_kernel<<<grid, CROP_THREADS, smem, stream>>>(p);
+                        (size_t)band * CROP_SPAN * sizeof(float) + (size_t)band * sizeof(int);
+    dim3 grid((h + band - 1) / band, b);
+    if (C == 3) hpb_crop_pixels_kernel<3><<<grid, CROP_THREADS, smem, stream>>>(p);
+    else if (C == 4) hpb_crop_pixels_kernel<4><<<grid, CROP_THREADS, smem, stream>>>(p);
+    else {
+        hpb_set_error("hpb_crop: C must be 3 or 4 (got %d)", C);
+        return HPB_EINVAL;
+    }
     HPB_CUDA_OK(cudaGetLastError());
     ctx->launches++;
     return HPB_OK;

@@ -7,18 +7,31 @@
 // explicit IEEE op / fmaf so results are bit-identical to the CPU oracle used by the tests (the library is built
 // with -fmad=false).
 //
-// Structure (one persistent CTA per SM, looping over scenes):
-//   phase A  vertex stage: object -> camera -> 24.8 fixed-point screen position + 1/z, staged in SHARED memory
-//            (12 B per vertex; meshes that do not fit fall back to a per-CTA global scratch slice).
-//   phase B  triangle stage: one thread per triangle, exact integer edge functions with a top-left rule over the
-//            triangle's pixel bounding box; depth test = 64-bit atomicMin of (depth bits << 32 | triangle id) on a
-//            per-CTA visibility buffer that stays resident in L2 (it is re-armed in phase C, never re-cleared).
-//   phase C  resolve: one thread per pixel, coalesced planar stores; the winning triangle is re-set-up, attributes
-//            are interpolated perspective-correctly, texture is trilinearly filtered from an RGBA8 mip chain.
-//            Background pixels are written as zeros here, so the outputs need no separate clear pass.
+// Structure: a persistent grid of thread-block CLUSTERS; each cluster (G = 1, 2, 4 or 8 CTAs, one CTA per SM) loops
+// over scenes.  G > 1 is chosen for small batches so that one scene is spread over several SMs (the refiner renders
+// only 4..64 scenes per launch); for b >= #SMs G = 1 and each SM renders whole scenes.
+//   phase A  vertex stage (every CTA of the cluster, redundantly): object -> camera -> 24.8 fixed-point screen
+//            position + 1/z, staged in SHARED memory (12 B per vertex; meshes that do not fit fall back to a per-CTA
+//            global scratch slice).  The screen bounding box of the scene is reduced on the way.
+//   phase B  triangle stage: the cluster's CTAs split the triangle list.  One lane per triangle: exact integer edge
+//            functions with a top-left rule; small triangles are walked by their own lane in a warp-convergent
+//            loop, big ones (or ones needing 64-bit edge functions) by the whole warp.  Depth test = 64-bit
+//            atomicMin of (depth bits << 32 | triangle id) on a per-cluster visibility buffer that stays resident
+//            in L2 (it is re-armed in phase C, never re-cleared).
+//   phase C  resolve: the cluster's CTAs split the pixels; one thread per pixel, coalesced planar stores.  Only pixels
+//            inside the scene's bounding box read the visibility buffer; the winning triangle is re-set-up,
+//            attributes are interpolated perspective-correctly, texture is trilinearly filtered from an RGBA8 mip
+//            chain.  Background pixels are written as zeros here, so the outputs need no separate clear pass.
+#include <cooperative_groups.h>
+
 #include "hpb_common.cuh"
 
+namespace cg = cooperative_groups;
+
 namespace {
+
+constexpr int RASTER_THREADS = 1024;
+constexpr int SMALL_TRI_MAX = 32;  // bbox pixels a lane walks on its own; larger triangles are walked by the warp
 
 struct RasterParams {
     const HpbMeshDev *meshes;
@@ -27,6 +40,7 @@ struct RasterParams {
     const float *K;
     const float *ambient;
     int b, h, w;
+    unsigned w_magic;  // floor(2^32 / w) + 1
     float z_near;
     float inv_near, cd, a_f, b_f, eps_hi;
     uint32_t flags;
@@ -37,10 +51,11 @@ struct RasterParams {
     long long rgb_bs, nrm_bs, depth_bs, mask_bs;
     int views;            // scene i writes at base + (i / views) * bstride + (i % views) * view_stride
     long long view_stride;
-    unsigned long long *vis;   // [gridDim.x][h*w]
-    HpbSVert *vert_scratch;    // [gridDim.x][max_nv] when vertices do not fit in shared memory
+    unsigned long long *vis;      // [clusters][h*w]
+    unsigned char *vert_scratch;  // [CTAs][max_nv * 12] when vertices do not fit in shared memory
     int max_nv;
     int verts_in_smem;
+    int G;  // CTAs per cluster
 };
 
 __device__ __forceinline__ int snap_fixed(float u) {
@@ -61,19 +76,21 @@ struct TriSetup {
 };
 
 // Orients the triangle so area2 > 0.  Returns false for near-clipped or degenerate triangles.
-__device__ __forceinline__ bool setup_tri(const HpbSVert *sv, int4 f, TriSetup &t, float &iz0, float &iz1, float &iz2) {
-    const HpbSVert a = sv[f.x], b = sv[f.y], c = sv[f.z];
-    if (a.iz == 0.0f || b.iz == 0.0f || c.iz == 0.0f) return false;
+__device__ __forceinline__ bool setup_tri(const int2 *sxy, const float *siz, int4 f, TriSetup &t, float &iz0, float &iz1,
+                                          float &iz2) {
+    const int2 a = sxy[f.x], b = sxy[f.y], c = sxy[f.z];
+    const float za = siz[f.x], zb = siz[f.y], zc = siz[f.z];
+    if (za == 0.0f || zb == 0.0f || zc == 0.0f) return false;
     long long area2 = (long long)(b.x - a.x) * (long long)(c.y - a.y) - (long long)(c.x - a.x) * (long long)(b.y - a.y);
     if (area2 == 0) return false;
-    t.x0 = a.x; t.y0 = a.y; t.i0 = f.x; iz0 = a.iz;
+    t.x0 = a.x; t.y0 = a.y; t.i0 = f.x; iz0 = za;
     if (area2 < 0) {
-        t.x1 = c.x; t.y1 = c.y; t.i1 = f.z; iz1 = c.iz;
-        t.x2 = b.x; t.y2 = b.y; t.i2 = f.y; iz2 = b.iz;
+        t.x1 = c.x; t.y1 = c.y; t.i1 = f.z; iz1 = zc;
+        t.x2 = b.x; t.y2 = b.y; t.i2 = f.y; iz2 = zb;
         area2 = -area2;
     } else {
-        t.x1 = b.x; t.y1 = b.y; t.i1 = f.y; iz1 = b.iz;
-        t.x2 = c.x; t.y2 = c.y; t.i2 = f.z; iz2 = c.iz;
+        t.x1 = b.x; t.y1 = b.y; t.i1 = f.y; iz1 = zb;
+        t.x2 = c.x; t.y2 = c.y; t.i2 = f.z; iz2 = zc;
     }
     t.area2 = area2;
     return true;
@@ -81,40 +98,32 @@ __device__ __forceinline__ bool setup_tri(const HpbSVert *sv, int4 f, TriSetup &
 
 __device__ __forceinline__ float depth_from_iz(const RasterParams &p, float iz) { return (p.inv_near - iz) * p.cd; }
 
-// Phase B for one triangle; I = int (all intermediates provably fit 32 bits) or long long.
-template <typename I>
-__device__ __forceinline__ void raster_tri(const RasterParams &p, const TriSetup &t, float iz0, float iz1, float iz2,
-                                           int jx0, int jx1, int jy0, int jy1, unsigned tri_id,
-                                           unsigned long long *vis) {
-    const int b0 = edge_bias(t.x2 - t.x1, t.y2 - t.y1);
-    const int b1 = edge_bias(t.x0 - t.x2, t.y0 - t.y2);
-    const int b2 = edge_bias(t.x1 - t.x0, t.y1 - t.y0);
-    const int px0 = jx0 * HPB_SUBPIX + 128, py0 = jy0 * HPB_SUBPIX + 128;
-    // edge functions at the first pixel centre and their per-pixel steps
-    I e0r = (I)(t.x2 - t.x1) * (I)(py0 - t.y1) - (I)(t.y2 - t.y1) * (I)(px0 - t.x1);
-    I e1r = (I)(t.x0 - t.x2) * (I)(py0 - t.y2) - (I)(t.y0 - t.y2) * (I)(px0 - t.x2);
-    I e2r = (I)(t.x1 - t.x0) * (I)(py0 - t.y0) - (I)(t.y1 - t.y0) * (I)(px0 - t.x0);
-    const I sx0 = -(I)(t.y2 - t.y1) * HPB_SUBPIX, sy0 = (I)(t.x2 - t.x1) * HPB_SUBPIX;
-    const I sx1 = -(I)(t.y0 - t.y2) * HPB_SUBPIX, sy1 = (I)(t.x0 - t.x2) * HPB_SUBPIX;
-    const I sx2 = -(I)(t.y1 - t.y0) * HPB_SUBPIX, sy2 = (I)(t.x1 - t.x0) * HPB_SUBPIX;
-    const float inv = 1.0f / (float)t.area2;
-    for (int py = jy0; py <= jy1; ++py) {
-        I e0 = e0r, e1 = e1r, e2 = e2r;
-        unsigned long long *row = vis + (long long)py * p.w;
-        for (int px = jx0; px <= jx1; ++px) {
-            if (((e0 + b0) | (e1 + b1) | (e2 + b2)) >= 0) {
-                const float l0 = (float)e0 * inv, l1 = (float)e1 * inv, l2 = (float)e2 * inv;
-                const float iz = fmaf(l2, iz2, fmaf(l1, iz1, l0 * iz0));
-                float d = depth_from_iz(p, iz);
-                if (d <= 1.0f) {
-                    if (d < 0.0f) d = 0.0f;
-                    const unsigned long long key = ((unsigned long long)__float_as_uint(d) << 32) | tri_id;
-                    atomicMin(row + px, key);
-                }
-            }
-            e0 += sx0; e1 += sx1; e2 += sx2;
-        }
-        e0r += sy0; e1r += sy1; e2r += sy2;
+__device__ __forceinline__ void emit_fragment(const RasterParams &p, float l0, float l1, float l2, float iz0, float iz1,
+                                              float iz2, unsigned tri_id, unsigned long long *slot) {
+    const float iz = fmaf(l2, iz2, fmaf(l1, iz1, l0 * iz0));
+    float d = depth_from_iz(p, iz);
+    if (d <= 1.0f) {
+        if (d < 0.0f) d = 0.0f;
+        atomicMin(slot, ((unsigned long long)__float_as_uint(d) << 32) | tri_id);
+    }
+}
+
+// Whole-warp walk of one (big) triangle's bounding box with 64-bit edge functions; all lanes hold the same triangle.
+__device__ __forceinline__ void raster_tri_warp(const RasterParams &p, int x0, int y0, int x1, int y1, int x2, int y2,
+                                                float iz0, float iz1, float iz2, float inv, int jx0, int jx1, int jy0,
+                                                int jy1, unsigned tri_id, unsigned long long *vis, int lane) {
+    const int b0 = edge_bias(x2 - x1, y2 - y1), b1 = edge_bias(x0 - x2, y0 - y2), b2 = edge_bias(x1 - x0, y1 - y0);
+    const int roww = jx1 - jx0 + 1, total = roww * (jy1 - jy0 + 1);
+    // lanes cover 32 consecutive pixels of the row-major bounding box at a time
+    for (int idx = lane; idx < total; idx += 32) {
+        const int row = idx / roww, col = idx - row * roww;
+        const int px = jx0 + col, py = jy0 + row;
+        const int fxp = px * HPB_SUBPIX + 128, fyp = py * HPB_SUBPIX + 128;
+        const long long e0 = (long long)(x2 - x1) * (fyp - y1) - (long long)(y2 - y1) * (fxp - x1);
+        const long long e1 = (long long)(x0 - x2) * (fyp - y2) - (long long)(y0 - y2) * (fxp - x2);
+        const long long e2 = (long long)(x1 - x0) * (fyp - y0) - (long long)(y1 - y0) * (fxp - x0);
+        if (((e0 + b0) | (e1 + b1) | (e2 + b2)) >= 0)
+            emit_fragment(p, (float)e0 * inv, (float)e1 * inv, (float)e2 * inv, iz0, iz1, iz2, tri_id, vis + (long long)py * p.w + px);
     }
 }
 
@@ -128,16 +137,24 @@ __device__ __forceinline__ float hp_log2(float x) {
     return (float)e + q;
 }
 
-__device__ __forceinline__ float3 fetch_texel(const HpbMeshDev &m, int lvl, int x, int y) {
-    const int W = m.tex_w[lvl], H = m.tex_h[lvl];
-    x %= W; if (x < 0) x += W;
-    y %= H; if (y < 0) y += H;
-    const uchar4 c = __ldg(m.tex + m.tex_off[lvl] + (long long)y * W + x);
+template <bool POW2>
+__device__ __forceinline__ float3 fetch_texel(const uchar4 *tex, int W, int H, int x, int y) {
+    if (POW2) {
+        x &= W - 1;
+        y &= H - 1;
+    } else {
+        x %= W; if (x < 0) x += W;
+        y %= H; if (y < 0) y += H;
+    }
+    const uchar4 c = __ldg(tex + y * W + x);
     return make_float3((float)c.x, (float)c.y, (float)c.z);
 }
 
+template <bool POW2>
 __device__ __forceinline__ float3 sample_bilinear(const HpbMeshDev &m, int lvl, float u, float v) {
-    const float W = (float)m.tex_w[lvl], H = (float)m.tex_h[lvl];
+    const int Wi = m.tex_w[lvl], Hi = m.tex_h[lvl];
+    const uchar4 *tex = m.tex + m.tex_off[lvl];
+    const float W = (float)Wi, H = (float)Hi;
     const float x = fmaf(u, W, -0.5f);
     const float y = fmaf(1.0f - v, H, -0.5f);
     float xf = floorf(x), yf = floorf(y);
@@ -147,8 +164,8 @@ __device__ __forceinline__ float3 sample_bilinear(const HpbMeshDev &m, int lvl, 
     if (!(yf > -1.0e9f)) yf = -1.0e9f;
     if (yf > 1.0e9f) yf = 1.0e9f;
     const int x0 = (int)xf, y0 = (int)yf;
-    const float3 c00 = fetch_texel(m, lvl, x0, y0), c01 = fetch_texel(m, lvl, x0 + 1, y0);
-    const float3 c10 = fetch_texel(m, lvl, x0, y0 + 1), c11 = fetch_texel(m, lvl, x0 + 1, y0 + 1);
+    const float3 c00 = fetch_texel<POW2>(tex, Wi, Hi, x0, y0), c01 = fetch_texel<POW2>(tex, Wi, Hi, x0 + 1, y0);
+    const float3 c10 = fetch_texel<POW2>(tex, Wi, Hi, x0, y0 + 1), c11 = fetch_texel<POW2>(tex, Wi, Hi, x0 + 1, y0 + 1);
     float3 o;
     {
         const float top = fmaf(fx, c01.x - c00.x, c00.x), bot = fmaf(fx, c11.x - c10.x, c10.x);
@@ -165,8 +182,24 @@ __device__ __forceinline__ float3 sample_bilinear(const HpbMeshDev &m, int lvl, 
     return o;
 }
 
+template <bool POW2>
+__device__ __forceinline__ float3 sample_trilinear(const HpbMeshDev &m, float u, float v, float lod) {
+    const float maxl = (float)(m.tex_levels - 1);
+    if (lod > maxl) lod = maxl;
+    const float lf = floorf(lod);
+    const float fl = lod - lf;
+    const int li = (int)lf;
+    const float3 ca = sample_bilinear<POW2>(m, li, u, v);
+    if (fl > 0.0f && li + 1 < m.tex_levels) {
+        const float3 cb = sample_bilinear<POW2>(m, li + 1, u, v);
+        return make_float3(fmaf(fl, cb.x - ca.x, ca.x), fmaf(fl, cb.y - ca.y, ca.y), fmaf(fl, cb.z - ca.z, ca.z));
+    }
+    return ca;
+}
+
 // Panda3D's 32^3 "normal map" lookup (renderer/utils.py:63-79): texel k = floor(k*255/32), repeat wrap, linear.
-__device__ __forceinline__ float encode_normal(float c) {
+// lut[k] = (float)k / 255.0f (IEEE division, done once per CTA): the 8-bit framebuffer value returned as k/255.
+__device__ __forceinline__ float encode_normal(float c, const float *lut) {
     const float s = c - floorf(c);
     const float t = fmaf(s, 32.0f, -0.5f);
     const float kf = floorf(t);
@@ -176,45 +209,47 @@ __device__ __forceinline__ float encode_normal(float c) {
     const float T0 = (float)((k0 * 255) >> 5);
     const float T1 = (float)((k1 * 255) >> 5);
     const float val = fmaf(f, T1 - T0, T0);
-    return floorf(val + 0.5f) / 255.0f;
+    return lut[(int)floorf(val + 0.5f)];  // val in [0, 247]
 }
 
-__device__ __forceinline__ float quant8(float c) {
+__device__ __forceinline__ float quant8(float c, const float *lut) {
     float q = floorf(c + 0.5f);
     if (!(q > 0.0f)) q = 0.0f;
     if (q > 255.0f) q = 255.0f;
-    return q / 255.0f;
+    return lut[(int)q];
 }
 
-__device__ __forceinline__ float3 eye_normal(const float *T, const float *n) {
-    const float nx = __ldg(n), ny = __ldg(n + 1), nz = __ldg(n + 2);
-    float ex = fmaf(T[2], nz, fmaf(T[1], ny, T[0] * nx));
-    float ey = fmaf(T[6], nz, fmaf(T[5], ny, T[4] * nx));
-    float ez = fmaf(T[10], nz, fmaf(T[9], ny, T[8] * nx));
-    const float l2 = fmaf(ez, ez, fmaf(ey, ey, ex * ex));
-    if (l2 > 0.0f) {
-        const float r = 1.0f / sqrtf(l2);
-        ex *= r; ey *= r; ez *= r;
-    }
-    return make_float3(ex, ey, ez);
-}
-
-__global__ void __launch_bounds__(1024, 1) hpb_raster_kernel(const RasterParams p) {
+__global__ void __launch_bounds__(RASTER_THREADS, 1) hpb_raster_kernel(const RasterParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ HpbMeshDev sM;
     __shared__ float sT[16];
     __shared__ float sK[4];
     __shared__ float sAmb[3];
     __shared__ int sFinite;
+    __shared__ int sBox[4];  // min x, min y, max x, max y of the snapped vertices (fixed point)
+    __shared__ float sLut[256];
 
-    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int G = p.G;
+    const int rank = G > 1 ? (int)cg::this_cluster().block_rank() : 0;
+    const int group = blockIdx.x / G, n_groups = gridDim.x / G;
     const int npix = p.h * p.w;
-    unsigned long long *vis = p.vis + (size_t)blockIdx.x * npix;
-    HpbSVert *sv = p.verts_in_smem ? reinterpret_cast<HpbSVert *>(smem_raw)
-                                   : p.vert_scratch + (size_t)blockIdx.x * p.max_nv;
+    unsigned long long *vis = p.vis + (size_t)group * npix;
+    unsigned char *vbase = p.verts_in_smem ? smem_raw : p.vert_scratch + (size_t)blockIdx.x * p.max_nv * 12;
+    int2 *sxy = reinterpret_cast<int2 *>(vbase);
+    float *siz = reinterpret_cast<float *>(vbase + (size_t)p.max_nv * 8);
 
-    for (int hyp = blockIdx.x; hyp < p.b; hyp += gridDim.x) {
-        const HpbMeshDev &m = p.meshes[p.mesh_ids[hyp]];
-        if (tid == 0) sFinite = 1;
+    if (threadIdx.x < 256) sLut[threadIdx.x] = (float)threadIdx.x / 255.0f;
+    for (int hyp = group; hyp < p.b; hyp += n_groups) {
+        {
+            const int *src = reinterpret_cast<const int *>(p.meshes + p.mesh_ids[hyp]);
+            int *dst = reinterpret_cast<int *>(&sM);
+            for (int i = tid; i < (int)(sizeof(HpbMeshDev) / 4); i += RASTER_THREADS) dst[i] = src[i];
+        }
+        if (tid == 0) {
+            sFinite = 1;
+            sBox[0] = 0x7fffffff; sBox[1] = 0x7fffffff; sBox[2] = (int)0x80000000; sBox[3] = (int)0x80000000;
+        }
         __syncthreads();
         if (tid < 16) {
             const float v = p.TCO[(size_t)hyp * 16 + tid];
@@ -235,50 +270,136 @@ __global__ void __launch_bounds__(1024, 1) hpb_raster_kernel(const RasterParams 
         }
         __syncthreads();
         const bool finite = sFinite != 0;
+        const HpbMeshDev &m = sM;
         const int nv = m.nv, nf = m.nf;
+        int bx0 = 1, bx1 = 0, by0 = 1, by1 = 0;  // pixel bounding box of the scene (empty by default)
 
         if (finite) {
             // ---------------- phase A: vertex stage ----------------
             const float fx = sK[0], fy = sK[1], cx = sK[2], cy = sK[3];
-            for (int i = tid; i < nv; i += nthr) {
+            int mnx = 0x7fffffff, mny = 0x7fffffff, mxx = (int)0x80000000, mxy = (int)0x80000000;
+            for (int i = tid; i < nv; i += RASTER_THREADS) {
                 const float x = __ldg(m.pos + 3 * i), y = __ldg(m.pos + 3 * i + 1), z = __ldg(m.pos + 3 * i + 2);
                 const float X = fmaf(sT[2], z, fmaf(sT[1], y, fmaf(sT[0], x, sT[3])));
                 const float Y = fmaf(sT[6], z, fmaf(sT[5], y, fmaf(sT[4], x, sT[7])));
                 const float Z = fmaf(sT[10], z, fmaf(sT[9], y, fmaf(sT[8], x, sT[11])));
-                HpbSVert o;
-                if (!(Z >= p.z_near)) {
-                    o.x = 0; o.y = 0; o.iz = 0.0f;
-                } else {
-                    const float iz = 1.0f / Z;
-                    o.iz = iz;
+                int2 o = make_int2(0, 0);
+                float iz = 0.0f;
+                if (Z >= p.z_near) {
+                    iz = 1.0f / Z;
                     o.x = snap_fixed(fmaf(fx, X * iz, cx));
                     o.y = snap_fixed(fmaf(fy, Y * iz, cy));
+                    mnx = min(mnx, o.x); mxx = max(mxx, o.x);
+                    mny = min(mny, o.y); mxy = max(mxy, o.y);
                 }
-                sv[i] = o;
+                sxy[i] = o;
+                siz[i] = iz;
+            }
+            mnx = __reduce_min_sync(0xffffffffu, mnx); mny = __reduce_min_sync(0xffffffffu, mny);
+            mxx = __reduce_max_sync(0xffffffffu, mxx); mxy = __reduce_max_sync(0xffffffffu, mxy);
+            if (lane == 0 && mnx <= mxx) {
+                atomicMin(&sBox[0], mnx); atomicMin(&sBox[1], mny);
+                atomicMax(&sBox[2], mxx); atomicMax(&sBox[3], mxy);
             }
             __syncthreads();
+            if (sBox[0] <= sBox[2]) {
+                bx0 = max(ceil_div_pix(sBox[0]), 0); bx1 = min(floor_div_pix(sBox[2]), p.w - 1);
+                by0 = max(ceil_div_pix(sBox[1]), 0); by1 = min(floor_div_pix(sBox[3]), p.h - 1);
+            }
 
             // ---------------- phase B: triangle stage ----------------
-            for (int t = tid; t < nf; t += nthr) {
-                const int4 f = __ldg(m.faces + t);
-                TriSetup ts;
-                float iz0, iz1, iz2;
-                if (!setup_tri(sv, f, ts, iz0, iz1, iz2)) continue;
-                const int mnx = min(ts.x0, min(ts.x1, ts.x2)), mxx = max(ts.x0, max(ts.x1, ts.x2));
-                const int mny = min(ts.y0, min(ts.y1, ts.y2)), mxy = max(ts.y0, max(ts.y1, ts.y2));
-                const int jx0 = max(ceil_div_pix(mnx), 0), jx1 = min(floor_div_pix(mxx), p.w - 1);
-                const int jy0 = max(ceil_div_pix(mny), 0), jy1 = min(floor_div_pix(mxy), p.h - 1);
-                if (jx0 > jx1 || jy0 > jy1) continue;
-                // 32-bit path: |edge function| <= 2 * bbox_w * bbox_h (fixed point) over the (clamped) bbox
-                const long long bw = (long long)mxx - mnx + 2 * HPB_SUBPIX, bh = (long long)mxy - mny + 2 * HPB_SUBPIX;
-                if (bw * bh < (1ll << 29))
-                    raster_tri<int>(p, ts, iz0, iz1, iz2, jx0, jx1, jy0, jy1, (unsigned)t, vis);
-                else
-                    raster_tri<long long>(p, ts, iz0, iz1, iz2, jx0, jx1, jy0, jy1, (unsigned)t, vis);
+            if (bx0 <= bx1 && by0 <= by1) {
+                const int per = (nf + G - 1) / G;
+                const int lo = rank * per, hi = min(nf, lo + per);
+                for (int base = lo; base < hi; base += RASTER_THREADS) {  // trip count is warp-uniform
+                    const int t = base + tid;
+                    TriSetup ts;
+                    float iz0 = 0.f, iz1 = 0.f, iz2 = 0.f;
+                    int jx0 = 0, jx1 = -1, jy0 = 0, jy1 = -1, cnt = 0;
+                    bool big = false;
+                    if (t < hi && setup_tri(sxy, siz, __ldg(m.faces + t), ts, iz0, iz1, iz2)) {
+                        const int tmnx = min(ts.x0, min(ts.x1, ts.x2)), tmxx = max(ts.x0, max(ts.x1, ts.x2));
+                        const int tmny = min(ts.y0, min(ts.y1, ts.y2)), tmxy = max(ts.y0, max(ts.y1, ts.y2));
+                        jx0 = max(ceil_div_pix(tmnx), 0); jx1 = min(floor_div_pix(tmxx), p.w - 1);
+                        jy0 = max(ceil_div_pix(tmny), 0); jy1 = min(floor_div_pix(tmxy), p.h - 1);
+                        if (jx0 <= jx1 && jy0 <= jy1) {
+                            cnt = (jx1 - jx0 + 1) * (jy1 - jy0 + 1);
+                            // 32-bit edge functions are exact when |e| <= 2 * bbox_w * bbox_h (fixed point) < 2^31
+                            const long long bw = (long long)tmxx - tmnx + 2 * HPB_SUBPIX, bh = (long long)tmxy - tmny + 2 * HPB_SUBPIX;
+                            big = cnt > SMALL_TRI_MAX || !(bw * bh < (1ll << 29));
+                        }
+                    }
+                    const float inv = cnt ? __frcp_rn((float)ts.area2) : 0.0f;
+                    // ---- small triangles: every lane walks its own bounding box in two warp-convergent loops ----
+                    // loop 1 builds the lane's coverage bit mask (bit k = k-th bounding-box pixel, row-major) with
+                    // branch-free edge stepping; loop 2 emits one covered pixel per iteration.
+                    const int scnt = big ? 0 : cnt;
+                    const int mx = __reduce_max_sync(0xffffffffu, scnt);
+                    if (mx > 0) {
+                        // unsigned arithmetic: the stepped values are exact modulo 2^32 and the true edge values at
+                        // the bounding-box pixels fit 31 bits (see `big`); intermediate row jumps may wrap
+                        const int roww = jx1 - jx0 + 1;
+                        const int bb0 = edge_bias(ts.x2 - ts.x1, ts.y2 - ts.y1), bb1 = edge_bias(ts.x0 - ts.x2, ts.y0 - ts.y2),
+                                  bb2 = edge_bias(ts.x1 - ts.x0, ts.y1 - ts.y0);
+                        const int px0 = jx0 * HPB_SUBPIX + 128, py0 = jy0 * HPB_SUBPIX + 128;
+                        const unsigned E0 = (unsigned)((ts.x2 - ts.x1) * (py0 - ts.y1) - (ts.y2 - ts.y1) * (px0 - ts.x1) + bb0);
+                        const unsigned E1 = (unsigned)((ts.x0 - ts.x2) * (py0 - ts.y2) - (ts.y0 - ts.y2) * (px0 - ts.x2) + bb1);
+                        const unsigned E2 = (unsigned)((ts.x1 - ts.x0) * (py0 - ts.y0) - (ts.y1 - ts.y0) * (px0 - ts.x0) + bb2);
+                        const unsigned sx0 = (unsigned)(-(ts.y2 - ts.y1)) * HPB_SUBPIX, sx1 = (unsigned)(-(ts.y0 - ts.y2)) * HPB_SUBPIX,
+                                       sx2 = (unsigned)(-(ts.y1 - ts.y0)) * HPB_SUBPIX;
+                        const unsigned sy0 = (unsigned)(ts.x2 - ts.x1) * HPB_SUBPIX, sy1 = (unsigned)(ts.x0 - ts.x2) * HPB_SUBPIX,
+                                       sy2 = (unsigned)(ts.x1 - ts.x0) * HPB_SUBPIX;
+                        unsigned cov = 0;
+                        {
+                            unsigned e0 = E0, e1 = E1, e2 = E2;
+                            const unsigned rj0 = sy0 - (unsigned)roww * sx0, rj1 = sy1 - (unsigned)roww * sx1, rj2 = sy2 - (unsigned)roww * sx2;
+                            int col = 0;
+                            for (int k = 0; k < mx; ++k) {
+                                cov |= (~(e0 | e1 | e2) >> 31) << k;
+                                e0 += sx0; e1 += sx1; e2 += sx2;
+                                const bool wrap = ++col == roww;
+                                e0 += wrap ? rj0 : 0u; e1 += wrap ? rj1 : 0u; e2 += wrap ? rj2 : 0u;
+                                col = wrap ? 0 : col;
+                            }
+                        }
+                        cov &= scnt >= 32 ? 0xffffffffu : ((1u << scnt) - 1u);
+                        const int mxn = __reduce_max_sync(0xffffffffu, __popc(cov));
+                        const unsigned rcp = 65535u / (unsigned)max(roww, 1) + 1u;  // k / roww == (k * rcp) >> 16 for k, roww <= 32
+                        unsigned long long *org = vis + (long long)jy0 * p.w + jx0;
+                        for (int j = 0; j < mxn; ++j) {
+                            if (cov) {
+                                const int k = __ffs(cov) - 1;
+                                cov &= cov - 1;
+                                const int row = (int)(((unsigned)k * rcp) >> 16), col = k - row * roww;
+                                const int e0 = (int)(E0 + (unsigned)col * sx0 + (unsigned)row * sy0) - bb0;
+                                const int e1 = (int)(E1 + (unsigned)col * sx1 + (unsigned)row * sy1) - bb1;
+                                const int e2 = (int)(E2 + (unsigned)col * sx2 + (unsigned)row * sy2) - bb2;
+                                emit_fragment(p, (float)e0 * inv, (float)e1 * inv, (float)e2 * inv, iz0, iz1, iz2, (unsigned)t,
+                                              org + row * p.w + col);
+                            }
+                        }
+                    }
+                    // ---- big triangles: the whole warp walks one triangle at a time ----
+                    unsigned bm = __ballot_sync(0xffffffffu, big);
+                    while (bm) {
+                        const int src = __ffs(bm) - 1;
+                        bm &= bm - 1;
+                        const int x0 = __shfl_sync(0xffffffffu, ts.x0, src), y0 = __shfl_sync(0xffffffffu, ts.y0, src);
+                        const int x1 = __shfl_sync(0xffffffffu, ts.x1, src), y1 = __shfl_sync(0xffffffffu, ts.y1, src);
+                        const int x2 = __shfl_sync(0xffffffffu, ts.x2, src), y2 = __shfl_sync(0xffffffffu, ts.y2, src);
+                        const float z0 = __shfl_sync(0xffffffffu, iz0, src), z1 = __shfl_sync(0xffffffffu, iz1, src);
+                        const float z2 = __shfl_sync(0xffffffffu, iz2, src), iv = __shfl_sync(0xffffffffu, inv, src);
+                        const int ax0 = __shfl_sync(0xffffffffu, jx0, src), ax1 = __shfl_sync(0xffffffffu, jx1, src);
+                        const int ay0 = __shfl_sync(0xffffffffu, jy0, src), ay1 = __shfl_sync(0xffffffffu, jy1, src);
+                        raster_tri_warp(p, x0, y0, x1, y1, x2, y2, z0, z1, z2, iv, ax0, ax1, ay0, ay1,
+                                        (unsigned)(base + (tid & ~31) + src), vis, lane);
+                    }
+                }
             }
             __threadfence();
-            __syncthreads();
         }
+        if (G > 1) cg::this_cluster().sync();
+        else __syncthreads();
 
         // ---------------- phase C: resolve ----------------
         const size_t oi = (size_t)(hyp / p.views), ov = (size_t)(hyp % p.views) * p.view_stride;
@@ -286,57 +407,76 @@ __global__ void __launch_bounds__(1024, 1) hpb_raster_kernel(const RasterParams 
         float *nrm = (p.flags & HPB_RENDER_NORMALS) ? p.nrm + oi * p.nrm_bs + ov : nullptr;
         float *dep = (p.flags & HPB_RENDER_DEPTH) ? p.depth + oi * p.depth_bs + ov : nullptr;
         uint8_t *msk = (p.flags & HPB_RENDER_MASK) ? p.mask + (size_t)hyp * p.mask_bs : nullptr;  // never view-interleaved
-        for (int pix = tid; pix < npix; pix += nthr) {
+        const bool textured = m.tex != nullptr && m.uv != nullptr;
+        for (int pix = rank * RASTER_THREADS + tid; pix < npix; pix += G * RASTER_THREADS) {
+            int py = (int)__umulhi((unsigned)pix, p.w_magic);
+            if (py * p.w > pix) --py;
+            const int px = pix - py * p.w;
             unsigned long long key = HPB_VIS_EMPTY;
-            if (finite) {
+            if (px >= bx0 && px <= bx1 && py >= by0 && py <= by1) {
                 key = __ldcg(vis + pix);
                 if (key != HPB_VIS_EMPTY) __stcg(vis + pix, HPB_VIS_EMPTY);  // re-arm for the next scene
             }
             float r = 0.f, g = 0.f, bl = 0.f, n0 = 0.f, n1 = 0.f, n2 = 0.f, z = 0.f;
             if (key != HPB_VIS_EMPTY) {
-                const int py = pix / p.w, px = pix - py * p.w;
                 const unsigned t = (unsigned)(key & 0xffffffffull);
-                const int4 f = __ldg(m.faces + t);
                 TriSetup ts;
                 float iz0, iz1, iz2;
-                setup_tri(sv, f, ts, iz0, iz1, iz2);
+                setup_tri(sxy, siz, __ldg(m.faces + t), ts, iz0, iz1, iz2);
                 const int fxp = px * HPB_SUBPIX + 128, fyp = py * HPB_SUBPIX + 128;
-                const long long e0 = (long long)(ts.x2 - ts.x1) * (fyp - ts.y1) - (long long)(ts.y2 - ts.y1) * (fxp - ts.x1);
-                const long long e1 = (long long)(ts.x0 - ts.x2) * (fyp - ts.y2) - (long long)(ts.y0 - ts.y2) * (fxp - ts.x2);
-                const long long e2 = (long long)(ts.x1 - ts.x0) * (fyp - ts.y0) - (long long)(ts.y1 - ts.y0) * (fxp - ts.x0);
-                const float inv = 1.0f / (float)ts.area2;
-                const float l0 = (float)e0 * inv, l1 = (float)e1 * inv, l2 = (float)e2 * inv;
+                // barycentric edge values at the pixel centre; e0 + e1 + e2 == area2 exactly.  32-bit products are exact
+                // when the triangle's fixed-point bounding box is small (same bound as in phase B), the usual case.
+                float fe0, fe1, fe2;
+                {
+                    const long long bw = (long long)max(ts.x0, max(ts.x1, ts.x2)) - min(ts.x0, min(ts.x1, ts.x2)) + 2 * HPB_SUBPIX;
+                    const long long bh = (long long)max(ts.y0, max(ts.y1, ts.y2)) - min(ts.y0, min(ts.y1, ts.y2)) + 2 * HPB_SUBPIX;
+                    if (bw * bh < (1ll << 29)) {
+                        const int e0 = (ts.x2 - ts.x1) * (fyp - ts.y1) - (ts.y2 - ts.y1) * (fxp - ts.x1);
+                        const int e1 = (ts.x0 - ts.x2) * (fyp - ts.y2) - (ts.y0 - ts.y2) * (fxp - ts.x2);
+                        const int e2 = (int)ts.area2 - e0 - e1;
+                        fe0 = (float)e0; fe1 = (float)e1; fe2 = (float)e2;
+                    } else {
+                        const long long e0 = (long long)(ts.x2 - ts.x1) * (fyp - ts.y1) - (long long)(ts.y2 - ts.y1) * (fxp - ts.x1);
+                        const long long e1 = (long long)(ts.x0 - ts.x2) * (fyp - ts.y2) - (long long)(ts.y0 - ts.y2) * (fxp - ts.x2);
+                        const long long e2 = ts.area2 - e0 - e1;
+                        fe0 = (float)e0; fe1 = (float)e1; fe2 = (float)e2;
+                    }
+                }
+                const float inv = __frcp_rn((float)ts.area2);
+                const float l0 = fe0 * inv, l1 = fe1 * inv, l2 = fe2 * inv;
                 const float w0 = l0 * iz0, w1 = l1 * iz1, w2 = l2 * iz2;
                 const float iz = fmaf(l2, iz2, fmaf(l1, iz1, w0));
                 const float d = __uint_as_float((unsigned)(key >> 32));
                 z = p.a_f / (d - p.b_f);
                 if (d > p.eps_hi) z = 0.0f;
-                const float s = 1.0f / iz;
+                const float s = __frcp_rn(iz);
                 const float p0 = w0 * s, p1 = w1 * s, p2 = w2 * s;
                 if (nrm) {
-                    const float3 a = eye_normal(sT, m.nrm + 3 * ts.i0);
-                    const float3 b = eye_normal(sT, m.nrm + 3 * ts.i1);
-                    const float3 c = eye_normal(sT, m.nrm + 3 * ts.i2);
-                    float nx = fmaf(p2, c.x, fmaf(p1, b.x, p0 * a.x));
-                    float ny = fmaf(p2, c.y, fmaf(p1, b.y, p0 * a.y));
-                    float nz = fmaf(p2, c.z, fmaf(p1, b.z, p0 * a.z));
+                    // object-space normal interpolated over the triangle, rotated into the eye frame, normalised once
+                    const float *na = m.nrm + 3 * ts.i0, *nb = m.nrm + 3 * ts.i1, *nc = m.nrm + 3 * ts.i2;
+                    const float ox = fmaf(p2, __ldg(nc), fmaf(p1, __ldg(nb), p0 * __ldg(na)));
+                    const float oy = fmaf(p2, __ldg(nc + 1), fmaf(p1, __ldg(nb + 1), p0 * __ldg(na + 1)));
+                    const float oz = fmaf(p2, __ldg(nc + 2), fmaf(p1, __ldg(nb + 2), p0 * __ldg(na + 2)));
+                    float nx = fmaf(sT[2], oz, fmaf(sT[1], oy, sT[0] * ox));
+                    float ny = fmaf(sT[6], oz, fmaf(sT[5], oy, sT[4] * ox));
+                    float nz = fmaf(sT[10], oz, fmaf(sT[9], oy, sT[8] * ox));
                     const float len2 = fmaf(nz, nz, fmaf(ny, ny, nx * nx));
                     if (len2 > 0.0f) {
-                        const float rl = 1.0f / sqrtf(len2);
+                        const float rl = __frcp_rn(__fsqrt_rn(len2));
                         nx *= rl; ny *= rl; nz *= rl;
                     }
-                    n0 = encode_normal(nx);
-                    n1 = encode_normal(nz);
-                    n2 = encode_normal(-ny);
+                    n0 = encode_normal(nx, sLut);
+                    n1 = encode_normal(nz, sLut);
+                    n2 = encode_normal(-ny, sLut);
                 }
                 if (rgb) {
                     float3 col = make_float3(255.0f, 255.0f, 255.0f);
-                    if (m.tex && m.uv) {
-                        const float u0 = __ldg(m.uv + 2 * ts.i0), v0 = __ldg(m.uv + 2 * ts.i0 + 1);
-                        const float u1 = __ldg(m.uv + 2 * ts.i1), v1 = __ldg(m.uv + 2 * ts.i1 + 1);
-                        const float u2 = __ldg(m.uv + 2 * ts.i2), v2 = __ldg(m.uv + 2 * ts.i2 + 1);
-                        const float u = fmaf(p2, u2, fmaf(p1, u1, p0 * u0));
-                        const float v = fmaf(p2, v2, fmaf(p1, v1, p0 * v0));
+                    if (textured) {
+                        const float2 t0 = __ldg(reinterpret_cast<const float2 *>(m.uv) + ts.i0);
+                        const float2 t1 = __ldg(reinterpret_cast<const float2 *>(m.uv) + ts.i1);
+                        const float2 t2 = __ldg(reinterpret_cast<const float2 *>(m.uv) + ts.i2);
+                        const float u = fmaf(p2, t2.x, fmaf(p1, t1.x, p0 * t0.x));
+                        const float v = fmaf(p2, t2.y, fmaf(p1, t1.y, p0 * t0.y));
                         const float sc = (float)HPB_SUBPIX * inv;
                         const float dl0x = (float)(-(ts.y2 - ts.y1)) * sc, dl0y = (float)(ts.x2 - ts.x1) * sc;
                         const float dl1x = (float)(-(ts.y0 - ts.y2)) * sc, dl1y = (float)(ts.x0 - ts.x2) * sc;
@@ -344,10 +484,10 @@ __global__ void __launch_bounds__(1024, 1) hpb_raster_kernel(const RasterParams 
                         const float g0x = dl0x * iz0, g1x = dl1x * iz1, g2x = dl2x * iz2;
                         const float g0y = dl0y * iz0, g1y = dl1y * iz1, g2y = dl2y * iz2;
                         const float dDx = g0x + g1x + g2x, dDy = g0y + g1y + g2y;
-                        const float dNux = fmaf(g2x, u2, fmaf(g1x, u1, g0x * u0));
-                        const float dNuy = fmaf(g2y, u2, fmaf(g1y, u1, g0y * u0));
-                        const float dNvx = fmaf(g2x, v2, fmaf(g1x, v1, g0x * v0));
-                        const float dNvy = fmaf(g2y, v2, fmaf(g1y, v1, g0y * v0));
+                        const float dNux = fmaf(g2x, t2.x, fmaf(g1x, t1.x, g0x * t0.x));
+                        const float dNuy = fmaf(g2y, t2.x, fmaf(g1y, t1.x, g0y * t0.x));
+                        const float dNvx = fmaf(g2x, t2.y, fmaf(g1x, t1.y, g0x * t0.y));
+                        const float dNvy = fmaf(g2y, t2.y, fmaf(g1y, t1.y, g0y * t0.y));
                         const float W0 = (float)m.tex_w[0], H0 = (float)m.tex_h[0];
                         const float ax = (dNux - u * dDx) * s * W0, bx = (dNvx - v * dDx) * s * H0;
                         const float ay = (dNuy - u * dDy) * s * W0, by = (dNvy - v * dDy) * s * H0;
@@ -355,29 +495,16 @@ __global__ void __launch_bounds__(1024, 1) hpb_raster_kernel(const RasterParams 
                         const float rho2 = r2x > r2y ? r2x : r2y;
                         float lod = 0.0f;
                         if (rho2 > 1.0f && rho2 < 1.0e30f) lod = 0.5f * hp_log2(rho2);
-                        const float maxl = (float)(m.tex_levels - 1);
-                        if (lod > maxl) lod = maxl;
-                        const float lf = floorf(lod);
-                        const float fl = lod - lf;
-                        const int li = (int)lf;
-                        const float3 ca = sample_bilinear(m, li, u, v);
-                        if (fl > 0.0f && li + 1 < m.tex_levels) {
-                            const float3 cb = sample_bilinear(m, li + 1, u, v);
-                            col.x = fmaf(fl, cb.x - ca.x, ca.x);
-                            col.y = fmaf(fl, cb.y - ca.y, ca.y);
-                            col.z = fmaf(fl, cb.z - ca.z, ca.z);
-                        } else {
-                            col = ca;
-                        }
+                        col = m.tex_pow2 ? sample_trilinear<true>(m, u, v, lod) : sample_trilinear<false>(m, u, v, lod);
                     } else if (m.vcol) {
                         const uchar4 c0 = __ldg(m.vcol + ts.i0), c1 = __ldg(m.vcol + ts.i1), c2 = __ldg(m.vcol + ts.i2);
                         col.x = fmaf(p2, (float)c2.x, fmaf(p1, (float)c1.x, p0 * (float)c0.x));
                         col.y = fmaf(p2, (float)c2.y, fmaf(p1, (float)c1.y, p0 * (float)c0.y));
                         col.z = fmaf(p2, (float)c2.z, fmaf(p1, (float)c1.z, p0 * (float)c0.z));
                     }
-                    r = quant8(col.x * sAmb[0]);
-                    g = quant8(col.y * sAmb[1]);
-                    bl = quant8(col.z * sAmb[2]);
+                    r = quant8(col.x * sAmb[0], sLut);
+                    g = quant8(col.y * sAmb[1], sLut);
+                    bl = quant8(col.z * sAmb[2], sLut);
                 }
             }
             if (rgb) {
@@ -393,7 +520,10 @@ __global__ void __launch_bounds__(1024, 1) hpb_raster_kernel(const RasterParams 
             if (dep) __stcs(dep + pix, z);
             if (msk) msk[pix] = z > 0.0f ? 1 : 0;
         }
-        __syncthreads();
+        // the next scene's phase A overwrites the vertex stage, and its phase B (from any CTA of the cluster) writes
+        // the visibility buffer this CTA has just re-armed
+        if (G > 1) cg::this_cluster().sync();
+        else __syncthreads();
     }
 }
 
@@ -449,12 +579,39 @@ int hpb_launch_raster(hpb_ctx *ctx, const int32_t *mesh_ids, const float *TCO, c
                       int views, int64_t view_stride, cudaStream_t stream) {
     if (b == 0) return HPB_OK;
     const int npix = h * w;
-    // persistent grid: one CTA per SM (1024 threads, vertices in shared memory), never more CTAs than scenes
-    const int grid = b < ctx->sm_count ? b : ctx->sm_count;
-
-    const size_t smem_need = (size_t)ctx->max_nv * sizeof(HpbSVert);
+    const int nv_pad = (ctx->max_nv + 1) & ~1;  // keeps the int2 array 8-byte aligned in every CTA's slice
+    const size_t smem_need = (size_t)nv_pad * 12;
     const size_t smem_cap = (size_t)ctx->max_smem_optin > 4096 ? (size_t)ctx->max_smem_optin - 2048 : 0;
     const int verts_in_smem = smem_need <= smem_cap;
+    const size_t smem = verts_in_smem ? smem_need : 0;
+    HPB_CUDA_OK(cudaFuncSetAttribute(hpb_raster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+
+    // how many clusters of 1/2/4/8 CTAs can be co-resident (one CTA per SM); queried once per shared-memory size
+    if (ctx->max_clusters_smem != smem) {
+        for (int k = 0; k < 4; ++k) {
+            const int G = 1 << k;
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(G * 8, 1, 1);
+            cfg.blockDim = dim3(RASTER_THREADS, 1, 1);
+            cfg.dynamicSmemBytes = smem;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = G; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at;
+            cfg.numAttrs = 1;
+            int n = 0;
+            if (G == 1) n = ctx->sm_count;
+            else if (cudaOccupancyMaxActiveClusters(&n, hpb_raster_kernel, &cfg) != cudaSuccess) { n = 0; cudaGetLastError(); }
+            ctx->max_clusters[k] = n;
+        }
+        ctx->max_clusters_smem = smem;
+    }
+    // persistent grid: the largest cluster size that still gives every scene its own cluster
+    int k = 0;
+    while (k < 3 && ctx->max_clusters[k + 1] >= b) ++k;
+    const int G = 1 << k;
+    const int n_groups = b < ctx->max_clusters[k] ? b : ctx->max_clusters[k];
+    const int n_ctas = n_groups * G;
 
     // workspace (grown on demand; the visibility buffer is armed once and re-armed by the kernel itself)
     const size_t vis_need = (size_t)ctx->sm_count * npix;
@@ -469,13 +626,13 @@ int hpb_launch_raster(hpb_ctx *ctx, const int32_t *mesh_ids, const float *TCO, c
         ctx->launches++;
     }
     if (!verts_in_smem) {
-        const size_t need = (size_t)ctx->sm_count * ctx->max_nv;
-        if (ctx->vert_scratch_elems < need) {
+        const size_t need = (size_t)ctx->sm_count * nv_pad * 12;
+        if (ctx->vert_scratch_bytes < need) {
             if (ctx->vert_scratch) HPB_CUDA_OK(cudaFree(ctx->vert_scratch));
             ctx->vert_scratch = nullptr;
-            ctx->vert_scratch_elems = 0;
-            HPB_CUDA_OK(cudaMalloc(&ctx->vert_scratch, need * sizeof(HpbSVert)));
-            ctx->vert_scratch_elems = need;
+            ctx->vert_scratch_bytes = 0;
+            HPB_CUDA_OK(cudaMalloc(&ctx->vert_scratch, need));
+            ctx->vert_scratch_bytes = need;
         }
     }
 
@@ -486,6 +643,7 @@ int hpb_launch_raster(hpb_ctx *ctx, const int32_t *mesh_ids, const float *TCO, c
     p.K = K;
     p.ambient = ambient;
     p.b = b; p.h = h; p.w = w;
+    p.w_magic = (unsigned)((1ull << 32) / (unsigned)w) + 1u;
     p.z_near = z_near;
     p.inv_near = 1.0f / z_near;
     const float inv_far = 1.0f / z_far;
@@ -500,13 +658,21 @@ int hpb_launch_raster(hpb_ctx *ctx, const int32_t *mesh_ids, const float *TCO, c
     p.views = views; p.view_stride = view_stride;
     p.vis = ctx->vis;
     p.vert_scratch = ctx->vert_scratch;
-    p.max_nv = ctx->max_nv;
+    p.max_nv = nv_pad;
     p.verts_in_smem = verts_in_smem;
+    p.G = G;
 
-    const size_t smem = verts_in_smem ? smem_need : 0;
-    HPB_CUDA_OK(cudaFuncSetAttribute(hpb_raster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    hpb_raster_kernel<<<grid, 1024, smem, stream>>>(p);
-    HPB_CUDA_OK(cudaGetLastError());
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(n_ctas, 1, 1);
+    cfg.blockDim = dim3(RASTER_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = G; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = G > 1 ? 1 : 0;
+    HPB_CUDA_OK(cudaLaunchKernelEx(&cfg, hpb_raster_kernel, p));
     ctx->launches++;
     return HPB_OK;
 }

@@ -21,7 +21,8 @@
  *                               (megapose/models/pose_rigid.py:415-420): colour = texture (mip-mapped,
  *                               :68) * min(sum(ambient),1); 8-bit framebuffer, returned as k/255
  *                               (panda3d_batch_renderer.py:249).
- *   normals                     eye-space unit normal looked up in a 32^3 RGB texture whose texel
+ *   normals                     eye-space unit normal (object normal interpolated over the triangle, rotated by
+ *                               R_CO, normalised per pixel) looked up in a 32^3 RGB texture whose texel
  *                               (x,y,z) = floor((x,y,z)*255/32), repeat wrap, linear filter
  *                               (toolbox/renderer/utils.py:63-79, panda3d_scene_renderer.py:221-230),
  *                               in Panda camera axes (x right, y forward, z up).
@@ -198,10 +199,9 @@ static int render_one(const hpo_mesh *m, const float *T, const float *K, int h, 
     const int64_t nv = m->n_verts, nf = m->n_faces;
     int *sx = (int *)malloc(sizeof(int) * nv), *sy = (int *)malloc(sizeof(int) * nv);
     float *viz = (float *)malloc(sizeof(float) * nv);
-    float *vn = (float *)malloc(sizeof(float) * 3 * nv);
     uint8_t *vbad = (uint8_t *)malloc(nv);
     uint64_t *zb = (uint64_t *)malloc(sizeof(uint64_t) * npix);
-    if (!sx || !sy || !viz || !vn || !vbad || !zb) return -1;
+    if (!sx || !sy || !viz || !vbad || !zb) return -1;
     memset(zb, 0xff, sizeof(uint64_t) * npix);
 
     const float fx = K[0], fy = K[4], cx = K[2], cy = K[5];
@@ -222,17 +222,6 @@ static int render_one(const hpo_mesh *m, const float *T, const float *K, int h, 
         viz[i] = iz;
         sx[i] = snap(fmaf(fx, X * iz, cx));
         sy[i] = snap(fmaf(fy, Y * iz, cy));
-        if (m->nrm) {
-            const float nx = m->nrm[3 * i], ny = m->nrm[3 * i + 1], nz = m->nrm[3 * i + 2];
-            float ex = fmaf(T[2], nz, fmaf(T[1], ny, T[0] * nx));
-            float ey = fmaf(T[6], nz, fmaf(T[5], ny, T[4] * nx));
-            float ez = fmaf(T[10], nz, fmaf(T[9], ny, T[8] * nx));
-            float l2 = fmaf(ez, ez, fmaf(ey, ey, ex * ex));
-            if (l2 > 0.0f) { float r = 1.0f / sqrtf(l2); ex *= r; ey *= r; ez *= r; }
-            vn[3 * i] = ex; vn[3 * i + 1] = ey; vn[3 * i + 2] = ez;
-        } else {
-            vn[3 * i] = vn[3 * i + 1] = vn[3 * i + 2] = 0.0f;
-        }
     }
 
     /* pass 1: visibility (depth bits << 32 | triangle id), min wins */
@@ -297,10 +286,18 @@ static int render_one(const hpo_mesh *m, const float *T, const float *K, int h, 
             const float s = 1.0f / iz;
             const float p0 = w0 * s, p1 = w1 * s, p2 = w2 * s;
             if (nrm_out) {
-                const float *n0 = vn + 3 * ts.i0, *n1 = vn + 3 * ts.i1, *n2 = vn + 3 * ts.i2;
-                float nx = fmaf(p2, n2[0], fmaf(p1, n1[0], p0 * n0[0]));
-                float ny = fmaf(p2, n2[1], fmaf(p1, n1[1], p0 * n0[1]));
-                float nz = fmaf(p2, n2[2], fmaf(p1, n1[2], p0 * n0[2]));
+                /* object-space normal interpolated perspective-correctly, then rotated into the eye frame and
+                 * normalised once per pixel (for an orthonormal R identical to interpolating per-vertex eye normals) */
+                float ox = 0.0f, oy = 0.0f, oz = 0.0f;
+                if (m->nrm) {
+                    const float *n0 = m->nrm + 3 * ts.i0, *n1 = m->nrm + 3 * ts.i1, *n2 = m->nrm + 3 * ts.i2;
+                    ox = fmaf(p2, n2[0], fmaf(p1, n1[0], p0 * n0[0]));
+                    oy = fmaf(p2, n2[1], fmaf(p1, n1[1], p0 * n0[1]));
+                    oz = fmaf(p2, n2[2], fmaf(p1, n1[2], p0 * n0[2]));
+                }
+                float nx = fmaf(T[2], oz, fmaf(T[1], oy, T[0] * ox));
+                float ny = fmaf(T[6], oz, fmaf(T[5], oy, T[4] * ox));
+                float nz = fmaf(T[10], oz, fmaf(T[9], oy, T[8] * ox));
                 const float len2 = fmaf(nz, nz, fmaf(ny, ny, nx * nx));
                 if (len2 > 0.0f) { const float r = 1.0f / sqrtf(len2); nx *= r; ny *= r; nz *= r; }
                 nrm_out[pi] = encode_normal(nx);
@@ -354,7 +351,7 @@ static int render_one(const hpo_mesh *m, const float *T, const float *K, int h, 
             }
         }
     }
-    free(sx); free(sy); free(viz); free(vn); free(vbad); free(zb);
+    free(sx); free(sy); free(viz); free(vbad); free(zb);
     (void)flags;
     return 0;
 }

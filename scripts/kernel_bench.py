@@ -1,0 +1,54 @@
+"""Kernel timing (CUDA events) for the rasteriser and crop kernels on the bench's real-use poses (SO(3) grid + bbox init).
+usage: kernel_bench.py [b ...]   (b = scenes per launch)"""
+import os, sys, json
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import bench as B
+from happypose_b200 import ops, _capi
+from happypose_b200._capi import Context
+from happypose_b200.utils import transform_utils
+
+def timeit(fn, warm=3, it=10):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(it):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / it
+
+def main():
+    dev = torch.device("cuda:0")
+    ctx = Context.get(dev)
+    d = np.load(B.MESH)
+    pos = (d["verts"].astype(np.float64) * 0.001).astype(np.float32)
+    mid = ops.mesh_upload(ctx, pos, d["faces"], d["normals"], d["uv"], texture=d["texture"])
+    grid = transform_utils.load_SO3_grid(576).to(dev)
+    pts_all = torch.as_tensor(pos[None]).to(dev)
+    pts = torch.as_tensor(pos[np.random.RandomState(0).choice(len(pos), 2000, replace=False)][None]).to(dev)
+    img = torch.rand(1, 3, 480, 640, device=dev)
+    bs = [int(a) for a in sys.argv[1:]] or [1, 4, 64, 576, 2304]
+    peak = B.measured_peak_gbs()[0]
+    for b in bs:
+        R = grid[torch.arange(b, device=dev) % 576]
+        zero = torch.zeros(b, dtype=torch.int32, device=dev)
+        K = torch.as_tensor(B.K_BBQ).to(dev).expand(b, 3, 3).contiguous()
+        boxes = torch.as_tensor(B.BBOX_BBQ).to(dev).expand(b, 4).contiguous()
+        TCO = ops.tco_init(ctx, _capi.TCO_INIT_AUTODEPTH_WITH_R, boxes, K, pts_all, zero, R)
+        ids = torch.full((b,), mid, dtype=torch.int32, device=dev)
+        x = torch.empty((b, 9, 240, 320), device=dev)
+        tCR = TCO[:, :3, 3].contiguous()
+        _, K_crop, _, _ = ops.crop(ctx, img, zero, pts, zero, K, TCO, tCR, (240, 320), out=x)
+        ms = timeit(lambda: ops.render(ctx, ids, TCO, K_crop, (240, 320), render_normals=True, out=x, out_channel_offset=3))
+        gb = b * 6 * 240 * 320 * 4 / 1e9
+        cov = float((x[:, 3:6].sum(1) > 0).float().mean())
+        print(json.dumps({"kernel": "raster rgb+normals", "b": b, "ms": round(ms, 4), "hyps_per_s": round(b / ms * 1e3), "GBps": round(gb / ms * 1e3, 1), "frac": round(gb / ms * 1e3 / peak, 4), "coverage": round(cov, 3)}))
+        ms = timeit(lambda: ops.crop(ctx, img, zero, pts, zero, K, TCO, tCR, (240, 320), out=x))
+        gb = b * 3 * 240 * 320 * 4 / 1e9
+        print(json.dumps({"kernel": "crop (boxes+pixels)", "b": b, "ms": round(ms, 4), "hyps_per_s": round(b / ms * 1e3), "GBps": round(gb / ms * 1e3, 1), "frac": round(gb / ms * 1e3 / peak, 4)}))
+
+if __name__ == "__main__":
+    main()
