@@ -120,6 +120,12 @@ class Context:
             cls._by_device[index] = ctx
         return ctx
 
+    def __deepcopy__(self, memo):  # one context per device: models that are deep-copied keep sharing it
+        return self
+
+    def __copy__(self):
+        return self
+
     def launch_count(self) -> int:
         return int(self.lib.hpb_launch_count(self.handle))
 

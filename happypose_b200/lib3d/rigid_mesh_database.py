@@ -91,6 +91,9 @@ class BatchedMeshes(TensorCollection):
         self.register_tensor("symmetries", symmetries)
         self.__dict__["_subset_cache"] = {}
 
+    def __deepcopy__(self, memo):  # read-only database: copies of a model keep sharing it (and its device buffers)
+        return self
+
     @property
     def n_sym_mapping(self):
         return {label: obj["n_sym"] for label, obj in self.infos.items()}

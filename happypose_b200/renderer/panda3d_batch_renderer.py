@@ -75,6 +75,9 @@ class Panda3dBatchRenderer:
         self._label_to_mesh_id[obj.label] = ops.mesh_upload(
             self._ctx, verts_m, mesh.faces, normals, mesh.uv, mesh.vcolor, mesh.texture)
 
+    def __deepcopy__(self, memo):  # meshes live in the per-device context: model copies share the renderer
+        return self
+
     @property
     def device(self) -> torch.device:
         return self._ctx.device

@@ -43,14 +43,20 @@ def make_scene(mesh_arrays: Sequence[dict], scales: Sequence[float]) -> OracleSc
     return OracleScene(meshes, points)
 
 
-def cpu_model(model):
-    """Float32 CPU copy of a PosePredictor's torch network + the configuration flags the pipeline reads."""
+def cpu_model(model, net_device="cpu"):
+    """Float32 copy of a PosePredictor's torch network + the configuration flags the pipeline reads.
+
+    net_device: where the (reference, unchanged) torch network is evaluated.  "cpu" = everything on the host (bench
+    baseline, smoke).  The parity tests pass the GPU here: the ResNet is not part of the ported path, and evaluating
+    it with the same cuDNN kernels on both sides makes the comparison measure the kernels under test (raster, crop,
+    pose update) instead of cuDNN-vs-oneDNN summation order, which a random-init ResNet amplifies across iterations.
+    Every other operation of the oracle pipeline stays on the CPU."""
     import copy
     from types import SimpleNamespace
 
-    backbone = copy.deepcopy(model.backbone).cpu().float().eval()
-    heads = {k: copy.deepcopy(h).cpu().float().eval() for k, h in model.heads.items()}
-    ns = SimpleNamespace(backbone=backbone, heads=heads, render_size=tuple(model.render_size))
+    backbone = copy.deepcopy(model.backbone).to(net_device).float().eval()
+    heads = {k: copy.deepcopy(h).to(net_device).float().eval() for k, h in model.heads.items()}
+    ns = SimpleNamespace(backbone=backbone, heads=heads, render_size=tuple(model.render_size), net_device=net_device)
     for k, default in (("input_depth", False), ("render_normals", False), ("render_depth", False), ("n_rendered_views", 1),
                        ("multiview_type", "TCO+front_3views"), ("remove_TCO_rendering", False),
                        ("depth_normalization_type", "none"), ("pose_dim", 9)):
@@ -61,10 +67,10 @@ def cpu_model(model):
 def _net(model, x: np.ndarray) -> Dict[str, np.ndarray]:
     """PosePredictor.net_forward on the CPU in float32 (pose_rigid.py:352-374)."""
     with torch.no_grad():
-        f = model.backbone(torch.as_tensor(x))
+        f = model.backbone(torch.as_tensor(x).to(getattr(model, "net_device", "cpu")))
         if f.dim() == 4:
             f = f.flatten(2).mean(dim=-1)
-        return {k: head(f).numpy() for k, head in model.heads.items()}
+        return {k: head(f).cpu().numpy() for k, head in model.heads.items()}
 
 
 def _render(scene: OracleScene, obj_ids, TCO, K, size, normals, depth, n_threads):
@@ -193,9 +199,7 @@ def cosypose_forward(model, scene: OracleScene, images, K_rows, im_ids, obj_ids,
         crops, K_crop, boxes_rend, boxes_crop = O.crop_inputs(images[:, :3], K_rows, TCO_input, tCR, pts, model.render_size, im_ids=im_ids)
         renders = _render(scene, obj_ids, TCO_input, K_crop, model.render_size, False, False, n_threads)
         x = np.concatenate([crops, renders], 1).astype(np.float32)
-        with torch.no_grad():
-            f = model.backbone(torch.as_tensor(x))
-            pose = model.heads["pose"](f.flatten(2).mean(dim=-1)).numpy()
+        pose = _net(model, x)["pose"]
         if model.pose_dim == 9:
             dR = O.compute_rotation_matrix_from_ortho6d(pose[:, 0:6])
             v = pose[:, 6:9]

