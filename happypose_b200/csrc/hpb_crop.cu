@@ -9,21 +9,21 @@
 // Two kernels:
 //   hpb_crop_boxes_kernel   one CTA per hypothesis: projects the object's point set, reduces min/max, builds
 //                           boxes_rend, boxes_crop and K_crop on the device.
-//   hpb_crop_pixels_kernel  one CTA per (hypothesis, band of output rows).  roi_align's 4x4 bilinear samples per
-//                           output pixel are separable: the 4 row samples and the 4 column samples of a bin are
-//                           folded into dense per-row / per-column tap weights in shared memory (a 2-3 tap span
-//                           when up-sampling, the usual case), so a pixel costs span_y*span_x loads per channel
-//                           instead of 64.  The frame is indexed by im_id: no per-hypothesis copy of the frame
-//                           (the reference materialises images[batch_im_ids], pose_estimator.py:390).
-//                           Stores are coalesced along x.  RGB-D frames also resample the depth-validity map and
+//   hpb_crop_pixels_kernel  one CTA per (hypothesis, band of output rows), one THREAD per output column.  roi_align's
+//                           4x4 bilinear samples per output pixel are separable: the 4 row samples and the 4 column
+//                           samples of a bin fold into dense 4-tap row / column weights; a thread keeps a rolling
+//                           window of horizontally filtered source rows in registers while it marches down its
+//                           column, so a pixel costs ~bin_h * 4 loads per channel instead of 64.  The frame is
+//                           indexed by im_id: no per-hypothesis copy of the frame (the reference materialises
+//                           images[batch_im_ids], pose_estimator.py:390).  Stores are coalesced along x.  RGB-D frames also resample the depth-validity map and
 //                           zero depth where validity < 0.99 (cropping.py:181-195).
 #include "hpb_common.cuh"
 
 namespace {
 
 constexpr int CROP_SPAN = 4;       // dense tap span handled by the fast path
-constexpr int CROP_BAND_MAX = 48;  // most output rows one CTA handles (fewer when the batch is small)
-constexpr int CROP_THREADS = 256;
+constexpr int CROP_BAND_MAX = 64;  // most output rows one CTA handles (fewer when the batch is small)
+constexpr int CROP_MAX_THREADS = 512;  // output widths beyond this take the generic path
 
 struct CropBoxParams {
     const float *points;
@@ -178,16 +178,20 @@ __device__ __forceinline__ bool axis_weights(float start, float bin, int i, int 
     return true;
 }
 
+// One thread per output COLUMN, marching down the band's rows.  roi_align's 4x4 samples per output pixel are separable:
+// the thread keeps its 4 column-tap weights in registers for the whole band, and a rolling window of 4 horizontally
+// filtered source rows (per channel); every output pixel is then a 4-tap vertical combination of the window.  Going
+// down one output row advances the window by floor/ceil(bin_h) source rows, so (when up-sampling, the usual case) a
+// pixel costs < 1 new filtered row = 4 loads per channel, instead of 64 taps per channel.
 template <int C>
-__global__ void __launch_bounds__(CROP_THREADS) hpb_crop_pixels_kernel(const CropPixParams p) {
+__global__ void __launch_bounds__(CROP_MAX_THREADS) hpb_crop_pixels_kernel(const CropPixParams p) {
+    constexpr int NCH = C == 4 ? 5 : C;  // RGB-D: the depth-validity map is resampled as a 5th channel
     const int n = blockIdx.y;
     const int band = p.band;
     const int row0 = blockIdx.x * band;
     const int tid = threadIdx.x;
     extern __shared__ float sm[];
-    float *sWX = sm;                                  // [w][CROP_SPAN]
-    int *sBX = reinterpret_cast<int *>(sWX + (size_t)p.w * CROP_SPAN);  // [w]
-    float *sWY = reinterpret_cast<float *>(sBX + p.w);  // [band][CROP_SPAN]
+    float *sWY = sm;                                             // [band][CROP_SPAN]
     int *sBY = reinterpret_cast<int *>(sWY + band * CROP_SPAN);  // [band]
     __shared__ int sGeneric;
 
@@ -197,21 +201,23 @@ __global__ void __launch_bounds__(CROP_THREADS) hpb_crop_pixels_kernel(const Cro
     const float bin_w = roi_w / (float)p.w, bin_h = roi_h / (float)p.h;
     if (tid == 0) sGeneric = 0;
     __syncthreads();
-    for (int j = tid; j < p.w; j += blockDim.x) {
+    const int rows = min(band, p.h - row0);
+    for (int i = tid; i < rows; i += blockDim.x) {
         float wt[CROP_SPAN];
-        int base;
-        if (!axis_weights(x1, bin_w, j, p.W, base, wt)) sGeneric = 1;
-        sBX[j] = base;
-        *reinterpret_cast<float4 *>(sWX + j * CROP_SPAN) = make_float4(wt[0], wt[1], wt[2], wt[3]);
-    }
-    for (int i = tid; i < band; i += blockDim.x) {
-        float wt[CROP_SPAN] = {0.f, 0.f, 0.f, 0.f};
         int base = 0;
-        if (row0 + i < p.h) {
-            if (!axis_weights(y1, bin_h, row0 + i, p.H, base, wt)) sGeneric = 1;
-        }
+        if (!axis_weights(y1, bin_h, row0 + i, p.H, base, wt)) sGeneric = 1;
         sBY[i] = base;
         *reinterpret_cast<float4 *>(sWY + i * CROP_SPAN) = make_float4(wt[0], wt[1], wt[2], wt[3]);
+    }
+    // column taps of this thread's columns (registers); a span over CROP_SPAN anywhere sends the CTA to the generic path
+    float wx[CROP_SPAN] = {0.f, 0.f, 0.f, 0.f};
+    int bxx = 0;
+    const int j0 = tid;
+    if (j0 < p.w) {
+        if (!axis_weights(x1, bin_w, j0, p.W, bxx, wx)) sGeneric = 1;
+    }
+    for (int j = tid + blockDim.x; j < p.w; j += blockDim.x) {  // only when w > blockDim.x: those columns go generic
+        sGeneric = 1;
     }
     __syncthreads();
     const bool generic = sGeneric != 0;
@@ -219,9 +225,63 @@ __global__ void __launch_bounds__(CROP_THREADS) hpb_crop_pixels_kernel(const Cro
     const float *img = p.images + (size_t)im * C * p.H * p.W;
     float *out = p.crops + (size_t)n * p.crops_bs;
     const size_t plane_in = (size_t)p.H * p.W, plane_out = (size_t)p.h * p.w;
-    const int rows = min(band, p.h - row0);
-    const int npx = rows * p.w;
 
+    if (!generic) {
+        if (j0 >= p.w) return;
+        const int xo0 = min(bxx, p.W - 1), xo1 = min(bxx + 1, p.W - 1), xo2 = min(bxx + 2, p.W - 1), xo3 = min(bxx + 3, p.W - 1);
+        float hwin[CROP_SPAN][NCH];  // horizontally filtered source rows win_base .. win_base+3
+#pragma unroll
+        for (int r = 0; r < CROP_SPAN; ++r)
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) hwin[r][c] = 0.f;
+        int win_base = -0x40000000;
+        auto filter_row = [&](int yy, float (&dst)[NCH]) {
+            const float *src = img + (size_t)min(yy, p.H - 1) * p.W;
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const float *pl = src + c * plane_in;
+                const float v0 = __ldg(pl + xo0), v1 = __ldg(pl + xo1), v2 = __ldg(pl + xo2), v3 = __ldg(pl + xo3);
+                dst[c] = fmaf(wx[3], v3, fmaf(wx[2], v2, fmaf(wx[1], v1, wx[0] * v0)));
+                if (C == 4 && c == 3)
+                    dst[NCH - 1] = fmaf(wx[3], v3 > 0.f ? 1.f : 0.f, fmaf(wx[2], v2 > 0.f ? 1.f : 0.f,
+                                        fmaf(wx[1], v1 > 0.f ? 1.f : 0.f, wx[0] * (v0 > 0.f ? 1.f : 0.f))));
+            }
+        };
+        float *o = out + (size_t)row0 * p.w + j0;
+        for (int i = 0; i < rows; ++i, o += p.w) {
+            const float4 wy = *reinterpret_cast<const float4 *>(sWY + i * CROP_SPAN);
+            float acc[NCH];
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) acc[c] = 0.f;
+            if (wy.x != 0.f || wy.y != 0.f || wy.z != 0.f || wy.w != 0.f) {  // uniform over the CTA
+                const int by = sBY[i];
+                int shift = by - win_base;
+                if (shift < 0 || shift >= CROP_SPAN) {  // (re)fill the whole window
+#pragma unroll
+                    for (int r = 0; r < CROP_SPAN; ++r) filter_row(by + r, hwin[r]);
+                } else {
+                    for (; shift > 0; --shift) {
+#pragma unroll
+                        for (int r = 0; r + 1 < CROP_SPAN; ++r)
+#pragma unroll
+                            for (int c = 0; c < NCH; ++c) hwin[r][c] = hwin[r + 1][c];
+                        filter_row(by - shift + CROP_SPAN, hwin[CROP_SPAN - 1]);
+                    }
+                }
+                win_base = by;
+#pragma unroll
+                for (int c = 0; c < NCH; ++c)
+                    acc[c] = fmaf(wy.w, hwin[3][c], fmaf(wy.z, hwin[2][c], fmaf(wy.y, hwin[1][c], wy.x * hwin[0][c])));
+            }
+            if (C == 4 && acc[NCH - 1] < 0.99f) acc[3] = 0.0f;  // cropping.py:191-195
+#pragma unroll
+            for (int c = 0; c < C; ++c) __stcs(o + c * plane_out, acc[c]);
+        }
+        return;
+    }
+
+    // generic roi_align: 4x4 samples, 4 taps each (heavy down-sampling: crop box wider than ~1.7x the output)
+    const int npx = rows * p.w;
     for (int q = tid; q < npx; q += blockDim.x) {
         const int i = q / p.w, j = q - i * p.w;
         const int oy = row0 + i;
@@ -229,50 +289,21 @@ __global__ void __launch_bounds__(CROP_THREADS) hpb_crop_pixels_kernel(const Cro
 #pragma unroll
         for (int c = 0; c < C; ++c) acc[c] = 0.f;
         float accv = 0.f;
-        if (!generic) {
-            const int by = sBY[i], bxx = sBX[j];
-            const float4 wy4 = *reinterpret_cast<const float4 *>(sWY + i * CROP_SPAN);
-            const float4 wx4 = *reinterpret_cast<const float4 *>(sWX + j * CROP_SPAN);
-            const float wys[CROP_SPAN] = {wy4.x, wy4.y, wy4.z, wy4.w};
-            const float wxs[CROP_SPAN] = {wx4.x, wx4.y, wx4.z, wx4.w};
+        for (int sy = 0; sy < 4; ++sy) {
+            const AxisTap ty = axis_tap(y1 + (float)oy * bin_h + ((float)sy + 0.5f) * bin_h / 4.0f, p.H);
+            if (!ty.valid) continue;
+            for (int sx = 0; sx < 4; ++sx) {
+                const AxisTap tx = axis_tap(x1 + (float)j * bin_w + ((float)sx + 0.5f) * bin_w / 4.0f, p.W);
+                if (!tx.valid) continue;
+                const float w1 = ty.wlo * tx.wlo, w2 = ty.wlo * tx.whi, w3 = ty.whi * tx.wlo, w4 = ty.whi * tx.whi;
 #pragma unroll
-            for (int ky = 0; ky < CROP_SPAN; ++ky) {
-                const float wy = wys[ky];
-                if (wy == 0.0f) continue;
-                const int yy = min(by + ky, p.H - 1);
-#pragma unroll
-                for (int kx = 0; kx < CROP_SPAN; ++kx) {
-                    const float wx = wxs[kx];
-                    if (wx == 0.0f) continue;
-                    const int xx = min(bxx + kx, p.W - 1);
-                    const float wgt = wy * wx;
-                    const float *src = img + (size_t)yy * p.W + xx;
-#pragma unroll
-                    for (int c = 0; c < C; ++c) {
-                        const float v = __ldg(src + c * plane_in);
-                        acc[c] = fmaf(wgt, v, acc[c]);
-                        if (c == 3) accv = fmaf(wgt, v > 0.0f ? 1.0f : 0.0f, accv);
-                    }
-                }
-            }
-        } else {
-            // generic roi_align: 4x4 samples, 4 taps each (heavy down-sampling; rare on this path)
-            for (int sy = 0; sy < 4; ++sy) {
-                const AxisTap ty = axis_tap(y1 + (float)oy * bin_h + ((float)sy + 0.5f) * bin_h / 4.0f, p.H);
-                if (!ty.valid) continue;
-                for (int sx = 0; sx < 4; ++sx) {
-                    const AxisTap tx = axis_tap(x1 + (float)j * bin_w + ((float)sx + 0.5f) * bin_w / 4.0f, p.W);
-                    if (!tx.valid) continue;
-                    const float w1 = ty.wlo * tx.wlo, w2 = ty.wlo * tx.whi, w3 = ty.whi * tx.wlo, w4 = ty.whi * tx.whi;
-#pragma unroll
-                    for (int c = 0; c < C; ++c) {
-                        const float *pl = img + c * plane_in;
-                        const float v1 = __ldg(pl + (size_t)ty.lo * p.W + tx.lo), v2 = __ldg(pl + (size_t)ty.lo * p.W + tx.hi);
-                        const float v3 = __ldg(pl + (size_t)ty.hi * p.W + tx.lo), v4 = __ldg(pl + (size_t)ty.hi * p.W + tx.hi);
-                        acc[c] += 0.0625f * (w1 * v1 + w2 * v2 + w3 * v3 + w4 * v4);
-                        if (c == 3)
-                            accv += 0.0625f * (w1 * (v1 > 0.f) + w2 * (v2 > 0.f) + w3 * (v3 > 0.f) + w4 * (v4 > 0.f));
-                    }
+                for (int c = 0; c < C; ++c) {
+                    const float *pl = img + c * plane_in;
+                    const float v1 = __ldg(pl + (size_t)ty.lo * p.W + tx.lo), v2 = __ldg(pl + (size_t)ty.lo * p.W + tx.hi);
+                    const float v3 = __ldg(pl + (size_t)ty.hi * p.W + tx.lo), v4 = __ldg(pl + (size_t)ty.hi * p.W + tx.hi);
+                    acc[c] += 0.0625f * (w1 * v1 + w2 * v2 + w3 * v3 + w4 * v4);
+                    if (c == 3)
+                        accv += 0.0625f * (w1 * (v1 > 0.f) + w2 * (v2 > 0.f) + w3 * (v3 > 0.f) + w4 * (v4 > 0.f));
                 }
             }
         }
@@ -311,11 +342,11 @@ int hpb_launch_crop_pixels(hpb_ctx *ctx, const float *images, int n_im, int C, i
     int band = CROP_BAND_MAX;
     while (band > 8 && (long long)b * ((h + band - 1) / band) < 2ll * ctx->sm_count) band /= 2;
     p.band = band;
-    const size_t smem = (size_t)w * CROP_SPAN * sizeof(float) + (size_t)w * sizeof(int) +
-                        (size_t)band * CROP_SPAN * sizeof(float) + (size_t)band * sizeof(int);
+    const size_t smem = (size_t)band * CROP_SPAN * sizeof(float) + (size_t)band * sizeof(int);
     dim3 grid((h + band - 1) / band, b);
-    if (C == 3) hpb_crop_pixels_kernel<3><<<grid, CROP_THREADS, smem, stream>>>(p);
-    else if (C == 4) hpb_crop_pixels_kernel<4><<<grid, CROP_THREADS, smem, stream>>>(p);
+    const int threads = w >= CROP_MAX_THREADS ? CROP_MAX_THREADS : ((w + 31) / 32) * 32;  // one thread per output column
+    if (C == 3) hpb_crop_pixels_kernel<3><<<grid, threads, smem, stream>>>(p);
+    else if (C == 4) hpb_crop_pixels_kernel<4><<<grid, threads, smem, stream>>>(p);
     else {
         hpb_set_error("hpb_crop: C must be 3 or 4 (got %d)", C);
         return HPB_EINVAL;

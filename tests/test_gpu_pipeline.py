@@ -258,7 +258,8 @@ def test_pipeline_bf16_runs_and_is_close_to_fp32(models):
     c32, e32 = est32.forward_coarse_model(obs, _add_ids(det))
     assert next(coarse16.backbone.parameters()).dtype == torch.bfloat16
     assert e16["logits"].dtype == torch.float32
-    np.testing.assert_allclose(e16["logits"].cpu().numpy(), e32["logits"].cpu().numpy(), atol=0.15)
+    # bf16 carries 8 mantissa bits (1 ulp at |logit| ~ 13 is 0.0625): a few ulps through 34 layers
+    np.testing.assert_allclose(e16["logits"].cpu().numpy(), e32["logits"].cpu().numpy(), rtol=2e-2, atol=0.1)
     final, extra = est16.run_inference_pipeline(obs, detections=det, n_refiner_iterations=5, n_pose_hypotheses=1)
     assert len(final) == 1 and torch.isfinite(final.poses).all()
 
