@@ -75,6 +75,7 @@ int hpb_destroy(hpb_ctx *ctx) {
     cudaFree(ctx->meshes_dev);
     cudaFree(ctx->vis);
     cudaFree(ctx->vert_scratch);
+    cudaFree(ctx->frame_pack);
     cudaFree(ctx->topk_ws);
     delete ctx;
     return HPB_OK;

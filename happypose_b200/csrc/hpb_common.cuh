@@ -52,6 +52,9 @@ struct hpb_ctx {
     size_t vert_scratch_bytes = 0;
     int max_clusters[4] = {0, 0, 0, 0};  // co-resident clusters of size 1,2,4,8 (queried once per shared-memory size)
     size_t max_clusters_smem = (size_t)-1;
+    // crop workspace: pixel-interleaved copy of the observed frames
+    void *frame_pack = nullptr;
+    size_t frame_pack_bytes = 0;
     // top-k workspace
     void *topk_ws = nullptr;
     size_t topk_ws_bytes = 0;

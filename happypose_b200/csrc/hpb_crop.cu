@@ -22,8 +22,10 @@
 namespace {
 
 constexpr int CROP_SPAN = 4;       // dense tap span handled by the fast path
-constexpr int CROP_BAND_MAX = 64;  // most output rows one CTA handles (fewer when the batch is small)
-constexpr int CROP_MAX_THREADS = 512;  // output widths beyond this take the generic path
+constexpr int CROP_BAND_MAX = 48;
+constexpr int CROP_CHUNK = 8;    // output rows per chunk of the column march
+constexpr int CROP_SROWS = 20;   // filtered source rows staged per chunk (8 rows * bin_h <= 1.9 + 4 taps)  // most output rows one CTA handles (fewer when the batch is small)
+constexpr int CROP_MAX_THREADS = 384;  // output widths beyond this take the generic path
 
 struct CropBoxParams {
     const float *points;
@@ -118,7 +120,24 @@ struct CropPixParams {
     float *crops;
     long long crops_bs;
     int band;  // output rows per CTA
+    const float4 *packed;  // [n_im,H,W] pixel-interleaved copy of `images` (r,g,b,depth|0) or nullptr
 };
+
+// Planar [n_im,C,H,W] -> pixel-interleaved float4 [n_im,H,W]: the crop then fetches all channels of a tap with ONE
+// 16-byte load.  Done per hpb_crop call when few distinct frames serve many hypotheses (the usual case: 1 frame).
+template <int C>
+__global__ void hpb_pack_frames_kernel(const float *images, long long n_px_per_im, long long total, float4 *out) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < total; i += stride) {
+        const long long im = i / n_px_per_im, px = i - im * n_px_per_im;
+        const float *src = images + im * C * n_px_per_im + px;
+        float4 v;
+        v.x = __ldg(src); v.y = __ldg(src + n_px_per_im); v.z = __ldg(src + 2 * n_px_per_im);
+        v.w = C == 4 ? __ldg(src + 3 * n_px_per_im) : 0.0f;
+        out[i] = v;
+    }
+}
 
 // One roi_align sample coordinate along one axis (torchvision roi_align bilinear_interpolate, aligned=False).
 struct AxisTap {
@@ -183,8 +202,8 @@ __device__ __forceinline__ bool axis_weights(float start, float bin, int i, int 
 // filtered source rows (per channel); every output pixel is then a 4-tap vertical combination of the window.  Going
 // down one output row advances the window by floor/ceil(bin_h) source rows, so (when up-sampling, the usual case) a
 // pixel costs < 1 new filtered row = 4 loads per channel, instead of 64 taps per channel.
-template <int C>
-__global__ void __launch_bounds__(CROP_MAX_THREADS) hpb_crop_pixels_kernel(const CropPixParams p) {
+template <int C, bool PACKED>
+__global__ void __launch_bounds__(CROP_MAX_THREADS, 3) hpb_crop_pixels_kernel(const CropPixParams p) {
     constexpr int NCH = C == 4 ? 5 : C;  // RGB-D: the depth-validity map is resampled as a 5th channel
     const int n = blockIdx.y;
     const int band = p.band;
@@ -216,9 +235,7 @@ __global__ void __launch_bounds__(CROP_MAX_THREADS) hpb_crop_pixels_kernel(const
     if (j0 < p.w) {
         if (!axis_weights(x1, bin_w, j0, p.W, bxx, wx)) sGeneric = 1;
     }
-    for (int j = tid + blockDim.x; j < p.w; j += blockDim.x) {  // only when w > blockDim.x: those columns go generic
-        sGeneric = 1;
-    }
+    if (tid + (int)blockDim.x < p.w || p.W < CROP_SPAN) sGeneric = 1;  // more columns than threads / tiny frames: generic path
     __syncthreads();
     const bool generic = sGeneric != 0;
     const int im = p.im_ids[n];
@@ -228,7 +245,27 @@ __global__ void __launch_bounds__(CROP_MAX_THREADS) hpb_crop_pixels_kernel(const
 
     if (!generic) {
         if (j0 >= p.w) return;
-        const int xo0 = min(bxx, p.W - 1), xo1 = min(bxx + 1, p.W - 1), xo2 = min(bxx + 2, p.W - 1), xo3 = min(bxx + 3, p.W - 1);
+        // Re-base the 4 column taps so they are 4 CONSECUTIVE pixels inside the frame: taps clamped to the last column
+        // (roi_align clamps samples in (W-1, W] to W-1) have their weights folded onto that column.  One base pointer
+        // per thread then serves all taps with immediate offsets.
+        {
+            const int over = max(0, bxx + CROP_SPAN - 1 - (p.W - 1));
+            if (over > 0) {
+                float w2[CROP_SPAN] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int k = 0; k < CROP_SPAN; ++k) {
+                    const int jn = min(bxx + k, p.W - 1) - (bxx - over);
+#pragma unroll
+                    for (int q = 0; q < CROP_SPAN; ++q)
+                        if (q == jn) w2[q] += wx[k];
+                }
+#pragma unroll
+                for (int k = 0; k < CROP_SPAN; ++k) wx[k] = w2[k];
+                bxx -= over;
+            }
+        }
+        const int xo0 = bxx, xo1 = bxx + 1, xo2 = bxx + 2, xo3 = bxx + 3;
+        const float4 *col4 = PACKED ? p.packed + (size_t)im * p.H * p.W + xo0 : nullptr;  // taps at col4[0..3]
         float hwin[CROP_SPAN][NCH];  // horizontally filtered source rows win_base .. win_base+3
 #pragma unroll
         for (int r = 0; r < CROP_SPAN; ++r)
@@ -236,6 +273,19 @@ __global__ void __launch_bounds__(CROP_MAX_THREADS) hpb_crop_pixels_kernel(const
             for (int c = 0; c < NCH; ++c) hwin[r][c] = 0.f;
         int win_base = -0x40000000;
         auto filter_row = [&](int yy, float (&dst)[NCH]) {
+            if (PACKED) {
+                const float4 *src = col4 + (size_t)min(yy, p.H - 1) * p.W;
+                const float4 v0 = __ldg(src), v1 = __ldg(src + 1), v2 = __ldg(src + 2), v3 = __ldg(src + 3);
+                dst[0] = fmaf(wx[3], v3.x, fmaf(wx[2], v2.x, fmaf(wx[1], v1.x, wx[0] * v0.x)));
+                dst[1] = fmaf(wx[3], v3.y, fmaf(wx[2], v2.y, fmaf(wx[1], v1.y, wx[0] * v0.y)));
+                dst[2] = fmaf(wx[3], v3.z, fmaf(wx[2], v2.z, fmaf(wx[1], v1.z, wx[0] * v0.z)));
+                if (C == 4) {
+                    dst[3] = fmaf(wx[3], v3.w, fmaf(wx[2], v2.w, fmaf(wx[1], v1.w, wx[0] * v0.w)));
+                    dst[NCH - 1] = fmaf(wx[3], v3.w > 0.f ? 1.f : 0.f, fmaf(wx[2], v2.w > 0.f ? 1.f : 0.f,
+                                        fmaf(wx[1], v1.w > 0.f ? 1.f : 0.f, wx[0] * (v0.w > 0.f ? 1.f : 0.f))));
+                }
+                return;
+            }
             const float *src = img + (size_t)min(yy, p.H - 1) * p.W;
 #pragma unroll
             for (int c = 0; c < C; ++c) {
@@ -334,22 +384,45 @@ int hpb_launch_crop_pixels(hpb_ctx *ctx, const float *images, int n_im, int C, i
                            const float *boxes, int b, int h, int w, float *crops, int64_t crops_bs,
                            cudaStream_t stream) {
     if (b == 0) return HPB_OK;
+    if (C != 3 && C != 4) {
+        hpb_set_error("hpb_crop: C must be 3 or 4 (got %d)", C);
+        return HPB_EINVAL;
+    }
     CropPixParams p;
     p.images = images; p.im_ids = im_ids; p.boxes = boxes;
     p.n_im = n_im; p.C = C; p.H = H; p.W = W; p.b = b; p.h = h; p.w = w;
     p.crops = crops; p.crops_bs = crops_bs;
-    // rows per CTA: enough CTAs to fill the machine for small batches, long bands (column weights amortised) otherwise
+    p.packed = nullptr;
+    // few distinct frames, many hypotheses: interleave the frames once so a tap is one 16-byte load
+    const long long n_px = (long long)H * W, total = n_px * n_im;
+    if ((long long)n_im * 8 <= b && total * 16 <= (1ll << 28)) {
+        if (ctx->frame_pack_bytes < (size_t)total * 16) {
+            if (ctx->frame_pack) HPB_CUDA_OK(cudaFree(ctx->frame_pack));
+            ctx->frame_pack = nullptr;
+            ctx->frame_pack_bytes = 0;
+            HPB_CUDA_OK(cudaMalloc(&ctx->frame_pack, (size_t)total * 16));
+            ctx->frame_pack_bytes = (size_t)total * 16;
+        }
+        const int blocks = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
+        if (C == 3) hpb_pack_frames_kernel<3><<<blocks, 256, 0, stream>>>(images, n_px, total, (float4 *)ctx->frame_pack);
+        else hpb_pack_frames_kernel<4><<<blocks, 256, 0, stream>>>(images, n_px, total, (float4 *)ctx->frame_pack);
+        HPB_CUDA_OK(cudaGetLastError());
+        ctx->launches++;
+        p.packed = (const float4 *)ctx->frame_pack;
+    }
+    // rows per CTA: enough CTAs to fill the machine for small batches, long bands (window fill amortised) otherwise
     int band = CROP_BAND_MAX;
     while (band > 8 && (long long)b * ((h + band - 1) / band) < 2ll * ctx->sm_count) band /= 2;
     p.band = band;
+    const int threads = w >= CROP_MAX_THREADS ? CROP_MAX_THREADS : ((w + 31) / 32) * 32;  // one thread per output column
     const size_t smem = (size_t)band * CROP_SPAN * sizeof(float) + (size_t)band * sizeof(int);
     dim3 grid((h + band - 1) / band, b);
-    const int threads = w >= CROP_MAX_THREADS ? CROP_MAX_THREADS : ((w + 31) / 32) * 32;  // one thread per output column
-    if (C == 3) hpb_crop_pixels_kernel<3><<<grid, threads, smem, stream>>>(p);
-    else if (C == 4) hpb_crop_pixels_kernel<4><<<grid, threads, smem, stream>>>(p);
-    else {
-        hpb_set_error("hpb_crop: C must be 3 or 4 (got %d)", C);
-        return HPB_EINVAL;
+    if (C == 3) {
+        if (p.packed) hpb_crop_pixels_kernel<3, true><<<grid, threads, smem, stream>>>(p);
+        else hpb_crop_pixels_kernel<3, false><<<grid, threads, smem, stream>>>(p);
+    } else {
+        if (p.packed) hpb_crop_pixels_kernel<4, true><<<grid, threads, smem, stream>>>(p);
+        else hpb_crop_pixels_kernel<4, false><<<grid, threads, smem, stream>>>(p);
     }
     HPB_CUDA_OK(cudaGetLastError());
     ctx->launches++;

@@ -2,11 +2,13 @@
 usage: python scripts/ncu_lines.py <both.csv from `ncu -i rep --page source --csv --print-source cuda,sass`> <source file> [top]"""
 import collections, csv, sys
 
-def main(path, srcfile, top=30):
+def main(path, srcfile, top=30, kernel=""):
     rows = list(csv.reader(open(path)))
-    start = [i for i, r in enumerate(rows) if r and r[0] == "Line No"][0]
-    ends = [i for i, r in enumerate(rows) if r and r[0] == "Function Name"]
-    end = ends[1] if len(ends) > 1 else len(rows)
+    fn = [i for i, r in enumerate(rows) if r and r[0] == "Function Name" and kernel in r[1]]
+    first = fn[0] if fn else 0
+    start = [i for i, r in enumerate(rows) if r and r[0] == "Line No" and i > first][0]
+    ends = [i for i, r in enumerate(rows) if r and r[0] == "Function Name" and i > start]
+    end = ends[0] if ends else len(rows)
     hdr = rows[start]
     iS, iI, iT = hdr.index("# Samples"), hdr.index("Instructions Executed"), hdr.index("Thread Instructions Executed")
     agg = collections.defaultdict(lambda: [0, 0, 0])
@@ -31,4 +33,4 @@ def main(path, srcfile, top=30):
         print(f"  L{k:4d} {100*v[0]/totS:5.1f}% smp {100*v[1]/totI:5.1f}% inst thr {v[2]/max(v[1],1):4.1f}  {src[k-1].strip()[:100]}")
 
 if __name__ == "__main__":
-    main(sys.argv[1], sys.argv[2], int(sys.argv[3]) if len(sys.argv) > 3 else 30)
+    main(sys.argv[1], sys.argv[2], int(sys.argv[3]) if len(sys.argv) > 3 else 30, sys.argv[4] if len(sys.argv) > 4 else "")
