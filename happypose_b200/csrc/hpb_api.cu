@@ -21,6 +21,11 @@ int hpb_launch_tco_init(hpb_ctx *ctx, int variant, const float *boxes, const flo
                         cudaStream_t stream);
 int hpb_launch_multiview(hpb_ctx *ctx, const float *TCO, const float *tCR, int b, const float *positions_host,
                          int n_extra, int n_views, int keep_tco, float *out, cudaStream_t stream);
+int hpb_launch_pack_input(hpb_ctx *ctx, const float *x, int64_t bstride, int b, int C, int h, int w, void *out, int Cp,
+                          cudaStream_t stream);
+int hpb_launch_maxpool(hpb_ctx *ctx, const void *in, int b, int H, int W, int C, void *out, cudaStream_t stream);
+int hpb_launch_pack_s2d(hpb_ctx *ctx, const float *x, int64_t bstride, int b, int C, int H, int W, void *out, int Cz,
+                        cudaStream_t stream);
 int hpb_launch_normalize_depth(hpb_ctx *ctx, float *depth, int64_t bstride, const int32_t *chans, int n_planes,
                                const float *tCR, int b, int h, int w, int kind, cudaStream_t stream);
 int hpb_launch_topk(hpb_ctx *ctx, const float *scores, const int32_t *groups, int n, int n_groups, int K,
@@ -364,6 +369,38 @@ int hpb_topk_segmented(hpb_ctx *ctx, const float *scores_dev, const int32_t *gro
     HPB_REQUIRE(n == 0 || (scores_dev && group_ids_dev && out_idx_dev), "NULL pointer");
     HpbDeviceGuard guard(ctx->device);
     return hpb_launch_topk(ctx, scores_dev, group_ids_dev, n, n_groups, K, out_idx_dev, out_count_dev, (cudaStream_t)stream);
+}
+
+int hpb_pack_input_bf16(hpb_ctx *ctx, const float *x_dev, int64_t x_bstride, int b, int C, int h, int w, void *out_dev,
+                        int C_padded, void *stream) {
+    HPB_REQUIRE(ctx && b >= 0 && C > 0 && h > 0 && w > 0, "bad argument");
+    HPB_REQUIRE(C_padded >= C && C_padded % 8 == 0, "C_padded must be a multiple of 8 and >= C");
+    if (b == 0) return HPB_OK;
+    HPB_REQUIRE(x_dev && out_dev, "NULL pointer");
+    HPB_REQUIRE(((uintptr_t)out_dev & 15) == 0, "output must be 16-byte aligned");
+    HpbDeviceGuard guard(ctx->device);
+    return hpb_launch_pack_input(ctx, x_dev, x_bstride, b, C, h, w, out_dev, C_padded, (cudaStream_t)stream);
+}
+
+int hpb_maxpool3x3s2_bf16_nhwc(hpb_ctx *ctx, const void *in_dev, int b, int H, int W, int C, void *out_dev, void *stream) {
+    HPB_REQUIRE(ctx && b >= 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, "bad argument (C must be a multiple of 8)");
+    if (b == 0) return HPB_OK;
+    HPB_REQUIRE(in_dev && out_dev, "NULL pointer");
+    HPB_REQUIRE((((uintptr_t)in_dev | (uintptr_t)out_dev) & 15) == 0, "buffers must be 16-byte aligned");
+    HpbDeviceGuard guard(ctx->device);
+    return hpb_launch_maxpool(ctx, in_dev, b, H, W, C, out_dev, (cudaStream_t)stream);
+}
+
+int hpb_pack_input_s2d_bf16(hpb_ctx *ctx, const float *x_dev, int64_t x_bstride, int b, int C, int H, int W, void *out_dev,
+                            int C_padded, void *stream) {
+    HPB_REQUIRE(ctx && b >= 0 && C > 0 && H > 0 && W > 0, "bad argument");
+    HPB_REQUIRE(H % 2 == 0 && W % 2 == 0, "space-to-depth needs even H and W");
+    HPB_REQUIRE(C_padded >= 4 * C && C_padded % 8 == 0 && C <= 64, "C_padded must be a multiple of 8 and >= 4*C (C <= 64)");
+    if (b == 0) return HPB_OK;
+    HPB_REQUIRE(x_dev && out_dev, "NULL pointer");
+    HPB_REQUIRE(((uintptr_t)out_dev & 15) == 0, "output must be 16-byte aligned");
+    HpbDeviceGuard guard(ctx->device);
+    return hpb_launch_pack_s2d(ctx, x_dev, x_bstride, b, C, H, W, out_dev, C_padded, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -346,3 +346,179 @@ int hpb_launch_normalize_depth(hpb_ctx *ctx, float *depth, int64_t bstride, cons
     ctx->launches++;
     return HPB_OK;
 }
+
+// ------------------------------------------------------------------------------------------------------------------
+// Network-input packing: float32 planar [b,C,h,w] -> bfloat16 pixel-interleaved [b,h,w,Cp] (torch channels_last), the
+// layout cuDNN's tensor-core convolutions consume.  Channels C..Cp-1 are zero.  One thread per pixel: C coalesced plane
+// reads, Cp*2 contiguous bytes written as 16-byte stores.  Rounding = round-to-nearest-even (== torch .to(bfloat16)).
+// Replaces torch's x.to(bfloat16, channels_last) pass plus cuDNN's own channel-padding pass in front of the stem.
+// ------------------------------------------------------------------------------------------------------------------
+#include <cuda_bf16.h>
+
+namespace {
+
+template <int CP>
+__global__ void __launch_bounds__(256) hpb_pack_input_kernel(const float *x, long long bstride, int C, long long npix, long long total,
+                                                              uint4 *out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const long long n = i / npix, px = i - n * npix;
+    const float *src = x + n * bstride + px;
+    __nv_bfloat16 v[CP];
+#pragma unroll
+    for (int c = 0; c < CP; ++c) v[c] = __float2bfloat16_rn(c < C ? __ldcs(src + (long long)c * npix) : 0.0f);
+    uint4 *dst = out + i * (CP / 8);
+#pragma unroll
+    for (int q = 0; q < CP / 8; ++q) {
+        uint4 w;
+        w.x = (unsigned)__bfloat16_as_ushort(v[8 * q]) | ((unsigned)__bfloat16_as_ushort(v[8 * q + 1]) << 16);
+        w.y = (unsigned)__bfloat16_as_ushort(v[8 * q + 2]) | ((unsigned)__bfloat16_as_ushort(v[8 * q + 3]) << 16);
+        w.z = (unsigned)__bfloat16_as_ushort(v[8 * q + 4]) | ((unsigned)__bfloat16_as_ushort(v[8 * q + 5]) << 16);
+        w.w = (unsigned)__bfloat16_as_ushort(v[8 * q + 6]) | ((unsigned)__bfloat16_as_ushort(v[8 * q + 7]) << 16);
+        dst[q] = w;
+    }
+}
+
+}  // namespace
+
+int hpb_launch_pack_input(hpb_ctx *ctx, const float *x, int64_t bstride, int b, int C, int h, int w, void *out, int Cp,
+                          cudaStream_t stream) {
+    if (b == 0) return HPB_OK;
+    const long long npix = (long long)h * w, total = npix * b;
+    const unsigned blocks = (unsigned)((total + 255) / 256);
+    uint4 *o = reinterpret_cast<uint4 *>(out);
+    switch (Cp) {
+        case 8: hpb_pack_input_kernel<8><<<blocks, 256, 0, stream>>>(x, bstride, C, npix, total, o); break;
+        case 16: hpb_pack_input_kernel<16><<<blocks, 256, 0, stream>>>(x, bstride, C, npix, total, o); break;
+        case 24: hpb_pack_input_kernel<24><<<blocks, 256, 0, stream>>>(x, bstride, C, npix, total, o); break;
+        case 32: hpb_pack_input_kernel<32><<<blocks, 256, 0, stream>>>(x, bstride, C, npix, total, o); break;
+        case 40: hpb_pack_input_kernel<40><<<blocks, 256, 0, stream>>>(x, bstride, C, npix, total, o); break;
+        default:
+            hpb_set_error("hpb_pack_input_bf16: padded channel count %d not in {8,16,24,32,40}", Cp);
+            return HPB_EINVAL;
+    }
+    HPB_CUDA_OK(cudaGetLastError());
+    ctx->launches++;
+    return HPB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// 3x3 / stride 2 / pad 1 max-pool on bfloat16 pixel-interleaved (NHWC) activations: the ResNet stem's nn.MaxPool2d(3, 2, 1)
+// (torchvision_resnet.py:215).  Pure streaming op (read 4x what it writes); one thread = 8 channels (one 16-byte vector)
+// of one output pixel, 9 vector loads, packed bf16x2 max (NaN-propagating like torch).  Max is exact, so the result is
+// bit-identical to torch's kernel.
+// ------------------------------------------------------------------------------------------------------------------
+namespace {
+
+__device__ __forceinline__ uint4 bf16x8_max(uint4 a, uint4 b) {
+    uint4 r;
+    __nv_bfloat162 x, y, z;
+#define HPB_MAX_LANE(f)                                    \
+    x = *reinterpret_cast<__nv_bfloat162 *>(&a.f);          \
+    y = *reinterpret_cast<__nv_bfloat162 *>(&b.f);          \
+    z = __hmax2_nan(x, y);                                  \
+    r.f = *reinterpret_cast<unsigned *>(&z);
+    HPB_MAX_LANE(x) HPB_MAX_LANE(y) HPB_MAX_LANE(z) HPB_MAX_LANE(w)
+#undef HPB_MAX_LANE
+    return r;
+}
+
+__global__ void __launch_bounds__(256) hpb_maxpool_kernel(const uint4 *in, int H, int W, int C8, int Ho, int Wo, long long total,
+                                                           uint4 *out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int c = (int)(i % C8);
+    long long t = i / C8;
+    const int ow = (int)(t % Wo);
+    t /= Wo;
+    const int oh = (int)(t % Ho);
+    const long long n = t / Ho;
+    const uint4 *base = in + n * H * W * C8 + c;
+    const unsigned NEG = 0xff80ff80u;  // bf16 -inf pair
+    uint4 m = make_uint4(NEG, NEG, NEG, NEG);
+    const int h0 = 2 * oh - 1, w0 = 2 * ow - 1;
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy) {
+        const int y = h0 + dy;
+        if (y < 0 || y >= H) continue;
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+            const int x = w0 + dx;
+            if (x < 0 || x >= W) continue;
+            m = bf16x8_max(m, __ldg(base + ((long long)y * W + x) * C8));
+        }
+    }
+    out[i] = m;
+}
+
+}  // namespace
+
+int hpb_launch_maxpool(hpb_ctx *ctx, const void *in, int b, int H, int W, int C, void *out, cudaStream_t stream) {
+    if (b == 0) return HPB_OK;
+    const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1, C8 = C / 8;
+    const long long total = (long long)b * Ho * Wo * C8;
+    const unsigned blocks = (unsigned)((total + 255) / 256);
+    hpb_maxpool_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const uint4 *>(in), H, W, C8, Ho, Wo, total,
+                                                   reinterpret_cast<uint4 *>(out));
+    HPB_CUDA_OK(cudaGetLastError());
+    ctx->launches++;
+    return HPB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Space-to-depth network-input packing for the ResNet stem.  A 7x7 / stride 2 / pad 3 convolution over C channels equals
+// a 4x4 / stride 1 / no-pad convolution over 4C channels of z, where z[n, I, J, (r*2+s)*C + c] = xpad[n, c, 2I+r, 2J+s]
+// and xpad is x zero-padded by 3 pixels (w'[o,(r,s,c),a,b] = w[o,c,2a+r,2b+s], zero for tap index 7).  The stride-1 form
+// has a 4x deeper reduction per tap and runs several times faster on the tensor cores than cuDNN's strided 9/27-channel
+// stem.  This kernel builds z (bfloat16, pixel-interleaved, channels padded to Cz with zeros) straight from the float32
+// planar network input the rasteriser / crop kernels wrote: one thread = 8 consecutive channels of one z pixel.
+// ------------------------------------------------------------------------------------------------------------------
+namespace {
+
+__global__ void __launch_bounds__(256) hpb_pack_s2d_kernel(const float *x, long long bstride, int C, int H, int W, int Hz, int Wz,
+                                                            int Cz8, unsigned c_magic, long long total, uint4 *out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int q = (int)(i % Cz8);
+    long long t = i / Cz8;
+    const int J = (int)(t % Wz);
+    t /= Wz;
+    const int I = (int)(t % Hz);
+    const long long n = t / Hz;
+    const float *src = x + n * bstride;
+    const long long plane = (long long)H * W;
+    unsigned short v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const int k = 8 * q + e;
+        const int rs = (int)(((unsigned)k * c_magic) >> 16);  // k / C for k < 4C + 8 <= 65536 / C
+        const int c = k - rs * C;
+        float f = 0.0f;
+        if (rs < 4) {
+            const int y = 2 * I + (rs >> 1) - 3, xx = 2 * J + (rs & 1) - 3;
+            if (y >= 0 && y < H && xx >= 0 && xx < W) f = __ldg(src + c * plane + (long long)y * W + xx);
+        }
+        v[e] = __bfloat16_as_ushort(__float2bfloat16_rn(f));
+    }
+    uint4 w;
+    w.x = (unsigned)v[0] | ((unsigned)v[1] << 16);
+    w.y = (unsigned)v[2] | ((unsigned)v[3] << 16);
+    w.z = (unsigned)v[4] | ((unsigned)v[5] << 16);
+    w.w = (unsigned)v[6] | ((unsigned)v[7] << 16);
+    out[i] = w;
+}
+
+}  // namespace
+
+int hpb_launch_pack_s2d(hpb_ctx *ctx, const float *x, int64_t bstride, int b, int C, int H, int W, void *out, int Cz,
+                        cudaStream_t stream) {
+    if (b == 0) return HPB_OK;
+    const int Hz = H / 2 + 3, Wz = W / 2 + 3, Cz8 = Cz / 8;
+    const long long total = (long long)b * Hz * Wz * Cz8;
+    const unsigned blocks = (unsigned)((total + 255) / 256);
+    const unsigned c_magic = 65535u / (unsigned)C + 1u;
+    hpb_pack_s2d_kernel<<<blocks, 256, 0, stream>>>(x, bstride, C, H, W, Hz, Wz, Cz8, c_magic, total, reinterpret_cast<uint4 *>(out));
+    HPB_CUDA_OK(cudaGetLastError());
+    ctx->launches++;
+    return HPB_OK;
+}

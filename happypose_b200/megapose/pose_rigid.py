@@ -33,6 +33,7 @@ import torch
 from torch import nn
 
 from .. import _capi, ops
+from . import fast_resnet
 from .._capi import Context
 from ..lib3d.rigid_mesh_database import BatchedMeshes
 from ..renderer.panda3d_batch_renderer import Panda3dBatchRenderer
@@ -142,6 +143,7 @@ class PosePredictor(nn.Module):
         self.timing_dict: Dict[str, float] = defaultdict(float)
         self.debug_data = PosePredictorDebugData()
         self._net_ready = False
+        self._folded = None
 
     # ---- properties of the reference -----------------------------------------------------------
     @property
@@ -220,10 +222,16 @@ class PosePredictor(nn.Module):
         return ops.pose_update(self._ctx(), TCO, K_crop, pose_outputs, tCR, _capi.POSE_MEGAPOSE)
 
     def _prepare_net(self, x: torch.Tensor) -> None:
+        """Once, on first use: choose how the (unchanged) torch network is executed.  On CUDA with a reduced-precision
+        compute dtype a torchvision-style ResNet is run through fast_resnet.FoldedResNet (batch-norm folded, fused
+        cuDNN conv+bias+ReLU epilogues, channels_last); anything else runs the module as is."""
         if self._net_ready:
             return
+        self._folded = None
         if x.is_cuda and self.compute_dtype != torch.float32:
-            self.backbone.to(dtype=self.compute_dtype, memory_format=torch.channels_last)
+            self._folded = fast_resnet.try_fold(self.backbone, self.compute_dtype, self._ctx())
+            if self._folded is None:
+                self.backbone.to(dtype=self.compute_dtype, memory_format=torch.channels_last)
             for head in self.heads.values():
                 head.to(dtype=self.compute_dtype)
         self._net_ready = True
@@ -231,9 +239,12 @@ class PosePredictor(nn.Module):
     def net_forward(self, x: torch.Tensor) -> Dict[str, torch.Tensor]:
         """pose_rigid.py:352-374.  The torch backbone runs in bf16/channels_last; head outputs come back float32."""
         self._prepare_net(x)
-        if x.is_cuda and self.compute_dtype != torch.float32:
-            x = x.to(dtype=self.compute_dtype, memory_format=torch.channels_last)
-        x = self.backbone(x)
+        if self._folded is not None:
+            x = self._folded(x)  # packs the fp32 planar input to bf16 NHWC itself (space-to-depth for the 7x7 stem)
+        else:
+            if x.is_cuda and self.compute_dtype != torch.float32:
+                x = x.to(dtype=self.compute_dtype, memory_format=torch.channels_last)
+            x = self.backbone(x)
         if x.dim() == 4:
             x = x.flatten(2).mean(dim=-1)
         elif x.dim() != 2:

@@ -331,6 +331,39 @@ def normalize_depth_(ctx: Context, x: torch.Tensor, channels: Sequence[int], tCR
     return x
 
 
+def pack_input_bf16(ctx: Context, x: torch.Tensor, c_padded: int) -> torch.Tensor:
+    """x [b,C,h,w] float32 (contiguous) -> [b,c_padded,h,w] bfloat16 in channels_last memory, extra channels zero."""
+    dev = ctx.device
+    assert x.is_contiguous() and x.dtype == torch.float32 and x.dim() == 4
+    b, C, h, w = x.shape
+    out = torch.empty((b, c_padded, h, w), dtype=torch.bfloat16, device=dev, memory_format=torch.channels_last)
+    rc = ctx.lib.hpb_pack_input_bf16(ctx.handle, ptr(x), x.stride(0), b, C, h, w, ptr(out), c_padded, stream_ptr(dev))
+    ctx.check(rc, "hpb_pack_input_bf16")
+    return out
+
+
+def pack_input_s2d_bf16(ctx: Context, x: torch.Tensor, c_padded: int) -> torch.Tensor:
+    """x [b,C,H,W] float32 -> z [b,c_padded,H/2+3,W/2+3] bfloat16 channels_last: 2x2 space-to-depth of x zero-padded by 3
+    (see hpb_pack_input_s2d_bf16); a 7x7/s2/p3 convolution of x is a 4x4/s1/p0 convolution of z."""
+    dev = ctx.device
+    assert x.is_contiguous() and x.dtype == torch.float32 and x.dim() == 4
+    b, C, H, W = x.shape
+    out = torch.empty((b, c_padded, H // 2 + 3, W // 2 + 3), dtype=torch.bfloat16, device=dev, memory_format=torch.channels_last)
+    rc = ctx.lib.hpb_pack_input_s2d_bf16(ctx.handle, ptr(x), x.stride(0), b, C, H, W, ptr(out), c_padded, stream_ptr(dev))
+    ctx.check(rc, "hpb_pack_input_s2d_bf16")
+    return out
+
+
+def maxpool3x3s2_bf16(ctx: Context, x: torch.Tensor) -> torch.Tensor:
+    """F.max_pool2d(x, 3, 2, 1) for a bfloat16 channels_last [b,C,H,W] tensor (C % 8 == 0); returns channels_last."""
+    assert x.dtype == torch.bfloat16 and x.dim() == 4 and x.is_contiguous(memory_format=torch.channels_last)
+    b, C, H, W = x.shape
+    out = torch.empty((b, C, (H - 1) // 2 + 1, (W - 1) // 2 + 1), dtype=torch.bfloat16, device=x.device, memory_format=torch.channels_last)
+    rc = ctx.lib.hpb_maxpool3x3s2_bf16_nhwc(ctx.handle, ptr(x), b, H, W, C, ptr(out), stream_ptr(ctx.device))
+    ctx.check(rc, "hpb_maxpool3x3s2_bf16_nhwc")
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 # top-K
 # ------------------------------------------------------------------------------------------------

@@ -180,6 +180,32 @@ int hpb_normalize_depth(hpb_ctx *ctx, float *depth_dev, int64_t bstride, const i
 int hpb_topk_segmented(hpb_ctx *ctx, const float *scores_dev, const int32_t *group_ids_dev, int n, int n_groups,
                        int K, int64_t *out_idx_dev, int32_t *out_count_dev, void *stream);
 
+/*
+ * Network-input packing: float32 planar x_dev [b,C,h,w] (batch stride x_bstride elements) -> bfloat16 pixel-interleaved
+ * out_dev [b,h,w,C_padded] (= a torch channels_last [b,C_padded,h,w] bfloat16 tensor); channels C..C_padded-1 are zero.
+ * This is the hand-off from the kernels above to the (unchanged) torch ResNet run in bf16: it replaces the
+ * torch.cat((images_crop, renders)) + dtype/layout conversion in front of net_forward (pose_rigid.py:352-374, :629).
+ */
+int hpb_pack_input_bf16(hpb_ctx *ctx, const float *x_dev, int64_t x_bstride, int b, int C, int h, int w, void *out_dev,
+                        int C_padded, void *stream);
+
+/*
+ * Space-to-depth variant of hpb_pack_input_bf16 for a 7x7 / stride 2 / pad 3 stem convolution (ResNet conv1,
+ * torchvision_resnet.py:211): out_dev [b, H/2+3, W/2+3, C_padded] bfloat16 with
+ *   out[n, I, J, (r*2+s)*C + c] = xpad[n, c, 2I+r, 2J+s],  xpad = x zero-padded by 3 pixels,  channels 4C.. zero,
+ * so that conv1 becomes a 4x4 / stride 1 / unpadded convolution over 4C channels (same sums, 4x deeper reduction per
+ * tap).  H and W even, C_padded >= 4C and a multiple of 8.
+ */
+int hpb_pack_input_s2d_bf16(hpb_ctx *ctx, const float *x_dev, int64_t x_bstride, int b, int C, int H, int W, void *out_dev,
+                            int C_padded, void *stream);
+
+/*
+ * nn.MaxPool2d(kernel_size=3, stride=2, padding=1) of the ResNet stem (torchvision_resnet.py:215) on bfloat16
+ * pixel-interleaved activations: in_dev [b,H,W,C] -> out_dev [b,(H-1)/2+1,(W-1)/2+1,C], C a multiple of 8.
+ * Bit-identical to torch.nn.functional.max_pool2d (max is exact; NaN propagates).
+ */
+int hpb_maxpool3x3s2_bf16_nhwc(hpb_ctx *ctx, const void *in_dev, int b, int H, int W, int C, void *out_dev, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

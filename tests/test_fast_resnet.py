@@ -1,0 +1,63 @@
+"""CPU: folding batch-norm into the convolutions (fast_resnet.FoldedResNet) is the same eval-mode function as the module."""
+import torch
+
+from happypose_b200.megapose.backbones import make_backbone
+from happypose_b200.megapose.fast_resnet import fold_conv_bn, s2d_reference, s2d_weight, try_fold
+
+
+def _randomise_bn(net, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    for m in net.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.running_mean.copy_(torch.randn(m.running_mean.shape, generator=g) * 0.1)
+            m.running_var.copy_(torch.rand(m.running_var.shape, generator=g) + 0.5)
+            m.weight.data.copy_(torch.rand(m.weight.shape, generator=g) + 0.5)
+            m.bias.data.copy_(torch.randn(m.bias.shape, generator=g) * 0.1)
+
+
+def test_fold_conv_bn_is_exact_affine():
+    torch.manual_seed(0)
+    conv = torch.nn.Conv2d(5, 7, 3, padding=1, bias=False)
+    bn = torch.nn.BatchNorm2d(7).eval()
+    _randomise_bn(bn)
+    w, b = fold_conv_bn(conv, bn)
+    x = torch.randn(2, 5, 9, 11)
+    with torch.no_grad():
+        ref = bn(conv(x))
+        got = torch.nn.functional.conv2d(x, w, b, padding=1)
+    assert torch.allclose(ref, got, atol=1e-5)
+
+
+def test_folded_resnet34_matches_module_fp32():
+    torch.manual_seed(1)
+    for n_in in (9, 27):
+        net = make_backbone("vanilla_resnet34", n_in).eval()
+        _randomise_bn(net, seed=n_in)
+        folded = try_fold(net, torch.float32)
+        assert folded is not None and folded.in_channels == n_in  # no channel padding on the CPU
+        x = torch.randn(2, n_in, 64, 96)
+        with torch.no_grad():
+            ref = net(x)
+            got = folded(x)
+        assert got.shape == ref.shape == (2, 512)
+        assert torch.allclose(ref, got, rtol=1e-3, atol=1e-3 * ref.abs().max().item())
+
+
+def test_try_fold_declines_training_mode_and_other_architectures():
+    net = make_backbone("vanilla_resnet34", 9)
+    assert try_fold(net.train(), torch.float32) is None
+    assert try_fold(make_backbone("resnet18", 6).eval(), torch.float32) is None  # pre-activation WideResNet: run as is
+
+
+def test_space_to_depth_stem_is_the_same_convolution():
+    """7x7 / stride 2 / pad 3 over C channels == 4x4 / stride 1 / pad 0 over the 2x2 space-to-depth of the padded input."""
+    torch.manual_seed(2)
+    for C, H, W in ((9, 24, 32), (27, 16, 20), (3, 8, 8)):
+        w = torch.randn(16, C, 7, 7)
+        b = torch.randn(16)
+        x = torch.randn(2, C, H, W)
+        cz = (4 * C + 7) // 8 * 8
+        ref = torch.nn.functional.conv2d(x, w, b, stride=2, padding=3)
+        got = torch.nn.functional.conv2d(s2d_reference(x, cz), s2d_weight(w, cz), b)
+        assert got.shape == ref.shape == (2, 16, H // 2, W // 2)
+        assert torch.allclose(ref, got, atol=1e-3)

@@ -390,3 +390,58 @@ def test_topk_large_and_ties(ctx):
     big = rs.randn(4608 * 2).astype(np.float32)
     gb = np.repeat(np.arange(2), 4608).astype(np.int32)
     assert (ops.topk_segmented(ctx, big, gb, 2, 7).cpu().numpy() == O.filter_top_k(big, gb, 7)).all()
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# network-input hand-off kernels (bit-exact: bf16 rounding and max are exact operations)
+# ----------------------------------------------------------------------------------------------------------------
+def test_pack_input_bf16_is_bit_exact(ctx):
+    from happypose_b200 import ops
+
+    torch.manual_seed(0)
+    for C, cp in ((9, 16), (27, 32), (3, 8)):
+        x = torch.randn(3, C, 24, 40, device="cuda")
+        got = ops.pack_input_bf16(ctx, x, cp)
+        assert got.shape == (3, cp, 24, 40) and got.is_contiguous(memory_format=torch.channels_last)
+        assert torch.equal(got[:, :C], x.to(torch.bfloat16)) and (got[:, C:] == 0).all()
+
+
+def test_pack_input_s2d_matches_torch_statement(ctx):
+    from happypose_b200 import ops
+    from happypose_b200.megapose.fast_resnet import s2d_reference
+
+    torch.manual_seed(1)
+    for C, H, W, cz in ((9, 240, 320, 64), (27, 16, 24, 128), (6, 10, 14, 24)):
+        x = torch.randn(2, C, H, W, device="cuda")
+        got = ops.pack_input_s2d_bf16(ctx, x, cz)
+        ref = s2d_reference(x, cz).to(torch.bfloat16)
+        assert got.shape == ref.shape == (2, cz, H // 2 + 3, W // 2 + 3)
+        assert torch.equal(got, ref)
+
+
+def test_maxpool_bf16_nhwc_is_bit_exact(ctx):
+    from happypose_b200 import ops
+
+    torch.manual_seed(2)
+    for shape in ((2, 64, 120, 160), (1, 8, 7, 9), (3, 16, 2, 2)):
+        x = torch.randn(shape, device="cuda").to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        got = ops.maxpool3x3s2_bf16(ctx, x)
+        ref = torch.nn.functional.max_pool2d(x, 3, 2, 1)
+        assert got.shape == ref.shape and torch.equal(got, ref)
+
+
+def test_folded_resnet_bf16_close_to_module(ctx):
+    """The shipped executor (BN folded, space-to-depth stem, fused epilogues, libhpb200 max-pool) against the plain module."""
+    from happypose_b200.megapose.backbones import make_backbone
+    from happypose_b200.megapose.fast_resnet import try_fold
+
+    torch.manual_seed(3)
+    net = make_backbone("vanilla_resnet34", 9).cuda().eval()
+    folded = try_fold(net, torch.bfloat16, ctx)
+    assert folded is not None and folded.stem_s2d is not None and folded.fast_pool
+    x = torch.rand(4, 9, 240, 320, device="cuda")
+    with torch.no_grad():
+        ref = net(x)
+        got = folded(x).float()
+    assert got.shape == ref.shape
+    assert (got - ref).abs().max() <= 0.03 * ref.abs().max()  # bf16 end to end

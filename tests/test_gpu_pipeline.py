@@ -256,7 +256,7 @@ def test_pipeline_bf16_runs_and_is_close_to_fp32(models):
     det, _, _ = _detections(1)
     c16, e16 = est16.forward_coarse_model(obs, _add_ids(det))
     c32, e32 = est32.forward_coarse_model(obs, _add_ids(det))
-    assert next(coarse16.backbone.parameters()).dtype == torch.bfloat16
+    assert coarse16._folded is not None and coarse16._folded.dtype == torch.bfloat16  # BN-folded bf16 executor in use
     assert e16["logits"].dtype == torch.float32
     # bf16 carries 8 mantissa bits (1 ulp at |logit| ~ 13 is 0.0625): a few ulps through 34 layers
     np.testing.assert_allclose(e16["logits"].cpu().numpy(), e32["logits"].cpu().numpy(), rtol=2e-2, atol=0.1)
