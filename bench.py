@@ -260,8 +260,7 @@ def run_ours(args):
         refiner.pose_fc.weight.mul_(1e-2)
         refiner.pose_fc.bias.copy_(torch.tensor([1.0, 0, 0, 0, 1, 0, 0, 0, 1]))
     est = PoseEstimator(refiner_model=refiner, coarse_model=coarse, bsz_objects=16, bsz_images=576, SO3_grid_size=M_GRID)
-    if hasattr(est, "use_cuda_graphs"):
-        est.use_cuda_graphs = not args.no_graphs
+    est.use_cuda_graphs = not args.no_graphs
     ctx = coarse._ctx()
 
     n_det = args.dets * world

@@ -201,10 +201,14 @@ __device__ __forceinline__ void look_at(const double pos[3], const double tgt[3]
     R[6] = r[2]; R[7] = f[2]; R[8] = u[2];
 }
 
-__constant__ float c_mv_pos[26 * 3];
+// camera positions of the extra views travel BY VALUE in the kernel parameters: nothing is read from host memory after the
+// launch call returns, so the launch can be captured into a CUDA graph
+struct MvPositions {
+    float p[26 * 3];
+};
 
 __global__ void hpb_multiview_kernel(const float *TCO, const float *tCR, int b, int n_extra, int n_views,
-                                     int keep_tco, float *out) {
+                                     int keep_tco, const MvPositions mv, float *out) {
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= b) return;
     const float *Tf = TCO + (size_t)n * 16;
@@ -239,7 +243,7 @@ __global__ void hpb_multiview_kernel(const float *TCO, const float *tCR, int b, 
     look_at(c0, ref, up, Rp);
     const M4 C0W = m4_rigid_inv(WC0);
     for (int e = 0; e < n_extra; ++e) {
-        const double q[3] = {c_mv_pos[3 * e] * radius, c_mv_pos[3 * e + 1] * radius, c_mv_pos[3 * e + 2] * radius};
+        const double q[3] = {mv.p[3 * e] * radius, mv.p[3 * e + 1] * radius, mv.p[3 * e + 2] * radius};
         const double pos[3] = {c0[0] + Rp[0] * q[0] + Rp[1] * q[1] + Rp[2] * q[2],
                                c0[1] + Rp[3] * q[0] + Rp[4] * q[1] + Rp[5] * q[2],
                                c0[2] + Rp[6] * q[0] + Rp[7] * q[1] + Rp[8] * q[2]};
@@ -323,10 +327,9 @@ int hpb_launch_tco_init(hpb_ctx *ctx, int variant, const float *boxes, const flo
 int hpb_launch_multiview(hpb_ctx *ctx, const float *TCO, const float *tCR, int b, const float *positions_host,
                          int n_extra, int n_views, int keep_tco, float *out, cudaStream_t stream) {
     if (b == 0) return HPB_OK;
-    if (n_extra > 0)
-        HPB_CUDA_OK(cudaMemcpyToSymbolAsync(c_mv_pos, positions_host, sizeof(float) * 3 * n_extra, 0,
-                                            cudaMemcpyHostToDevice, stream));
-    hpb_multiview_kernel<<<(b + 63) / 64, 64, 0, stream>>>(TCO, tCR, b, n_extra, n_views, keep_tco, out);
+    MvPositions mv;
+    for (int i = 0; i < 26 * 3; ++i) mv.p[i] = i < 3 * n_extra ? positions_host[i] : 0.0f;
+    hpb_multiview_kernel<<<(b + 63) / 64, 64, 0, stream>>>(TCO, tCR, b, n_extra, n_views, keep_tco, mv, out);
     HPB_CUDA_OK(cudaGetLastError());
     ctx->launches++;
     return HPB_OK;

@@ -47,6 +47,7 @@ class PoseEstimator(torch.nn.Module):
         bsz_images: int = 256,
         SO3_grid_size: int = 576,
         shard_across_ranks: bool = True,
+        use_cuda_graphs: bool = False,
     ) -> None:
         super().__init__()
         self.coarse_model = coarse_model
@@ -67,11 +68,24 @@ class PoseEstimator(torch.nn.Module):
         else:
             raise ValueError("At least one of refiner_model or  coarse_model must be specified.")
         self.eval()
+        self.use_cuda_graphs = use_cuda_graphs
         self.keep_all_outputs = False
         self.keep_all_coarse_outputs = False
         self.refiner_outputs = None
         self.coarse_outputs = None
         self.debug_dict: dict = {}
+
+    @property
+    def use_cuda_graphs(self) -> bool:
+        """Replay the launch-bound stages (refiner iterations, small scoring batches) as CUDA graphs."""
+        return self._use_cuda_graphs
+
+    @use_cuda_graphs.setter
+    def use_cuda_graphs(self, value: bool) -> None:
+        self._use_cuda_graphs = bool(value)
+        for m in (self.coarse_model, self.refiner_model):
+            if m is not None and hasattr(m, "use_cuda_graphs"):
+                m.use_cuda_graphs = bool(value)
 
     def load_SO3_grid(self, grid_size: int) -> None:
         self._SO3_grid = transform_utils.load_SO3_grid(grid_size).to(device)

@@ -38,6 +38,7 @@ from .._capi import Context
 from ..lib3d.rigid_mesh_database import BatchedMeshes
 from ..renderer.panda3d_batch_renderer import Panda3dBatchRenderer
 from ..renderer.types import Panda3dLightData, Resolution
+from ..utils.cuda_graphs import GraphCache
 from ..utils.timer import CudaTimer, SimpleTimer
 
 
@@ -144,6 +145,10 @@ class PosePredictor(nn.Module):
         self.debug_data = PosePredictorDebugData()
         self._net_ready = False
         self._folded = None
+        # replay launch-bound batches as CUDA graphs (utils/cuda_graphs.py); off by default, PoseEstimator turns it on
+        self.use_cuda_graphs = False
+        self.graph_max_batch = 64
+        self._graphs = GraphCache()
 
     # ---- properties of the reference -----------------------------------------------------------
     @property
@@ -335,10 +340,37 @@ class PosePredictor(nn.Module):
 
     def forward_ids(self, images, K, obj_ids, mesh_ids, im_ids, TCO, n_iterations=1, random_ambient_light=False, labels=None):
         """forward() on device-resident ids (no label lookups): obj_ids index mesh_db.points, mesh_ids the renderer's
-        meshes, im_ids the frames of `images`; K is per row [bsz,3,3]."""
+        meshes, im_ids the frames of `images`; K is per row [bsz,3,3].
+
+        Small batches (the refiner works on a handful of hypotheses, 5 dependent iterations each) are launch-bound:
+        with use_cuda_graphs the whole n_iterations loop is captured once per batch shape and replayed."""
+        bsz = TCO.shape[0]
+        if (self.use_cuda_graphs and TCO.is_cuda and not self.debug and not random_ambient_light and 0 < bsz <= self.graph_max_batch
+                and not torch.cuda.is_current_stream_capturing() and not ops.kernel_timer_active()):
+            tensors = (images.contiguous(), K.contiguous().float(), obj_ids, mesh_ids, im_ids, TCO.contiguous().float())
+
+            def fn(images_, K_, obj_ids_, mesh_ids_, im_ids_, TCO_):
+                return self._forward_ids_impl(images_, K_, obj_ids_, mesh_ids_, im_ids_, TCO_, n_iterations, False, None)
+
+            outputs, replayed = self._graphs.run(("refiner", n_iterations), fn, tensors)
+            if replayed:  # static graph buffers: hand out copies of the small tensors, views of the big ones
+                outputs = {k: self._detach_output(o, labels) for k, o in outputs.items()}
+            return outputs
+        return self._forward_ids_impl(images, K, obj_ids, mesh_ids, im_ids, TCO, n_iterations, random_ambient_light, labels)
+
+    @staticmethod
+    def _detach_output(o: "PosePredictorOutput", labels) -> "PosePredictorOutput":
+        c = lambda t: t.clone()  # noqa: E731
+        return PosePredictorOutput(
+            renders=o.renders, images_crop=o.images_crop,  # views of graph memory, valid until the next replay
+            TCO_input=c(o.TCO_input), TCO_output=c(o.TCO_output), TCV_O_input=c(o.TCV_O_input), tCR=c(o.tCR), labels=labels,
+            K=c(o.K), K_crop=c(o.K_crop), KV_crop=c(o.KV_crop), network_outputs={k: c(v) for k, v in o.network_outputs.items()},
+            boxes_rend=c(o.boxes_rend), boxes_crop=c(o.boxes_crop), renderings_logits=c(o.renderings_logits), timing_dict=o.timing_dict)
+
+    def _forward_ids_impl(self, images, K, obj_ids, mesh_ids, im_ids, TCO, n_iterations, random_ambient_light, labels):
         timing_dict: Dict[str, float] = defaultdict(float)
         if not self.input_depth:
-            images = images[:, self.input_rgb_dims]
+            images = images[:, :3]  # input_rgb_dims = [0, 1, 2]; a slice, not an index tensor (no copy, graph-capturable)
         bsz = TCO.shape[0]
         dtype, device = TCO.dtype, TCO.device
         ctx = self._ctx()
@@ -420,8 +452,24 @@ class PosePredictor(nn.Module):
     def forward_coarse_ids(self, images, K, obj_ids, mesh_ids, im_ids, TCO_input, cuda_timer=False, return_debug_data=False):
         """forward_coarse() on device-resident ids (see forward_ids)."""
         assert self.predict_rendered_views_logits, "Method only valid if coarse classification model"
+        bsz = TCO_input.shape[0]
+        if (self.use_cuda_graphs and TCO_input.is_cuda and not cuda_timer and not return_debug_data and not self.debug
+                and 0 < bsz <= self.graph_max_batch and not torch.cuda.is_current_stream_capturing() and not ops.kernel_timer_active()):
+            tensors = (images.contiguous(), K.contiguous().float(), obj_ids, mesh_ids, im_ids, TCO_input.contiguous().float())
+
+            def fn(images_, K_, obj_ids_, mesh_ids_, im_ids_, TCO_):
+                o = self._forward_coarse_ids_impl(images_, K_, obj_ids_, mesh_ids_, im_ids_, TCO_, False, False)
+                return o["logits"], o["scores"]
+
+            (logits, scores), replayed = self._graphs.run("coarse", fn, tensors)
+            if replayed:
+                logits, scores = logits.clone(), scores.clone()
+            return {"logits": logits, "scores": scores, "time": 0.0, "render_time": 0.0, "model_time": 0.0}
+        return self._forward_coarse_ids_impl(images, K, obj_ids, mesh_ids, im_ids, TCO_input, cuda_timer, return_debug_data)
+
+    def _forward_coarse_ids_impl(self, images, K, obj_ids, mesh_ids, im_ids, TCO_input, cuda_timer, return_debug_data):
         if not self.input_depth:
-            images = images[:, self.input_rgb_dims]
+            images = images[:, :3]  # input_rgb_dims = [0, 1, 2]; a slice, not an index tensor (no copy, graph-capturable)
         bsz = TCO_input.shape[0]
         ctx = self._ctx()
         device = TCO_input.device

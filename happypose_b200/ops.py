@@ -48,6 +48,10 @@ def set_kernel_timer(timer: Optional[KernelTimer]) -> None:
     _kernel_timer = timer
 
 
+def kernel_timer_active() -> bool:
+    return _kernel_timer is not None
+
+
 def _f32(t, device) -> torch.Tensor:
     return torch.as_tensor(t).to(device=device, dtype=torch.float32).contiguous()
 

@@ -16,6 +16,7 @@ coarse, refiner, mesh_db = make_pose_models(ds, device=dev, seed=0)
 with torch.no_grad():
     refiner.pose_fc.weight.mul_(1e-2); refiner.pose_fc.bias.copy_(torch.tensor([1.0, 0, 0, 0, 1, 0, 0, 0, 1]))
 est = PoseEstimator(refiner_model=refiner, coarse_model=coarse, bsz_objects=16, bsz_images=576, SO3_grid_size=576)
+est.use_cuda_graphs = os.environ.get('HPB_GRAPHS', '1') == '1'
 n_det = int(sys.argv[1]) if len(sys.argv) > 1 else 1
 boxes = torch.as_tensor(B.detections_arrays(n_det)).to(dev)
 image = torch.rand(1, 3, 480, 640, device=dev)

@@ -333,3 +333,25 @@ def test_cosypose_pipeline_config2_shape(object_dataset):
     assert "coarse/iteration=1" in preds and "refiner/iteration=4" in preds
     init = est.make_TCO_init(det, obs.K).poses
     assert torch.allclose(init[:, 2, 3], torch.ones(21, device="cuda"))  # TCO_init_from_boxes z_range=(1,1)
+
+
+def test_cuda_graph_replay_matches_eager(models):
+    """use_cuda_graphs: the refiner's 5-iteration loop and small scoring batches replayed as CUDA graphs give the eager result."""
+    from happypose_b200.inference.types import ObservationTensor
+    from happypose_b200.megapose.pose_estimator import PoseEstimator
+
+    coarse, refiner = models[0], models[1]
+    est = PoseEstimator(refiner_model=refiner, coarse_model=coarse, bsz_objects=8, bsz_images=64, SO3_grid_size=72)
+    image = np.random.RandomState(27).rand(1, 3, 480, 640).astype(np.float32)
+    obs = ObservationTensor(torch.as_tensor(image), torch.as_tensor(K_BBQ[None])).cuda()
+    results = []
+    for graphs in (False, True, True):
+        est.use_cuda_graphs = graphs
+        det, _, _ = _detections(2)
+        final, extra = est.run_inference_pipeline(obs, detections=det, n_refiner_iterations=3, n_pose_hypotheses=1)
+        results.append((final.poses.clone(), final.infos["pose_logit"].to_numpy().copy()))
+    est.use_cuda_graphs = False
+    assert refiner._graphs.replays >= 2 and refiner._graphs.captures >= 1
+    for poses, logits in results[1:]:
+        assert torch.allclose(poses, results[0][0], atol=1e-5)
+        np.testing.assert_allclose(logits, results[0][1], rtol=1e-4, atol=1e-4)
