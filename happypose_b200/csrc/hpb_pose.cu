@@ -478,37 +478,84 @@ int hpb_launch_maxpool(hpb_ctx *ctx, const void *in, int b, int H, int W, int C,
 // ------------------------------------------------------------------------------------------------------------------
 namespace {
 
-__global__ void __launch_bounds__(256) hpb_pack_s2d_kernel(const float *x, long long bstride, int C, int H, int W, int Hz, int Wz,
-                                                            int Cz8, unsigned c_magic, long long total, uint4 *out) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    const int q = (int)(i % Cz8);
-    long long t = i / Cz8;
-    const int J = (int)(t % Wz);
-    t /= Wz;
-    const int I = (int)(t % Hz);
-    const long long n = t / Hz;
+constexpr int S2D_THREADS = 256;
+constexpr int S2D_MARGIN = 4;  // zero columns left of x = 0 in the staged rows (needs >= 3; 4 keeps 8-byte stores aligned)
+
+// One CTA = one z row (n, I): the two x rows it draws from (y = 2I-3, 2I-2) are staged in shared memory as bfloat16 for
+// all C channels with coalesced 16-byte loads (each x element is read from HBM exactly once over the whole launch), with
+// zero margins so that the padding of the convolution needs no bounds checks; then every thread emits 16-byte vectors of
+// 8 consecutive z channels, consecutive threads writing consecutive addresses.
+//   staged row index  (r * C + c), plus one all-zero row for the padded channels k >= 4C
+//   staged column     xx + S2D_MARGIN for xx in [-S2D_MARGIN, W + 4)
+__global__ void __launch_bounds__(S2D_THREADS) hpb_pack_s2d_kernel(const float *x, long long bstride, int C, int H, int W, int Hz, int Wz,
+                                                                   int Cz8, int Wp, unsigned c_magic, uint4 *out) {
+    extern __shared__ __align__(16) unsigned short s_rows[];  // [(2C + 1)][Wp]
+    const int I = blockIdx.x;
+    const long long n = blockIdx.y;
+    const int tid = threadIdx.x;
     const float *src = x + n * bstride;
     const long long plane = (long long)H * W;
-    unsigned short v[8];
+    const int n_rows = 2 * C;
+    // ---- zero the margins and the zero row ----
+    {
+        const int right0 = W + S2D_MARGIN, nright = Wp - right0;
+        const int per_row = S2D_MARGIN + nright;
+        for (int i = tid; i < n_rows * per_row; i += S2D_THREADS) {
+            const int row = i / per_row, j = i - row * per_row;
+            s_rows[row * Wp + (j < S2D_MARGIN ? j : right0 + (j - S2D_MARGIN))] = 0;
+        }
+        for (int i = tid; i < Wp; i += S2D_THREADS) s_rows[n_rows * Wp + i] = 0;
+    }
+    // ---- stage the two source rows of every channel (float32 -> bfloat16, round to nearest even) ----
+    const bool vec = (W % 4 == 0) && (bstride % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+    if (vec) {
+        const int W4 = W >> 2;
+        for (int i = tid; i < n_rows * W4; i += S2D_THREADS) {
+            const int row = i / W4, j = i - row * W4;
+            const int r = row / C, c = row - r * C;
+            const int y = 2 * I + r - 3;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (y >= 0 && y < H) v = __ldcs(reinterpret_cast<const float4 *>(src + c * plane + (long long)y * W) + j);
+            const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+            uint2 w2;
+            w2.x = *reinterpret_cast<const unsigned *>(&lo);
+            w2.y = *reinterpret_cast<const unsigned *>(&hi);
+            *reinterpret_cast<uint2 *>(s_rows + row * Wp + S2D_MARGIN + 4 * j) = w2;
+        }
+    } else {
+        for (int i = tid; i < n_rows * W; i += S2D_THREADS) {
+            const int row = i / W, j = i - row * W;
+            const int r = row / C, c = row - r * C;
+            const int y = 2 * I + r - 3;
+            const float f = (y >= 0 && y < H) ? __ldcs(src + c * plane + (long long)y * W + j) : 0.0f;
+            s_rows[row * Wp + S2D_MARGIN + j] = __bfloat16_as_ushort(__float2bfloat16_rn(f));
+        }
+    }
+    __syncthreads();
+    // ---- emit: thread -> fixed channel octet q, strided over J ----
+    const int JT = S2D_THREADS / Cz8;  // z pixels per pass (launcher guarantees Cz8 <= S2D_THREADS)
+    const int q = tid % Cz8, j0 = tid / Cz8;
+    if (j0 >= JT) return;
+    int off[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
         const int k = 8 * q + e;
-        const int rs = (int)(((unsigned)k * c_magic) >> 16);  // k / C for k < 4C + 8 <= 65536 / C
+        const int rs = (int)(((unsigned)k * c_magic) >> 16);  // k / C for k < 4C + 64 <= 65536 / C
         const int c = k - rs * C;
-        float f = 0.0f;
-        if (rs < 4) {
-            const int y = 2 * I + (rs >> 1) - 3, xx = 2 * J + (rs & 1) - 3;
-            if (y >= 0 && y < H && xx >= 0 && xx < W) f = __ldg(src + c * plane + (long long)y * W + xx);
-        }
-        v[e] = __bfloat16_as_ushort(__float2bfloat16_rn(f));
+        off[e] = rs < 4 ? ((rs >> 1) * C + c) * Wp + (rs & 1) - 3 + S2D_MARGIN : n_rows * Wp;
     }
-    uint4 w;
-    w.x = (unsigned)v[0] | ((unsigned)v[1] << 16);
-    w.y = (unsigned)v[2] | ((unsigned)v[3] << 16);
-    w.z = (unsigned)v[4] | ((unsigned)v[5] << 16);
-    w.w = (unsigned)v[6] | ((unsigned)v[7] << 16);
-    out[i] = w;
+    uint4 *dst = out + ((n * Hz + I) * Wz) * Cz8 + q;
+    for (int J = j0; J < Wz; J += JT) {
+        unsigned short v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = s_rows[off[e] + 2 * J];  // 2J <= W + 4 < Wp also inside the zero row
+        uint4 w;
+        w.x = (unsigned)v[0] | ((unsigned)v[1] << 16);
+        w.y = (unsigned)v[2] | ((unsigned)v[3] << 16);
+        w.z = (unsigned)v[4] | ((unsigned)v[5] << 16);
+        w.w = (unsigned)v[6] | ((unsigned)v[7] << 16);
+        __stcs(dst + (long long)J * Cz8, w);
+    }
 }
 
 }  // namespace
@@ -517,10 +564,23 @@ int hpb_launch_pack_s2d(hpb_ctx *ctx, const float *x, int64_t bstride, int b, in
                         cudaStream_t stream) {
     if (b == 0) return HPB_OK;
     const int Hz = H / 2 + 3, Wz = W / 2 + 3, Cz8 = Cz / 8;
-    const long long total = (long long)b * Hz * Wz * Cz8;
-    const unsigned blocks = (unsigned)((total + 255) / 256);
+    if (Cz8 > S2D_THREADS || b > 65535) {
+        hpb_set_error("hpb_pack_input_s2d_bf16: C_padded %d or batch %d too large", Cz, b);
+        return HPB_EINVAL;
+    }
+    // staged row pitch (bf16 elements): W + margins, a multiple of 4 (8-byte stores) with an odd number of 8-byte units so that
+    // consecutive channel rows start in different shared-memory banks
+    int Wp = (W + S2D_MARGIN + 7 + 3) & ~3;
+    if (((Wp / 4) & 1) == 0) Wp += 4;
+    const size_t smem = (size_t)(2 * C + 1) * Wp * sizeof(unsigned short);
+    if (smem > (size_t)ctx->max_smem_optin) {
+        hpb_set_error("hpb_pack_input_s2d_bf16: %d channels x width %d do not fit in shared memory", C, W);
+        return HPB_EINVAL;
+    }
+    HPB_CUDA_OK(cudaFuncSetAttribute(hpb_pack_s2d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const unsigned c_magic = 65535u / (unsigned)C + 1u;
-    hpb_pack_s2d_kernel<<<blocks, 256, 0, stream>>>(x, bstride, C, H, W, Hz, Wz, Cz8, c_magic, total, reinterpret_cast<uint4 *>(out));
+    dim3 grid(Hz, b);
+    hpb_pack_s2d_kernel<<<grid, S2D_THREADS, smem, stream>>>(x, bstride, C, H, W, Hz, Wz, Cz8, Wp, c_magic, reinterpret_cast<uint4 *>(out));
     HPB_CUDA_OK(cudaGetLastError());
     ctx->launches++;
     return HPB_OK;

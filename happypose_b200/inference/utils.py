@@ -17,7 +17,13 @@ def add_instance_id(inputs: PandasTensorCollection) -> PandasTensorCollection:
     if "instance_id" in inputs.infos:
         return inputs
     df = inputs.infos
-    df["instance_id"] = df.groupby(["batch_im_id", "label"], sort=False).cumcount().to_numpy()
+    # cumcount of (batch_im_id, label) in row order, without a GroupBy object (this runs once per frame on the hot path)
+    seen: dict = {}
+    inst = np.empty(len(df), np.int64)
+    for i, key in enumerate(zip(df["batch_im_id"].tolist(), df["label"].tolist())):
+        inst[i] = seen.get(key, 0)
+        seen[key] = inst[i] + 1
+    df["instance_id"] = inst
     inputs.infos = df
     return inputs
 

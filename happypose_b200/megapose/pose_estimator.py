@@ -91,9 +91,18 @@ class PoseEstimator(torch.nn.Module):
         self._SO3_grid = transform_utils.load_SO3_grid(grid_size).to(device)
 
     # ------------------------------------------------------------------------------------------
-    def _row_ids(self, model, df: pd.DataFrame, dev) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
-        """(mesh-db ids, renderer mesh ids, frame ids) of every row, as int32 device tensors.  Labels are resolved
-        once per distinct label (KeyError on unknown labels, like mesh_db.select / the renderer)."""
+    def _row_ids(self, model, data, dev) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """(mesh-db ids, renderer mesh ids, frame ids) of every row, as int32 device tensors.  `data` is a
+        PandasTensorCollection (its device-resident row tensors are used when a previous stage attached them) or a
+        DataFrame.  Labels are resolved once per distinct label (KeyError on unknown labels, like mesh_db.select / the
+        renderer)."""
+        if isinstance(data, PandasTensorCollection):
+            rt = data.row_tensors
+            if all(k in rt for k in ("obj_ids", "mesh_ids", "im_ids")):
+                return rt["obj_ids"].to(dev), rt["mesh_ids"].to(dev), rt["im_ids"].to(dev)
+            df = data.infos
+        else:
+            df = data
         labels = df["label"].to_numpy()
         uniq, inv = np.unique(labels, return_inverse=True)
         db = np.array([model.mesh_db.label_to_id[u] for u in uniq], np.int32)[inv]
@@ -126,8 +135,7 @@ class PoseEstimator(torch.nn.Module):
         model = self.refiner_model
         dev = observation.images.device
         B = data_TCO_input.poses.shape[0]
-        df = data_TCO_input.infos
-        obj_ids, mesh_ids, im_ids = self._row_ids(model, df, dev)
+        obj_ids, mesh_ids, im_ids = self._row_ids(model, data_TCO_input, dev)
         K_rows = observation.K[im_ids.long()]
         lo, hi = self._my_rows(B, self.shard_across_ranks)
 
@@ -145,7 +153,8 @@ class PoseEstimator(torch.nn.Module):
             timer_.start()
             outputs_ = model.forward_ids(
                 observation.images, K_rows[s:e], obj_ids[s:e], mesh_ids[s:e], im_ids[s:e], data_TCO_input.poses[s:e],
-                n_iterations=n_iterations, labels=df["label"].iloc[s:e].tolist(), **refiner_kwargs)
+                n_iterations=n_iterations, labels=data_TCO_input.infos["label"].iloc[s:e].tolist() if keep_all_outputs else None,
+                **refiner_kwargs)
             timer_.stop()
             model_time += timer_.elapsed()
             if keep_all_outputs:
@@ -155,9 +164,14 @@ class PoseEstimator(torch.nn.Module):
                 for k, v in zip(keys, (o.TCO_output, o.TCO_input, o.K_crop, o.K, o.boxes_rend, o.boxes_crop)):
                     chunks[n][k].append(v)
 
-        infos = df.copy()
-        infos["refiner_batch_idx"] = batch_idx_col
-        infos["refiner_instance_idx"] = inst_idx_col
+        def make_infos(cache=[]):  # one frame shared by all iterations, built when first looked at
+            if not cache:
+                cache.append(data_TCO_input.infos.assign(refiner_batch_idx=batch_idx_col, refiner_instance_idx=inst_idx_col))
+            return cache[0]
+
+        row_tensors = {"obj_ids": obj_ids, "mesh_ids": mesh_ids, "im_ids": im_ids}
+        if "group_ids" in data_TCO_input.row_tensors:
+            row_tensors["group_ids"] = data_TCO_input.row_tensors["group_ids"]
         preds = {}
         for n in range(1, n_iterations + 1):
             tensors = {}
@@ -167,7 +181,8 @@ class PoseEstimator(torch.nn.Module):
                 local = torch.cat(parts, dim=0) if parts else torch.zeros((0,) + shape_tail, device=dev)
                 sharded = hdist.is_distributed() and self.shard_across_ranks
                 tensors[k] = hdist.all_gather_rows(local.contiguous(), B) if sharded else local
-            preds[f"iteration={n}"] = PandasTensorCollection(infos, **tensors)
+            preds[f"iteration={n}"] = PandasTensorCollection(make_infos, n_rows=B, row_tensors=row_tensors, **tensors)
+            preds[f"iteration={n}"].meta.update(data_TCO_input.meta)
 
         elapsed = time.time() - start_time
         extra_data = {"n_iterations": n_iterations, "outputs": all_outputs, "model_time": model_time, "time": elapsed}
@@ -175,13 +190,13 @@ class PoseEstimator(torch.nn.Module):
         return preds, extra_data
 
     # ------------------------------------------------------------------------------------------
-    def _score_rows(self, observation, df, TCO, cuda_timer, return_debug_data):
+    def _score_rows(self, observation, ids, TCO, cuda_timer, return_debug_data):
         """Shared by the coarse and scoring stages: forward_coarse over batches of bsz_images rows of this rank's
         slice, then all-gather.  Returns (logits [n], scores [n], render_time, model_time, n_batches, debug)."""
         model = self.coarse_model
         dev = observation.images.device
         n = TCO.shape[0]
-        obj_ids, mesh_ids, im_ids = self._row_ids(model, df, dev)
+        obj_ids, mesh_ids, im_ids = ids
         K_rows = observation.K[im_ids.long()]
         lo, hi = self._my_rows(n, self.shard_across_ranks)
         logits_l, scores_l, crops_l, renders_l = [], [], [], []
@@ -223,19 +238,24 @@ class PoseEstimator(torch.nn.Module):
         """Scores the estimates with the coarse model; adds pose_logit / pose_score (pose_estimator.py:223-325)."""
         start_time = time.time()
         assert self.coarse_model is not None
-        df = data_TCO.infos
+        n = len(data_TCO)
+        ids = self._row_ids(self.coarse_model, data_TCO, observation.images.device)
         logits, scores, render_time, model_time, n_batches, debug_data = self._score_rows(
-            observation, df, data_TCO.poses, cuda_timer, return_debug_data)
-        host = torch.stack([logits.reshape(len(df), -1)[:, 0], scores.reshape(len(df), -1)[:, 0]]).cpu().numpy()
-        df["pose_logit"] = host[0]
-        df["pose_score"] = host[1]
+            observation, ids, data_TCO.poses, cuda_timer, return_debug_data)
+        both = torch.stack([logits.reshape(n, -1)[:, 0], scores.reshape(n, -1)[:, 0]])
+
+        def add_scores(df, both=both):  # the stage's single D2H copy, taken when the frame is looked at
+            host = both.cpu().numpy()
+            return df.assign(pose_logit=host[0], pose_score=host[1])
+
+        data_TCO.map_infos(add_scores)  # in place, like the reference (df["pose_logit"] = ...; data_TCO.infos = df)
+
         elapsed = time.time() - start_time
         timing_str = f"time: {elapsed:.2f}, model_time: {model_time:.2f}, render_time: {render_time:.2f}"
         extra_data = {
             "render_time": render_time, "model_time": model_time, "time": elapsed, "logits": logits, "scores": scores,
             "debug": debug_data, "n_batches": n_batches, "timing_str": timing_str,
         }
-        data_TCO.infos = df
         return data_TCO, extra_data
 
     @torch.no_grad()
@@ -255,25 +275,27 @@ class PoseEstimator(torch.nn.Module):
         B = len(detections)
         M = SO3_grid.shape[0]
 
-        # every detection row repeated M times, with hypothesis_id / bbox_id columns (:351-362), vectorised
+        # every detection row repeated M times, with hypothesis_id / bbox_id columns (:351-362).  The row ids the kernels
+        # need are built on the device from B-sized host arrays; the B*M-row DataFrame itself is deferred (make_infos).
         df = detections.infos
-        df_hypotheses = df.loc[df.index.repeat(M)].copy()
-        df_hypotheses["hypothesis_id"] = np.tile(np.arange(M), B)
-        df_hypotheses["bbox_id"] = np.repeat(df.index.to_numpy(), M)
-        df_hypotheses = df_hypotheses.reset_index(drop=True)
-
-        bbox_ids = torch.as_tensor(df_hypotheses["bbox_id"].to_numpy()).to(dev)
-        m_idx = torch.as_tensor(df_hypotheses["hypothesis_id"].to_numpy()).to(dev)
-        bboxes = detections.bboxes.to(dev)[bbox_ids].float()
-        obj_ids, _, im_ids = self._row_ids(coarse_model, df_hypotheses, dev)
+        obj_ids_d, mesh_ids_d, im_ids_d = self._row_ids(coarse_model, detections, dev)
+        rep = torch.arange(B, device=dev).repeat_interleave(M)            # row -> detection position
+        m_idx = torch.arange(M, device=dev).repeat(B)                     # row -> grid rotation
+        obj_ids, mesh_ids, im_ids = obj_ids_d[rep].contiguous(), mesh_ids_d[rep].contiguous(), im_ids_d[rep].contiguous()
+        bboxes = detections.bboxes.to(dev)[rep].float()
         K_rows = observation.K[im_ids.long()]
+        # groups of the later top-K = (batch_im_id, label, instance_id); computed on the B detection rows
+        det_groups_np = tc.group_ids_from_columns(df, ["batch_im_id", "label", "instance_id"])
+        n_groups = int(det_groups_np.max()) + 1
+        det_groups = torch.as_tensor(det_groups_np).to(dev)
+        row_tensors = {"obj_ids": obj_ids, "mesh_ids": mesh_ids, "im_ids": im_ids, "group_ids": det_groups[rep].contiguous()}
         # initial poses of ALL rows on every rank (cheap; lets the top-K be replicated without exchanging poses)
         TCO = ops.tco_init(
             coarse_model._ctx(), _capi.TCO_INIT_AUTODEPTH_WITH_R, bboxes, K_rows, coarse_model.mesh_db.points, obj_ids,
             SO3_grid[m_idx])
 
         logits, scores, render_time, model_time, n_batches, dbg = self._score_rows(
-            observation, df_hypotheses, TCO, cuda_timer, return_debug_data)
+            observation, (obj_ids, mesh_ids, im_ids), TCO, cuda_timer, return_debug_data)
         logits = logits.reshape([B, M])
         scores = scores.reshape([B, M])
         debug_data = {}
@@ -281,16 +303,23 @@ class PoseEstimator(torch.nn.Module):
             H, W = dbg["images_crop"].shape[2:]
             debug_data = {"images_crop": dbg["images_crop"].reshape([B, M, -1, H, W]), "renders": dbg["renders"].reshape([B, M, -1, H, W])}
 
-        host = torch.stack([logits.flatten(), scores.flatten()]).cpu().numpy()  # the stage's single D2H copy
-        df_hypotheses["coarse_logit"] = host[0]
-        df_hypotheses["coarse_score"] = host[1]
+        both = torch.stack([logits.flatten(), scores.flatten()])
+
+        def make_infos(df=df, both=both):
+            host = both.cpu().numpy()  # the stage's single D2H copy, taken when the frame is looked at
+            pos = np.repeat(np.arange(B), M)
+            df_h = df.iloc[pos].reset_index(drop=True)
+            return df_h.assign(hypothesis_id=np.tile(np.arange(M), B), bbox_id=np.repeat(df.index.to_numpy(), M),
+                               coarse_logit=host[0], coarse_score=host[1])
+
         elapsed = time.time() - start_time
         timing_str = f"time: {elapsed:.2f}, model_time: {model_time:.2f}, render_time: {render_time:.2f}"
         extra_data = {
             "render_time": render_time, "model_time": model_time, "time": elapsed, "logits": logits, "scores": scores,
             "TCO": TCO.reshape([B, M, 4, 4]), "debug": debug_data, "n_batches": n_batches, "timing_str": timing_str,
         }
-        data_TCO = PandasTensorCollection(df_hypotheses, poses=TCO, bboxes=bboxes)
+        data_TCO = PandasTensorCollection(make_infos, n_rows=B * M, row_tensors=row_tensors, poses=TCO, bboxes=bboxes)
+        data_TCO.meta.update({"group_cols": ["batch_im_id", "label", "instance_id"], "n_groups": n_groups, "min_group_size": M})
         return data_TCO, extra_data
 
     # ------------------------------------------------------------------------------------------

@@ -371,9 +371,10 @@ def maxpool3x3s2_bf16(ctx: Context, x: torch.Tensor) -> torch.Tensor:
 # ------------------------------------------------------------------------------------------------
 # top-K
 # ------------------------------------------------------------------------------------------------
-def topk_segmented(ctx: Context, scores, group_ids, n_groups: int, K: int) -> torch.Tensor:
+def topk_segmented(ctx: Context, scores, group_ids, n_groups: int, K: int, expected_count: Optional[int] = None) -> torch.Tensor:
     """Row indices (int64, on device) kept by filter_top_pose_estimates, in global descending score order.
-    The single host sync is reading the survivor count, which sizes the result."""
+    The single host sync is reading the survivor count, which sizes the result; a caller that knows the count (every
+    group has at least K rows => n_groups * K) passes `expected_count` and nothing is read back."""
     dev = ctx.device
     s = _f32(scores, dev).reshape(-1)
     g = _i32(group_ids, dev).reshape(-1)
@@ -384,4 +385,7 @@ def topk_segmented(ctx: Context, scores, group_ids, n_groups: int, K: int) -> to
     cnt = torch.zeros((1,), dtype=torch.int32, device=dev)
     rc = ctx.lib.hpb_topk_segmented(ctx.handle, ptr(s), ptr(g), n, n_groups, K, ptr(out), ptr(cnt), stream_ptr(dev))
     ctx.check(rc, "hpb_topk_segmented")
+    if expected_count is not None:
+        assert 0 <= expected_count <= cap
+        return out[:expected_count]
     return out[: int(cnt.item())]

@@ -6,7 +6,7 @@ but selects on the GPU with the segmented top-K kernel instead of pandas sort_va
 """
 from __future__ import annotations
 
-from typing import List
+from typing import List, Optional
 
 import numpy as np
 import pandas as pd
@@ -88,10 +88,71 @@ class TensorCollection:
 
 
 class PandasTensorCollection(TensorCollection):
-    def __init__(self, infos: pd.DataFrame, **tensors):
+    """`infos` DataFrame + row-aligned tensors (tensor_collection.py:129-198).
+
+    Two additions that keep the device pipeline free of host synchronisation (the public behaviour is unchanged):
+      * `infos` may be given as a zero-argument callable (+ `n_rows`): the DataFrame is then built on first access.  The
+        stages of PoseEstimator.run_inference_pipeline chain such deferred frames, so all pandas work (and the
+        device->host copies of scores / survivor indices it needs) happens after every kernel has been enqueued.
+      * `row_tensors`: private row-aligned device tensors (mesh ids, frame ids, group ids) that follow the rows through
+        __getitem__ without appearing in `.tensors`; they spare the stages the label -> id look-ups through pandas.
+    """
+
+    def __init__(self, infos, n_rows: Optional[int] = None, row_tensors: Optional[dict] = None, **tensors):
         super().__init__(**tensors)
-        self.infos = infos.reset_index(drop=True)
-        self.meta = {}
+        self.__dict__["_infos"] = None
+        self.__dict__["_infos_thunk"] = None
+        self.__dict__["_n_rows"] = None
+        self.__dict__["_row_tensors"] = dict(row_tensors) if row_tensors else {}
+        if callable(infos) and not isinstance(infos, pd.DataFrame):
+            assert n_rows is not None, "a deferred infos frame needs n_rows"
+            self.__dict__["_infos_thunk"] = infos
+            self.__dict__["_n_rows"] = int(n_rows)
+        else:
+            self.__dict__["_infos"] = infos.reset_index(drop=True)
+        self.__dict__["meta"] = {}
+
+    # -- deferred DataFrame -----------------------------------------------------------------------
+    @property
+    def infos(self) -> pd.DataFrame:
+        if self.__dict__["_infos"] is None:
+            thunk = self.__dict__["_infos_thunk"]
+            df = thunk().reset_index(drop=True)
+            assert len(df) == self.__dict__["_n_rows"], (len(df), self.__dict__["_n_rows"])
+            self.__dict__["_infos"] = df
+            self.__dict__["_infos_thunk"] = None
+        return self.__dict__["_infos"]
+
+    @infos.setter
+    def infos(self, df: pd.DataFrame) -> None:
+        self.__dict__["_infos"] = df
+        self.__dict__["_infos_thunk"] = None
+        self.__dict__["_n_rows"] = None
+
+    def __setattr__(self, name, value):
+        if name == "infos":
+            PandasTensorCollection.infos.fset(self, value)
+        else:
+            super().__setattr__(name, value)
+
+    def map_infos(self, fn) -> None:
+        """In-place, deferred `self.infos = fn(self.infos)` (the row count must not change)."""
+        if self.infos_ready:
+            old, n = self.__dict__["_infos"], len(self.__dict__["_infos"])
+            source = lambda: old  # noqa: E731
+        else:
+            source, n = self.__dict__["_infos_thunk"], self.__dict__["_n_rows"]
+        self.__dict__["_infos"] = None
+        self.__dict__["_infos_thunk"] = lambda: fn(source().reset_index(drop=True))
+        self.__dict__["_n_rows"] = n
+
+    @property
+    def infos_ready(self) -> bool:
+        return self.__dict__["_infos"] is not None
+
+    @property
+    def row_tensors(self) -> dict:
+        return self.__dict__["_row_tensors"]
 
     def merge_df(self, df, *args, **kwargs):
         infos = self.infos.merge(df, how="left", *args, **kwargs)
@@ -100,22 +161,38 @@ class PandasTensorCollection(TensorCollection):
         return PandasTensorCollection(infos=infos, **self.tensors)
 
     def clone(self):
-        return PandasTensorCollection(self.infos.copy(), **super().clone().tensors)
+        return PandasTensorCollection(self.infos.copy(), row_tensors=self.row_tensors, **super().clone().tensors)
+
+    def to(self, torch_attr):
+        super().to(torch_attr)
+        if isinstance(torch_attr, (str, torch.device)):  # ids follow device moves, not dtype casts
+            for k, t in self.row_tensors.items():
+                self.row_tensors[k] = t.to(torch_attr)
+        return self
 
     def __repr__(self):
         body = "".join(f"    {k}: {t.shape} {t.dtype} {t.device},\n" for k, t in self._tensors.items())
         return f"{self.__class__.__name__}(\n{body}{'-' * 40}\n    infos:\n{self.infos!r}\n)"
 
     def __getitem__(self, ids):
+        tensors = super().__getitem__(ids).tensors
         if isinstance(ids, torch.Tensor):
-            rows = ids.detach().cpu().numpy()
-        else:
-            rows = ids
-        infos = self.infos.iloc[rows].reset_index(drop=True)
-        return PandasTensorCollection(infos, **super().__getitem__(ids).tensors)
+            rt = {k: t[ids.to(t.device)] for k, t in self.row_tensors.items()}
+            if ids.dtype != torch.bool:
+                # deferred: the index tensor is read back only when somebody looks at the frame
+                parent = self
+                return PandasTensorCollection(lambda: parent.infos.iloc[ids.detach().cpu().numpy()], n_rows=int(ids.numel()),
+                                              row_tensors=rt, **tensors)
+            return PandasTensorCollection(self.infos.iloc[ids.detach().cpu().numpy()], row_tensors=rt, **tensors)
+        rt = {}
+        if self.row_tensors:
+            idx = torch.as_tensor(np.asarray(ids))
+            rt = {k: t[idx.to(t.device)] for k, t in self.row_tensors.items()}
+        return PandasTensorCollection(self.infos.iloc[ids], row_tensors=rt, **tensors)
 
     def __len__(self):
-        return len(self.infos)
+        n = self.__dict__["_n_rows"]
+        return n if (n is not None and not self.infos_ready) else len(self.infos)
 
     def gather_distributed(self, tmp_dir=None):
         """Reference: pickle files in tmp_dir + barriers (tensor_collection.py:166-187).  Here: all_gather_object
@@ -132,7 +209,7 @@ class PandasTensorCollection(TensorCollection):
 
     def __setstate__(self, state):
         self.__init__(state["infos"], **state["tensors"])
-        self.meta = state["meta"]
+        self.__dict__["meta"] = state["meta"]
 
 
 def concatenate(datas):
@@ -147,10 +224,15 @@ def concatenate(datas):
 
 
 def group_ids_from_columns(df: pd.DataFrame, group_cols: List[str]) -> np.ndarray:
-    """Dense int32 group id per row for the (batch_im_id, label, instance_id)-style grouping."""
+    """Dense int32 group id per row for the (batch_im_id, label, instance_id)-style grouping (first-appearance order,
+    like groupby(sort=False).ngroup(), without building a GroupBy object: one factorize per column)."""
     if len(df) == 0:
         return np.zeros((0,), np.int32)
-    return df.groupby(group_cols, sort=False).ngroup().to_numpy().astype(np.int32)
+    key = np.zeros(len(df), np.int64)
+    for c in group_cols:
+        codes, uniques = pd.factorize(df[c].to_numpy(), use_na_sentinel=False)
+        key = key * max(len(uniques), 1) + codes
+    return pd.factorize(key)[0].astype(np.int32)
 
 
 def filter_top_pose_estimates(
@@ -165,21 +247,36 @@ def filter_top_pose_estimates(
 
     The selection runs on the GPU (hpb_topk_segmented); `scores_device` lets the caller pass the logits that are
     already resident on the device instead of the DataFrame column.  Ties: lowest row index first.
+
+    When the collection carries device-resident group ids (row_tensors["group_ids"] + meta["n_groups"],
+    meta["min_group_size"], set by PoseEstimator) and scores_device is given, nothing is read back to the host: the
+    survivor count is n_groups * top_K (every group has at least top_K rows) and the result's `infos` is deferred.
     """
     from .. import ops
     from .._capi import Context
 
-    df = data_TCO.infos
-    if len(df) == 0:
+    if len(data_TCO) == 0:
         return data_TCO
-    groups = group_ids_from_columns(df, group_cols)
-    n_groups = int(groups.max()) + 1
     device = data_TCO.device if len(data_TCO.tensors) > 0 else torch.device("cuda")
     ctx = Context.get(device)
+    groups_dev = data_TCO.row_tensors.get("group_ids") if group_cols == data_TCO.meta.get("group_cols") else None
+    expected = None
+    if groups_dev is not None and scores_device is not None:
+        groups = groups_dev
+        n_groups = int(data_TCO.meta["n_groups"])
+        if int(data_TCO.meta.get("min_group_size", 0)) >= int(top_K):
+            expected = n_groups * int(top_K)
+    else:
+        df = data_TCO.infos
+        groups = torch.as_tensor(group_ids_from_columns(df, group_cols))
+        n_groups = int(groups.max()) + 1
     if scores_device is None:
-        scores_device = torch.as_tensor(df[filter_field].to_numpy(dtype=np.float32))
+        scores_device = torch.as_tensor(data_TCO.infos[filter_field].to_numpy(dtype=np.float32))
     scores_device = scores_device.reshape(-1).to(ctx.device, torch.float32)
     if ascending:
         scores_device = -scores_device
-    keep = ops.topk_segmented(ctx, scores_device, torch.as_tensor(groups), n_groups, int(top_K))
-    return data_TCO[keep.to(device)]
+    keep = ops.topk_segmented(ctx, scores_device, groups, n_groups, int(top_K), expected_count=expected)
+    out = data_TCO[keep.to(device)]
+    if groups_dev is not None:
+        out.meta.update({"group_cols": group_cols, "n_groups": n_groups, "min_group_size": min(int(top_K), int(data_TCO.meta.get("min_group_size", 0)))})
+    return out
