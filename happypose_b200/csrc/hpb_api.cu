@@ -3,7 +3,9 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <algorithm>
 #include <new>
+#include <utility>
 
 #include "hpb_common.cuh"
 
@@ -38,6 +40,95 @@ void hpb_set_error(const char *fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
+}
+
+
+// Sign of the screen-space area2 of FRONT faces if the mesh is a closed, consistently oriented surface, else 0.
+// Vertices are welded by exact position (texture seams duplicate vertices); every undirected edge of the welded mesh
+// must be used as often forwards as backwards (a closed 2-chain), and every connected component must enclose a volume
+// of the same sign.  Then, for every pixel, #front-face hits == #back-face hits along the viewing ray, so a covered
+// pixel is always covered by a front face: skipping back faces cannot open holes.  oracle/raster.py restates this.
+static int hpb_closed_surface_sign(const float *verts, int64_t nv, const int32_t *faces, int64_t nf) {
+    std::vector<int32_t> order((size_t)nv), wid((size_t)nv);
+    for (int64_t i = 0; i < nv; ++i) order[(size_t)i] = (int32_t)i;
+    auto key = [&](int32_t i, int k) { float v = verts[3 * (size_t)i + k]; return v == 0.0f ? 0.0f : v; };
+    for (int64_t i = 0; i < 3 * nv; ++i)
+        if (!std::isfinite(verts[i])) return 0;
+    std::sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
+        for (int k = 0; k < 3; ++k) {
+            const float x = key(a, k), y = key(b, k);
+            if (x != y) return x < y;
+        }
+        return a < b;
+    });
+    int32_t n_w = 0;
+    for (int64_t i = 0; i < nv; ++i) {
+        const int32_t cur = order[(size_t)i];
+        if (i > 0) {
+            const int32_t prev = order[(size_t)i - 1];
+            if (!(key(cur, 0) == key(prev, 0) && key(cur, 1) == key(prev, 1) && key(cur, 2) == key(prev, 2))) ++n_w;
+        }
+        wid[(size_t)cur] = n_w;
+    }
+    ++n_w;
+    std::vector<int32_t> parent((size_t)n_w);
+    for (int32_t i = 0; i < n_w; ++i) parent[(size_t)i] = i;
+    auto find = [&](int32_t x) {
+        while (parent[(size_t)x] != x) { parent[(size_t)x] = parent[(size_t)parent[(size_t)x]]; x = parent[(size_t)x]; }
+        return x;
+    };
+    std::vector<std::pair<uint64_t, int32_t>> edges;
+    edges.reserve((size_t)nf * 3);
+    double mn[3] = {1e300, 1e300, 1e300}, mx[3] = {-1e300, -1e300, -1e300};
+    for (int64_t i = 0; i < nv; ++i)
+        for (int k = 0; k < 3; ++k) { const double v = verts[3 * i + k]; mn[k] = v < mn[k] ? v : mn[k]; mx[k] = v > mx[k] ? v : mx[k]; }
+    for (int64_t t = 0; t < nf; ++t) {
+        const int32_t w[3] = {wid[(size_t)faces[3 * t]], wid[(size_t)faces[3 * t + 1]], wid[(size_t)faces[3 * t + 2]]};
+        if (w[0] == w[1] || w[1] == w[2] || w[0] == w[2]) continue;  // zero-area face: never rasterised
+        for (int k = 0; k < 3; ++k) {
+            const int32_t u = w[k], v = w[(k + 1) % 3];
+            const uint64_t lo = (uint64_t)(u < v ? u : v), hi = (uint64_t)(u < v ? v : u);
+            edges.emplace_back((lo << 32) | hi, u < v ? 1 : -1);
+        }
+        const int32_t ra = find(w[0]), rb = find(w[1]), rc = find(w[2]);
+        parent[(size_t)rb] = ra;
+        parent[(size_t)find(rc)] = ra;
+    }
+    if (edges.empty()) return 0;
+    std::sort(edges.begin(), edges.end());
+    for (size_t i = 0; i < edges.size();) {
+        size_t j = i;
+        int sum = 0;
+        while (j < edges.size() && edges[j].first == edges[i].first) sum += edges[j++].second;
+        if (sum != 0) return 0;
+        i = j;
+    }
+    std::vector<double> vol((size_t)n_w, 0.0);
+    std::vector<char> used((size_t)n_w, 0);
+    for (int64_t t = 0; t < nf; ++t) {
+        const int32_t i0 = faces[3 * t], i1 = faces[3 * t + 1], i2 = faces[3 * t + 2];
+        const int32_t w0 = wid[(size_t)i0], w1 = wid[(size_t)i1], w2 = wid[(size_t)i2];
+        if (w0 == w1 || w1 == w2 || w0 == w2) continue;
+        const double a[3] = {verts[3 * (size_t)i0], verts[3 * (size_t)i0 + 1], verts[3 * (size_t)i0 + 2]};
+        const double b[3] = {verts[3 * (size_t)i1], verts[3 * (size_t)i1 + 1], verts[3 * (size_t)i1 + 2]};
+        const double c[3] = {verts[3 * (size_t)i2], verts[3 * (size_t)i2 + 1], verts[3 * (size_t)i2 + 2]};
+        const double det = a[0] * (b[1] * c[2] - b[2] * c[1]) - a[1] * (b[0] * c[2] - b[2] * c[0]) + a[2] * (b[0] * c[1] - b[1] * c[0]);
+        const int32_t r = find(w0);
+        vol[(size_t)r] += det / 6.0;
+        used[(size_t)r] = 1;
+    }
+    const double diag2 = (mx[0] - mn[0]) * (mx[0] - mn[0]) + (mx[1] - mn[1]) * (mx[1] - mn[1]) + (mx[2] - mn[2]) * (mx[2] - mn[2]);
+    const double tol = 1e-9 * diag2 * std::sqrt(diag2);
+    int sign = 0;
+    for (int32_t r = 0; r < n_w; ++r) {
+        if (!used[(size_t)r]) continue;
+        if (!(std::fabs(vol[(size_t)r]) > tol)) return 0;
+        const int sg = vol[(size_t)r] > 0 ? 1 : -1;
+        if (sign != 0 && sg != sign) return 0;
+        sign = sg;
+    }
+    // outward winding (positive volume): front faces project with area2 < 0 in (x right, y down) pixel coordinates
+    return sign > 0 ? -1 : (sign < 0 ? 1 : 0);
 }
 
 extern "C" {
@@ -75,7 +166,7 @@ int hpb_destroy(hpb_ctx *ctx) {
     if (!ctx) return HPB_OK;
     HpbDeviceGuard guard(ctx->device);
     for (auto &m : ctx->meshes) {
-        cudaFree(m.pos); cudaFree(m.nrm); cudaFree(m.uv); cudaFree(m.vcol); cudaFree(m.faces); cudaFree(m.tex);
+        cudaFree(m.pos); cudaFree(m.nrm); cudaFree(m.uv); cudaFree(m.vcol); cudaFree(m.faces); cudaFree(m.tex); cudaFree(m.nu); cudaFree(m.tv);
     }
     cudaFree(ctx->meshes_dev);
     cudaFree(ctx->vis);
@@ -143,6 +234,22 @@ int hpb_mesh_upload(hpb_ctx *ctx, const float *verts_xyz, const float *normals, 
         HPB_CUDA_OK(cudaMalloc(&m.faces, nf * 16));
         HPB_CUDA_OK(cudaMemcpy(m.faces, f4.data(), nf * 16, cudaMemcpyHostToDevice));
     }
+    {
+        std::vector<float> nu(nv * 4), tv(nv, 0.0f);
+        for (size_t i = 0; i < nv; ++i) {
+            nu[4 * i] = normals[3 * i]; nu[4 * i + 1] = normals[3 * i + 1]; nu[4 * i + 2] = normals[3 * i + 2];
+            nu[4 * i + 3] = uv ? uv[2 * i] : 0.0f;
+            if (uv) tv[i] = uv[2 * i + 1];
+        }
+        HPB_CUDA_OK(cudaMalloc(&m.nu, nv * 16));
+        HPB_CUDA_OK(cudaMemcpy(m.nu, nu.data(), nv * 16, cudaMemcpyHostToDevice));
+        HPB_CUDA_OK(cudaMalloc(&m.tv, nv * 4));
+        HPB_CUDA_OK(cudaMemcpy(m.tv, tv.data(), nv * 4, cudaMemcpyHostToDevice));
+    }
+    m.dev.nu = (const float4 *)m.nu;
+    m.dev.tv = (const float *)m.tv;
+    m.closed_sign = hpb_closed_surface_sign(verts_xyz, n_verts, faces, n_faces);
+    m.dev.cull_sign = m.closed_sign;
     m.dev.pos = (const float *)m.pos;
     m.dev.nrm = (const float *)m.nrm;
     m.dev.uv = (const float *)m.uv;
@@ -218,6 +325,30 @@ int hpb_mesh_get_mip(hpb_ctx *ctx, int32_t mesh_id, int level, uint8_t *out_host
         HpbDeviceGuard guard(ctx->device);
         HPB_CUDA_OK(cudaMemcpy(out_host, d.tex + d.tex_off[level], (size_t)d.tex_w[level] * d.tex_h[level] * 4, cudaMemcpyDeviceToHost));
     }
+    return HPB_OK;
+}
+
+int hpb_mesh_closed_sign(hpb_ctx *ctx, int32_t mesh_id, int *sign) {
+    HPB_REQUIRE(ctx && sign, "NULL argument");
+    if (mesh_id < 0 || mesh_id >= (int)ctx->meshes.size()) {
+        hpb_set_error("hpb_mesh_closed_sign: unknown mesh id %d", mesh_id);
+        return HPB_ENOTFOUND;
+    }
+    *sign = ctx->meshes[mesh_id].closed_sign;
+    return HPB_OK;
+}
+
+int hpb_mesh_set_cull(hpb_ctx *ctx, int32_t mesh_id, int enable) {
+    HPB_REQUIRE(ctx, "NULL ctx");
+    if (mesh_id < 0 || mesh_id >= (int)ctx->meshes.size()) {
+        hpb_set_error("hpb_mesh_set_cull: unknown mesh id %d", mesh_id);
+        return HPB_ENOTFOUND;
+    }
+    HpbDeviceGuard guard(ctx->device);
+    HpbMeshHost &m = ctx->meshes[mesh_id];
+    m.dev.cull_sign = enable ? m.closed_sign : 0;
+    HPB_CUDA_OK(cudaDeviceSynchronize());
+    HPB_CUDA_OK(cudaMemcpy(ctx->meshes_dev + mesh_id, &m.dev, sizeof(HpbMeshDev), cudaMemcpyHostToDevice));
     return HPB_OK;
 }
 

@@ -21,7 +21,14 @@ struct HpbMeshDev {
     const uchar4 *vcol;  // [nv] RGBA or nullptr
     const int4 *faces;   // [nf] (i0,i1,i2,0): padded to 16 B so one thread loads a triangle in one LDG.128
     const uchar4 *tex;   // RGBA8 mip chain or nullptr
+    const float4 *nu;    // [nv] (nx, ny, nz, u): the resolve stage fetches a vertex's normal and u with ONE LDG.128
+    const float *tv;     // [nv] v (0 when the mesh has no uv)
     int nv, nf;
+    // Back-face culling is semantically invisible on a closed, consistently oriented surface (every pixel a back
+    // face covers is also covered by a nearer front face), so the rasteriser skips back faces of such meshes.
+    // cull_sign = sign of the screen-space area2 of FRONT faces (-1: outward CCW winding, +1: inward), 0 = not
+    // provably closed -> two-sided rendering of every triangle (panda3d_scene_renderer.py:102).
+    int cull_sign;
     int tex_levels;
     int tex_pow2;  // 1 when level-0 width and height are powers of two (then every level is): wrap = bit mask
     int tex_w[HPB_MAX_MIPS];
@@ -33,8 +40,9 @@ struct HpbMeshDev {
 //   int2 xy  24.8 fixed-point screen position      float iz  1 / Z_cam (0 marks a near-clipped vertex)
 
 struct HpbMeshHost {
-    void *pos = nullptr, *nrm = nullptr, *uv = nullptr, *vcol = nullptr, *faces = nullptr, *tex = nullptr;
+    void *pos = nullptr, *nrm = nullptr, *uv = nullptr, *vcol = nullptr, *faces = nullptr, *tex = nullptr, *nu = nullptr, *tv = nullptr;
     HpbMeshDev dev;
+    int closed_sign = 0;  // result of the closed-surface analysis (dev.cull_sign is this, or 0 when culling is disabled)
 };
 
 struct hpb_ctx {

@@ -7,21 +7,30 @@
 // explicit IEEE op / fmaf so results are bit-identical to the CPU oracle used by the tests (the library is built
 // with -fmad=false).
 //
+// The workload is micro-polygon rendering: a 15 728-triangle mesh lands on ~19 000 pixels of a 320x240 view, i.e. a
+// triangle covers 1-3 pixels and half of the triangles face away.  The kernel is therefore triangle-parallel with
+// per-warp work compaction, and instruction-issue bound (not DRAM bound) by design; see DESIGN.md section 4.
+//
 // Structure: a persistent grid of thread-block CLUSTERS; each cluster (G = 1, 2, 4 or 8 CTAs, one CTA per SM) loops
 // over scenes.  G > 1 is chosen for small batches so that one scene is spread over several SMs (the refiner renders
 // only 4..64 scenes per launch); for b >= #SMs G = 1 and each SM renders whole scenes.
 //   phase A  vertex stage (every CTA of the cluster, redundantly): object -> camera -> 24.8 fixed-point screen
 //            position + 1/z, staged in SHARED memory (12 B per vertex; meshes that do not fit fall back to a per-CTA
 //            global scratch slice).  The screen bounding box of the scene is reduced on the way.
-//   phase B  triangle stage: the cluster's CTAs split the triangle list.  One lane per triangle: exact integer edge
-//            functions with a top-left rule; small triangles are walked by their own lane in a warp-convergent
-//            loop, big ones (or ones needing 64-bit edge functions) by the whole warp.  Depth test = 64-bit
-//            atomicMin of (depth bits << 32 | triangle id) on a per-cluster visibility buffer that stays resident
-//            in L2 (it is re-armed in phase C, never re-cleared).
+//   phase B  triangle stage: the cluster's CTAs split the triangle list.
+//            pass 1 (one lane per triangle, cheap): bounding box, signed area; triangles without a pixel centre,
+//            degenerate ones and -- on closed meshes -- back faces are dropped; the survivors' ids are COMPACTED into
+//            a per-warp shared-memory queue.
+//            pass 2 (whenever 32 ids are queued): full set-up, exact integer edge functions with a top-left rule, a
+//            per-triangle depth PLANE d(col,row); every lane walks its own bounding box in two warp-convergent loops
+//            (coverage mask, then one covered pixel per iteration).  Depth test = 64-bit atomicMin of
+//            (depth bits << 32 | triangle id << 1 | wide) on a per-cluster visibility buffer that stays resident in L2
+//            (re-armed in phase C, never re-cleared).  Big triangles are walked by the whole warp.
 //   phase C  resolve: the cluster's CTAs split the pixels; one thread per pixel, coalesced planar stores.  Only pixels
-//            inside the scene's bounding box read the visibility buffer; the winning triangle is re-set-up,
-//            attributes are interpolated perspective-correctly, texture is trilinearly filtered from an RGBA8 mip
-//            chain.  Background pixels are written as zeros here, so the outputs need no separate clear pass.
+//            inside the scene's bounding box read the visibility buffer; attributes are interpolated
+//            perspective-correctly from the un-normalised edge values (no area division), texture is trilinearly
+//            filtered from an RGBA8 mip chain.  Background pixels are written as zeros here, so the outputs need no
+//            separate clear pass.
 #include <cooperative_groups.h>
 
 #include "hpb_common.cuh"
@@ -31,7 +40,9 @@ namespace cg = cooperative_groups;
 namespace {
 
 constexpr int RASTER_THREADS = 1024;
+constexpr int RASTER_WARPS = RASTER_THREADS / 32;
 constexpr int SMALL_TRI_MAX = 32;  // bbox pixels a lane walks on its own; larger triangles are walked by the warp
+constexpr int VTX_CLIPPED = (int)0x80000000;  // screen x/y of a vertex in front of the near plane
 
 struct RasterParams {
     const HpbMeshDev *meshes;
@@ -68,50 +79,39 @@ __device__ __forceinline__ int snap_fixed(float u) {
 __device__ __forceinline__ int ceil_div_pix(int v) { return (v - 128 + 255) >> HPB_SUBPIX_BITS; }
 __device__ __forceinline__ int floor_div_pix(int v) { return (v - 128) >> HPB_SUBPIX_BITS; }
 __device__ __forceinline__ int edge_bias(int dx, int dy) { return (dy < 0 || (dy == 0 && dx > 0)) ? 0 : -1; }
+__device__ __forceinline__ int min3i(int a, int b, int c) { return min(a, min(b, c)); }
+__device__ __forceinline__ int max3i(int a, int b, int c) { return max(a, max(b, c)); }
 
-struct TriSetup {
-    int x0, y0, x1, y1, x2, y2;
-    int i0, i1, i2;
-    long long area2;
-};
-
-// Orients the triangle so area2 > 0.  Returns false for near-clipped or degenerate triangles.
-__device__ __forceinline__ bool setup_tri(const int2 *sxy, const float *siz, int4 f, TriSetup &t, float &iz0, float &iz1,
-                                          float &iz2) {
-    const int2 a = sxy[f.x], b = sxy[f.y], c = sxy[f.z];
-    const float za = siz[f.x], zb = siz[f.y], zc = siz[f.z];
-    if (za == 0.0f || zb == 0.0f || zc == 0.0f) return false;
-    long long area2 = (long long)(b.x - a.x) * (long long)(c.y - a.y) - (long long)(c.x - a.x) * (long long)(b.y - a.y);
-    if (area2 == 0) return false;
-    t.x0 = a.x; t.y0 = a.y; t.i0 = f.x; iz0 = za;
-    if (area2 < 0) {
-        t.x1 = c.x; t.y1 = c.y; t.i1 = f.z; iz1 = zc;
-        t.x2 = b.x; t.y2 = b.y; t.i2 = f.y; iz2 = zb;
-        area2 = -area2;
-    } else {
-        t.x1 = b.x; t.y1 = b.y; t.i1 = f.y; iz1 = zb;
-        t.x2 = c.x; t.y2 = c.y; t.i2 = f.z; iz2 = zc;
-    }
-    t.area2 = area2;
-    return true;
-}
-
-__device__ __forceinline__ float depth_from_iz(const RasterParams &p, float iz) { return (p.inv_near - iz) * p.cd; }
-
-__device__ __forceinline__ void emit_fragment(const RasterParams &p, float l0, float l1, float l2, float iz0, float iz1,
-                                              float iz2, unsigned tri_id, unsigned long long *slot) {
-    const float iz = fmaf(l2, iz2, fmaf(l1, iz1, l0 * iz0));
-    float d = depth_from_iz(p, iz);
+__device__ __forceinline__ void put_fragment(float d, unsigned lo, unsigned long long *slot) {
     if (d <= 1.0f) {
         if (d < 0.0f) d = 0.0f;
-        atomicMin(slot, ((unsigned long long)__float_as_uint(d) << 32) | tri_id);
+        atomicMin(slot, ((unsigned long long)__float_as_uint(d) << 32) | lo);
     }
+}
+
+// Depth plane of a triangle oriented so that area2 > 0, anchored at the pixel (jx0, jy0) of its clamped bounding box:
+//   d(col,row) = fmaf(Dx, col, fmaf(Dy, row, Dc)), the GL window depth (1/near - 1/z) / (1/near - 1/far).
+// e?o are the (unbiased) edge values at the anchor pixel; (x?,y?) the oriented fixed-point vertices.
+__device__ __forceinline__ void depth_plane(const RasterParams &p, float e0o, float e1o, float e2o, float area2f, int x0, int y0, int x1,
+                                            int y1, int x2, int y2, float iz0, float iz1, float iz2, float &Dc, float &Dx,
+                                            float &Dy) {
+    const float inv = __frcp_rn(area2f);
+    const float izc = fmaf(e2o * inv, iz2, fmaf(e1o * inv, iz1, (e0o * inv) * iz0));
+    const float d1 = iz1 - iz0, d2 = iz2 - iz0;
+    // per-pixel steps of the edge functions e1, e2: d/dx = -(edge dy) * 256, d/dy = (edge dx) * 256
+    const float sx1 = (float)(y2 - y0) * 256.0f, sx2 = (float)(y0 - y1) * 256.0f;
+    const float sy1 = (float)(x0 - x2) * 256.0f, sy2 = (float)(x1 - x0) * 256.0f;
+    const float gx = fmaf(sx2, d2, sx1 * d1) * inv;
+    const float gy = fmaf(sy2, d2, sy1 * d1) * inv;
+    Dc = (p.inv_near - izc) * p.cd;
+    Dx = -(gx * p.cd);
+    Dy = -(gy * p.cd);
 }
 
 // Whole-warp walk of one (big) triangle's bounding box with 64-bit edge functions; all lanes hold the same triangle.
 __device__ __forceinline__ void raster_tri_warp(const RasterParams &p, int x0, int y0, int x1, int y1, int x2, int y2,
-                                                float iz0, float iz1, float iz2, float inv, int jx0, int jx1, int jy0,
-                                                int jy1, unsigned tri_id, unsigned long long *vis, int lane) {
+                                                float Dc, float Dx, float Dy, int jx0, int jx1, int jy0, int jy1,
+                                                unsigned lo, unsigned long long *vis, int lane) {
     const int b0 = edge_bias(x2 - x1, y2 - y1), b1 = edge_bias(x0 - x2, y0 - y2), b2 = edge_bias(x1 - x0, y1 - y0);
     const int roww = jx1 - jx0 + 1, total = roww * (jy1 - jy0 + 1);
     // lanes cover 32 consecutive pixels of the row-major bounding box at a time
@@ -123,7 +123,7 @@ __device__ __forceinline__ void raster_tri_warp(const RasterParams &p, int x0, i
         const long long e1 = (long long)(x0 - x2) * (fyp - y2) - (long long)(y0 - y2) * (fxp - x2);
         const long long e2 = (long long)(x1 - x0) * (fyp - y0) - (long long)(y1 - y0) * (fxp - x0);
         if (((e0 + b0) | (e1 + b1) | (e2 + b2)) >= 0)
-            emit_fragment(p, (float)e0 * inv, (float)e1 * inv, (float)e2 * inv, iz0, iz1, iz2, tri_id, vis + (long long)py * p.w + px);
+            put_fragment(fmaf(Dx, (float)col, fmaf(Dy, (float)row, Dc)), lo, vis + (long long)py * p.w + px);
     }
 }
 
@@ -138,7 +138,7 @@ __device__ __forceinline__ float hp_log2(float x) {
 }
 
 template <bool POW2>
-__device__ __forceinline__ float3 fetch_texel(const uchar4 *tex, int W, int H, int x, int y) {
+__device__ __forceinline__ uchar4 fetch_texel(const uchar4 *tex, int W, int H, int x, int y) {
     if (POW2) {
         x &= W - 1;
         y &= H - 1;
@@ -146,17 +146,19 @@ __device__ __forceinline__ float3 fetch_texel(const uchar4 *tex, int W, int H, i
         x %= W; if (x < 0) x += W;
         y %= H; if (y < 0) y += H;
     }
-    const uchar4 c = __ldg(tex + y * W + x);
-    return make_float3((float)c.x, (float)c.y, (float)c.z);
+    return __ldg(tex + y * W + x);
+}
+
+__device__ __forceinline__ float bilerp(float fx, float fy, unsigned c00, unsigned c01, unsigned c10, unsigned c11) {
+    const float a = (float)c00, b = (float)c01, c = (float)c10, d = (float)c11;
+    const float top = fmaf(fx, b - a, a), bot = fmaf(fx, d - c, c);
+    return fmaf(fy, bot - top, top);
 }
 
 template <bool POW2>
-__device__ __forceinline__ float3 sample_bilinear(const HpbMeshDev &m, int lvl, float u, float v) {
-    const int Wi = m.tex_w[lvl], Hi = m.tex_h[lvl];
-    const uchar4 *tex = m.tex + m.tex_off[lvl];
-    const float W = (float)Wi, H = (float)Hi;
-    const float x = fmaf(u, W, -0.5f);
-    const float y = fmaf(1.0f - v, H, -0.5f);
+__device__ __forceinline__ float3 sample_bilinear(const uchar4 *tex, int Wi, int Hi, float u, float v) {
+    const float x = fmaf(u, (float)Wi, -0.5f);
+    const float y = fmaf(1.0f - v, (float)Hi, -0.5f);
     float xf = floorf(x), yf = floorf(y);
     const float fx = x - xf, fy = y - yf;
     if (!(xf > -1.0e9f)) xf = -1.0e9f;
@@ -164,22 +166,10 @@ __device__ __forceinline__ float3 sample_bilinear(const HpbMeshDev &m, int lvl, 
     if (!(yf > -1.0e9f)) yf = -1.0e9f;
     if (yf > 1.0e9f) yf = 1.0e9f;
     const int x0 = (int)xf, y0 = (int)yf;
-    const float3 c00 = fetch_texel<POW2>(tex, Wi, Hi, x0, y0), c01 = fetch_texel<POW2>(tex, Wi, Hi, x0 + 1, y0);
-    const float3 c10 = fetch_texel<POW2>(tex, Wi, Hi, x0, y0 + 1), c11 = fetch_texel<POW2>(tex, Wi, Hi, x0 + 1, y0 + 1);
-    float3 o;
-    {
-        const float top = fmaf(fx, c01.x - c00.x, c00.x), bot = fmaf(fx, c11.x - c10.x, c10.x);
-        o.x = fmaf(fy, bot - top, top);
-    }
-    {
-        const float top = fmaf(fx, c01.y - c00.y, c00.y), bot = fmaf(fx, c11.y - c10.y, c10.y);
-        o.y = fmaf(fy, bot - top, top);
-    }
-    {
-        const float top = fmaf(fx, c01.z - c00.z, c00.z), bot = fmaf(fx, c11.z - c10.z, c10.z);
-        o.z = fmaf(fy, bot - top, top);
-    }
-    return o;
+    const uchar4 c00 = fetch_texel<POW2>(tex, Wi, Hi, x0, y0), c01 = fetch_texel<POW2>(tex, Wi, Hi, x0 + 1, y0);
+    const uchar4 c10 = fetch_texel<POW2>(tex, Wi, Hi, x0, y0 + 1), c11 = fetch_texel<POW2>(tex, Wi, Hi, x0 + 1, y0 + 1);
+    return make_float3(bilerp(fx, fy, c00.x, c01.x, c10.x, c11.x), bilerp(fx, fy, c00.y, c01.y, c10.y, c11.y),
+                       bilerp(fx, fy, c00.z, c01.z, c10.z, c11.z));
 }
 
 template <bool POW2>
@@ -189,27 +179,25 @@ __device__ __forceinline__ float3 sample_trilinear(const HpbMeshDev &m, float u,
     const float lf = floorf(lod);
     const float fl = lod - lf;
     const int li = (int)lf;
-    const float3 ca = sample_bilinear<POW2>(m, li, u, v);
+    const float3 ca = sample_bilinear<POW2>(m.tex + m.tex_off[li], m.tex_w[li], m.tex_h[li], u, v);
     if (fl > 0.0f && li + 1 < m.tex_levels) {
-        const float3 cb = sample_bilinear<POW2>(m, li + 1, u, v);
+        const float3 cb = sample_bilinear<POW2>(m.tex + m.tex_off[li + 1], m.tex_w[li + 1], m.tex_h[li + 1], u, v);
         return make_float3(fmaf(fl, cb.x - ca.x, ca.x), fmaf(fl, cb.y - ca.y, ca.y), fmaf(fl, cb.z - ca.z, ca.z));
     }
     return ca;
 }
 
 // Panda3D's 32^3 "normal map" lookup (renderer/utils.py:63-79): texel k = floor(k*255/32), repeat wrap, linear.
-// lut[k] = (float)k / 255.0f (IEEE division, done once per CTA): the 8-bit framebuffer value returned as k/255.
-__device__ __forceinline__ float encode_normal(float c, const float *lut) {
+// tab[k] = (T_k, T_{k+1} - T_k) with T_k = floor(k*255/32); lut[q] = (float)q / 255.0f (IEEE division, done once per
+// CTA): the 8-bit framebuffer value returned as q/255.
+__device__ __forceinline__ float encode_normal(float c, const float2 *tab, const float *lut) {
     const float s = c - floorf(c);
     const float t = fmaf(s, 32.0f, -0.5f);
     const float kf = floorf(t);
     const float f = t - kf;
-    const int k0 = ((int)kf) & 31;
-    const int k1 = (k0 + 1) & 31;
-    const float T0 = (float)((k0 * 255) >> 5);
-    const float T1 = (float)((k1 * 255) >> 5);
-    const float val = fmaf(f, T1 - T0, T0);
-    return lut[(int)floorf(val + 0.5f)];  // val in [0, 247]
+    const float2 T = tab[((int)kf) & 31];
+    const float val = fmaf(f, T.y, T.x);
+    return lut[(int)(val + 0.5f)];  // val in [0, 247]: truncation == floor
 }
 
 __device__ __forceinline__ float quant8(float c, const float *lut) {
@@ -219,6 +207,80 @@ __device__ __forceinline__ float quant8(float c, const float *lut) {
     return lut[(int)q];
 }
 
+// Pass 2 of the triangle stage: every active lane rasterises the (small) triangle `t` it was handed.
+__device__ __forceinline__ void raster_small_tris(const RasterParams &p, const int4 *faces, const int2 *sxy, const float *siz,
+                                                  bool active, int t, unsigned long long *vis) {
+    int roww = 1, scnt = 0, jx0 = 0, jy0 = 0;
+    unsigned E0 = 0, E1 = 0, E2 = 0, sx0 = 0, sx1 = 0, sx2 = 0, sy0 = 0, sy1 = 0, sy2 = 0;
+    float Dc = 2.0f, Dx = 0.0f, Dy = 0.0f;
+    if (active) {
+        const int4 f = __ldg(faces + t);
+        const int2 a = sxy[f.x];
+        int2 b = sxy[f.y], c = sxy[f.z];
+        const float iz0 = siz[f.x];
+        float iz1 = siz[f.y], iz2 = siz[f.z];
+        // small triangles: every product below is exact in 32 bits (|.| <= 2 * bbox_w * bbox_h < 2^30)
+        int area2 = (b.x - a.x) * (c.y - a.y) - (c.x - a.x) * (b.y - a.y);
+        if (area2 < 0) {  // orient so that area2 > 0
+            const int2 tv = b; b = c; c = tv;
+            const float tz = iz1; iz1 = iz2; iz2 = tz;
+            area2 = -area2;
+        }
+        jx0 = max(ceil_div_pix(min3i(a.x, b.x, c.x)), 0);
+        jy0 = max(ceil_div_pix(min3i(a.y, b.y, c.y)), 0);
+        const int jx1 = min(floor_div_pix(max3i(a.x, b.x, c.x)), p.w - 1);
+        const int jy1 = min(floor_div_pix(max3i(a.y, b.y, c.y)), p.h - 1);
+        roww = jx1 - jx0 + 1;
+        scnt = roww * (jy1 - jy0 + 1);
+        const int px0 = jx0 * HPB_SUBPIX + 128, py0 = jy0 * HPB_SUBPIX + 128;
+        const int dx0 = c.x - b.x, dy0 = c.y - b.y, dx1 = a.x - c.x, dy1 = a.y - c.y, dx2 = b.x - a.x, dy2 = b.y - a.y;
+        const int e0o = dx0 * (py0 - b.y) - dy0 * (px0 - b.x);
+        const int e1o = dx1 * (py0 - c.y) - dy1 * (px0 - c.x);
+        const int e2o = dx2 * (py0 - a.y) - dy2 * (px0 - a.x);
+        depth_plane(p, (float)e0o, (float)e1o, (float)e2o, (float)area2, a.x, a.y, b.x, b.y, c.x, c.y, iz0, iz1, iz2, Dc, Dx, Dy);
+        // biased edge values: pixel covered <=> all three >= 0.  Unsigned arithmetic: the stepped values are exact modulo
+        // 2^32 and the true values at the bounding-box pixels fit 31 bits; intermediate row jumps may wrap.
+        E0 = (unsigned)(e0o + edge_bias(dx0, dy0));
+        E1 = (unsigned)(e1o + edge_bias(dx1, dy1));
+        E2 = (unsigned)(e2o + edge_bias(dx2, dy2));
+        sx0 = (unsigned)(-dy0) * HPB_SUBPIX; sx1 = (unsigned)(-dy1) * HPB_SUBPIX; sx2 = (unsigned)(-dy2) * HPB_SUBPIX;
+        sy0 = (unsigned)dx0 * HPB_SUBPIX; sy1 = (unsigned)dx1 * HPB_SUBPIX; sy2 = (unsigned)dx2 * HPB_SUBPIX;
+    }
+    // loop 1: coverage bit mask of the lane's bounding box (row-major), branch-free edge stepping.  Pixel k's bit is
+    // shifted in from the right, so after mx iterations it sits at position mx-1-k.
+    const int mx = __reduce_max_sync(0xffffffffu, scnt);
+    unsigned cov = 0;
+    {
+        unsigned e0 = E0, e1 = E1, e2 = E2;
+        const unsigned rj0 = sy0 - (unsigned)roww * sx0, rj1 = sy1 - (unsigned)roww * sx1, rj2 = sy2 - (unsigned)roww * sx2;
+        int col = 0;
+#pragma unroll 4
+        for (int k = 0; k < mx; ++k) {
+            cov = __funnelshift_l(~(e0 | e1 | e2), cov, 1);
+            e0 += sx0; e1 += sx1; e2 += sx2;
+            const bool wrap = ++col == roww;
+            e0 += wrap ? rj0 : 0u; e1 += wrap ? rj1 : 0u; e2 += wrap ? rj2 : 0u;
+            col = wrap ? 0 : col;
+        }
+    }
+    // keep the bits of pixels k < scnt, then put pixel k at bit k
+    cov = scnt > 0 ? (cov >> (mx - scnt)) : 0u;       // pixel k now at position scnt-1-k
+    cov = scnt > 0 ? (__brev(cov) >> (32 - scnt)) : 0u;  // pixel k at bit k
+    // loop 2: one covered pixel per iteration
+    const int mxn = __reduce_max_sync(0xffffffffu, __popc(cov));
+    const unsigned rcp = 65535u / (unsigned)roww + 1u;  // k / roww == (k * rcp) >> 16 for k, roww <= 32
+    unsigned long long *org = vis + (long long)jy0 * p.w + jx0;
+    const unsigned lo = (unsigned)t << 1;
+    for (int j = 0; j < mxn; ++j) {
+        if (cov) {
+            const int k = __ffs(cov) - 1;
+            cov &= cov - 1;
+            const int row = (int)(((unsigned)k * rcp) >> 16), col = k - row * roww;
+            put_fragment(fmaf(Dx, (float)col, fmaf(Dy, (float)row, Dc)), lo, org + row * p.w + col);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(RASTER_THREADS, 1) hpb_raster_kernel(const RasterParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ HpbMeshDev sM;
@@ -226,10 +288,13 @@ __global__ void __launch_bounds__(RASTER_THREADS, 1) hpb_raster_kernel(const Ras
     __shared__ float sK[4];
     __shared__ float sAmb[3];
     __shared__ int sFinite;
+    __shared__ int sClipped;
     __shared__ int sBox[4];  // min x, min y, max x, max y of the snapped vertices (fixed point)
     __shared__ float sLut[256];
+    __shared__ float2 sNrmTab[32];
+    __shared__ int sQueue[RASTER_WARPS][64];  // per-warp queue of surviving triangle ids (pass 1 -> pass 2)
 
-    const int tid = threadIdx.x, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int G = p.G;
     const int rank = G > 1 ? (int)cg::this_cluster().block_rank() : 0;
     const int group = blockIdx.x / G, n_groups = gridDim.x / G;
@@ -238,8 +303,13 @@ __global__ void __launch_bounds__(RASTER_THREADS, 1) hpb_raster_kernel(const Ras
     unsigned char *vbase = p.verts_in_smem ? smem_raw : p.vert_scratch + (size_t)blockIdx.x * p.max_nv * 12;
     int2 *sxy = reinterpret_cast<int2 *>(vbase);
     float *siz = reinterpret_cast<float *>(vbase + (size_t)p.max_nv * 8);
+    int *queue = sQueue[warp];
 
-    if (threadIdx.x < 256) sLut[threadIdx.x] = (float)threadIdx.x / 255.0f;
+    if (tid < 256) sLut[tid] = (float)tid / 255.0f;
+    if (tid < 32) {
+        const int T0 = (tid * 255) >> 5, T1 = (((tid + 1) & 31) * 255) >> 5;
+        sNrmTab[tid] = make_float2((float)T0, (float)T1 - (float)T0);
+    }
     for (int hyp = group; hyp < p.b; hyp += n_groups) {
         {
             const int *src = reinterpret_cast<const int *>(p.meshes + p.mesh_ids[hyp]);
@@ -248,6 +318,7 @@ __global__ void __launch_bounds__(RASTER_THREADS, 1) hpb_raster_kernel(const Ras
         }
         if (tid == 0) {
             sFinite = 1;
+            sClipped = 0;
             sBox[0] = 0x7fffffff; sBox[1] = 0x7fffffff; sBox[2] = (int)0x80000000; sBox[3] = (int)0x80000000;
         }
         __syncthreads();
@@ -278,12 +349,13 @@ __global__ void __launch_bounds__(RASTER_THREADS, 1) hpb_raster_kernel(const Ras
             // ---------------- phase A: vertex stage ----------------
             const float fx = sK[0], fy = sK[1], cx = sK[2], cy = sK[3];
             int mnx = 0x7fffffff, mny = 0x7fffffff, mxx = (int)0x80000000, mxy = (int)0x80000000;
+            bool clipped = false;
             for (int i = tid; i < nv; i += RASTER_THREADS) {
                 const float x = __ldg(m.pos + 3 * i), y = __ldg(m.pos + 3 * i + 1), z = __ldg(m.pos + 3 * i + 2);
                 const float X = fmaf(sT[2], z, fmaf(sT[1], y, fmaf(sT[0], x, sT[3])));
                 const float Y = fmaf(sT[6], z, fmaf(sT[5], y, fmaf(sT[4], x, sT[7])));
                 const float Z = fmaf(sT[10], z, fmaf(sT[9], y, fmaf(sT[8], x, sT[11])));
-                int2 o = make_int2(0, 0);
+                int2 o = make_int2(VTX_CLIPPED, VTX_CLIPPED);
                 float iz = 0.0f;
                 if (Z >= p.z_near) {
                     iz = 1.0f / Z;
@@ -291,6 +363,8 @@ __global__ void __launch_bounds__(RASTER_THREADS, 1) hpb_raster_kernel(const Ras
                     o.y = snap_fixed(fmaf(fy, Y * iz, cy));
                     mnx = min(mnx, o.x); mxx = max(mxx, o.x);
                     mny = min(mny, o.y); mxy = max(mxy, o.y);
+                } else {
+                    clipped = true;
                 }
                 sxy[i] = o;
                 siz[i] = iz;
@@ -301,6 +375,7 @@ __global__ void __launch_bounds__(RASTER_THREADS, 1) hpb_raster_kernel(const Ras
                 atomicMin(&sBox[0], mnx); atomicMin(&sBox[1], mny);
                 atomicMax(&sBox[2], mxx); atomicMax(&sBox[3], mxy);
             }
+            if (__any_sync(0xffffffffu, clipped) && lane == 0) sClipped = 1;
             __syncthreads();
             if (sBox[0] <= sBox[2]) {
                 bx0 = max(ceil_div_pix(sBox[0]), 0); bx1 = min(floor_div_pix(sBox[2]), p.w - 1);
@@ -309,92 +384,84 @@ __global__ void __launch_bounds__(RASTER_THREADS, 1) hpb_raster_kernel(const Ras
 
             // ---------------- phase B: triangle stage ----------------
             if (bx0 <= bx1 && by0 <= by1) {
+                // back faces of a closed surface are invisible unless the near plane has cut it open
+                const int cull = (sClipped == 0 && fx > 0.0f && fy > 0.0f) ? m.cull_sign : 0;
                 const int per = (nf + G - 1) / G;
                 const int lo = rank * per, hi = min(nf, lo + per);
+                int nq = 0;  // queued triangle ids of this warp (warp-uniform)
                 for (int base = lo; base < hi; base += RASTER_THREADS) {  // trip count is warp-uniform
+                    // ---- pass 1: classify ----
                     const int t = base + tid;
-                    TriSetup ts;
-                    float iz0 = 0.f, iz1 = 0.f, iz2 = 0.f;
-                    int jx0 = 0, jx1 = -1, jy0 = 0, jy1 = -1, cnt = 0;
-                    bool big = false;
-                    if (t < hi && setup_tri(sxy, siz, __ldg(m.faces + t), ts, iz0, iz1, iz2)) {
-                        const int tmnx = min(ts.x0, min(ts.x1, ts.x2)), tmxx = max(ts.x0, max(ts.x1, ts.x2));
-                        const int tmny = min(ts.y0, min(ts.y1, ts.y2)), tmxy = max(ts.y0, max(ts.y1, ts.y2));
+                    bool keep = false, big = false;
+                    int2 a = make_int2(0, 0), b = a, c = a;
+                    int4 f = make_int4(0, 0, 0, 0);
+                    int jx0 = 0, jx1 = -1, jy0 = 0, jy1 = -1;
+                    long long area2 = 0;
+                    if (t < hi) {
+                        f = __ldg(m.faces + t);
+                        a = sxy[f.x]; b = sxy[f.y]; c = sxy[f.z];
+                        const int tmnx = min3i(a.x, b.x, c.x), tmxx = max3i(a.x, b.x, c.x);
+                        const int tmny = min3i(a.y, b.y, c.y), tmxy = max3i(a.y, b.y, c.y);
                         jx0 = max(ceil_div_pix(tmnx), 0); jx1 = min(floor_div_pix(tmxx), p.w - 1);
                         jy0 = max(ceil_div_pix(tmny), 0); jy1 = min(floor_div_pix(tmxy), p.h - 1);
-                        if (jx0 <= jx1 && jy0 <= jy1) {
-                            cnt = (jx1 - jx0 + 1) * (jy1 - jy0 + 1);
-                            // 32-bit edge functions are exact when |e| <= 2 * bbox_w * bbox_h (fixed point) < 2^31
-                            const long long bw = (long long)tmxx - tmnx + 2 * HPB_SUBPIX, bh = (long long)tmxy - tmny + 2 * HPB_SUBPIX;
-                            big = cnt > SMALL_TRI_MAX || !(bw * bh < (1ll << 29));
-                        }
+                        area2 = (long long)(b.x - a.x) * (long long)(c.y - a.y) - (long long)(c.x - a.x) * (long long)(b.y - a.y);
+                        keep = tmnx != VTX_CLIPPED && jx0 <= jx1 && jy0 <= jy1 && area2 != 0;
+                        if (cull != 0) keep = keep && ((area2 < 0) == (cull < 0));
+                        // 32-bit edge functions are exact when |e| <= 2 * bbox_w * bbox_h (fixed point) < 2^30
+                        const unsigned bw = (unsigned)(tmxx - tmnx) + 2u * HPB_SUBPIX, bh = (unsigned)(tmxy - tmny) + 2u * HPB_SUBPIX;
+                        big = keep && ((jx1 - jx0 + 1) * (jy1 - jy0 + 1) > SMALL_TRI_MAX || __umulhi(bw, bh) != 0u || bw * bh >= (1u << 29));
                     }
-                    const float inv = cnt ? __frcp_rn((float)ts.area2) : 0.0f;
-                    // ---- small triangles: every lane walks its own bounding box in two warp-convergent loops ----
-                    // loop 1 builds the lane's coverage bit mask (bit k = k-th bounding-box pixel, row-major) with
-                    // branch-free edge stepping; loop 2 emits one covered pixel per iteration.
-                    const int scnt = big ? 0 : cnt;
-                    const int mx = __reduce_max_sync(0xffffffffu, scnt);
-                    if (mx > 0) {
-                        // unsigned arithmetic: the stepped values are exact modulo 2^32 and the true edge values at
-                        // the bounding-box pixels fit 31 bits (see `big`); intermediate row jumps may wrap
-                        const int roww = jx1 - jx0 + 1;
-                        const int bb0 = edge_bias(ts.x2 - ts.x1, ts.y2 - ts.y1), bb1 = edge_bias(ts.x0 - ts.x2, ts.y0 - ts.y2),
-                                  bb2 = edge_bias(ts.x1 - ts.x0, ts.y1 - ts.y0);
-                        const int px0 = jx0 * HPB_SUBPIX + 128, py0 = jy0 * HPB_SUBPIX + 128;
-                        const unsigned E0 = (unsigned)((ts.x2 - ts.x1) * (py0 - ts.y1) - (ts.y2 - ts.y1) * (px0 - ts.x1) + bb0);
-                        const unsigned E1 = (unsigned)((ts.x0 - ts.x2) * (py0 - ts.y2) - (ts.y0 - ts.y2) * (px0 - ts.x2) + bb1);
-                        const unsigned E2 = (unsigned)((ts.x1 - ts.x0) * (py0 - ts.y0) - (ts.y1 - ts.y0) * (px0 - ts.x0) + bb2);
-                        const unsigned sx0 = (unsigned)(-(ts.y2 - ts.y1)) * HPB_SUBPIX, sx1 = (unsigned)(-(ts.y0 - ts.y2)) * HPB_SUBPIX,
-                                       sx2 = (unsigned)(-(ts.y1 - ts.y0)) * HPB_SUBPIX;
-                        const unsigned sy0 = (unsigned)(ts.x2 - ts.x1) * HPB_SUBPIX, sy1 = (unsigned)(ts.x0 - ts.x2) * HPB_SUBPIX,
-                                       sy2 = (unsigned)(ts.x1 - ts.x0) * HPB_SUBPIX;
-                        unsigned cov = 0;
-                        {
-                            unsigned e0 = E0, e1 = E1, e2 = E2;
-                            const unsigned rj0 = sy0 - (unsigned)roww * sx0, rj1 = sy1 - (unsigned)roww * sx1, rj2 = sy2 - (unsigned)roww * sx2;
-                            int col = 0;
-                            for (int k = 0; k < mx; ++k) {
-                                cov |= (~(e0 | e1 | e2) >> 31) << k;
-                                e0 += sx0; e1 += sx1; e2 += sx2;
-                                const bool wrap = ++col == roww;
-                                e0 += wrap ? rj0 : 0u; e1 += wrap ? rj1 : 0u; e2 += wrap ? rj2 : 0u;
-                                col = wrap ? 0 : col;
-                            }
-                        }
-                        cov &= scnt >= 32 ? 0xffffffffu : ((1u << scnt) - 1u);
-                        const int mxn = __reduce_max_sync(0xffffffffu, __popc(cov));
-                        const unsigned rcp = 65535u / (unsigned)max(roww, 1) + 1u;  // k / roww == (k * rcp) >> 16 for k, roww <= 32
-                        unsigned long long *org = vis + (long long)jy0 * p.w + jx0;
-                        for (int j = 0; j < mxn; ++j) {
-                            if (cov) {
-                                const int k = __ffs(cov) - 1;
-                                cov &= cov - 1;
-                                const int row = (int)(((unsigned)k * rcp) >> 16), col = k - row * roww;
-                                const int e0 = (int)(E0 + (unsigned)col * sx0 + (unsigned)row * sy0) - bb0;
-                                const int e1 = (int)(E1 + (unsigned)col * sx1 + (unsigned)row * sy1) - bb1;
-                                const int e2 = (int)(E2 + (unsigned)col * sx2 + (unsigned)row * sy2) - bb2;
-                                emit_fragment(p, (float)e0 * inv, (float)e1 * inv, (float)e2 * inv, iz0, iz1, iz2, (unsigned)t,
-                                              org + row * p.w + col);
-                            }
-                        }
-                    }
-                    // ---- big triangles: the whole warp walks one triangle at a time ----
+                    // ---- big triangles (rare): the whole warp walks one triangle at a time ----
                     unsigned bm = __ballot_sync(0xffffffffu, big);
-                    while (bm) {
-                        const int src = __ffs(bm) - 1;
-                        bm &= bm - 1;
-                        const int x0 = __shfl_sync(0xffffffffu, ts.x0, src), y0 = __shfl_sync(0xffffffffu, ts.y0, src);
-                        const int x1 = __shfl_sync(0xffffffffu, ts.x1, src), y1 = __shfl_sync(0xffffffffu, ts.y1, src);
-                        const int x2 = __shfl_sync(0xffffffffu, ts.x2, src), y2 = __shfl_sync(0xffffffffu, ts.y2, src);
-                        const float z0 = __shfl_sync(0xffffffffu, iz0, src), z1 = __shfl_sync(0xffffffffu, iz1, src);
-                        const float z2 = __shfl_sync(0xffffffffu, iz2, src), iv = __shfl_sync(0xffffffffu, inv, src);
-                        const int ax0 = __shfl_sync(0xffffffffu, jx0, src), ax1 = __shfl_sync(0xffffffffu, jx1, src);
-                        const int ay0 = __shfl_sync(0xffffffffu, jy0, src), ay1 = __shfl_sync(0xffffffffu, jy1, src);
-                        raster_tri_warp(p, x0, y0, x1, y1, x2, y2, z0, z1, z2, iv, ax0, ax1, ay0, ay1,
-                                        (unsigned)(base + (tid & ~31) + src), vis, lane);
+                    if (bm) {
+                        float Dc = 0.f, Dx = 0.f, Dy = 0.f;
+                        if (big) {
+                            float iz0 = siz[f.x], iz1 = siz[f.y], iz2 = siz[f.z];
+                            if (area2 < 0) {
+                                const int2 tv = b; b = c; c = tv;
+                                const float tz = iz1; iz1 = iz2; iz2 = tz;
+                                area2 = -area2;
+                            }
+                            const int px0 = jx0 * HPB_SUBPIX + 128, py0 = jy0 * HPB_SUBPIX + 128;
+                            const long long e0o = (long long)(c.x - b.x) * (py0 - b.y) - (long long)(c.y - b.y) * (px0 - b.x);
+                            const long long e1o = (long long)(a.x - c.x) * (py0 - c.y) - (long long)(a.y - c.y) * (px0 - c.x);
+                            const long long e2o = (long long)(b.x - a.x) * (py0 - a.y) - (long long)(b.y - a.y) * (px0 - a.x);
+                            depth_plane(p, (float)e0o, (float)e1o, (float)e2o, (float)area2, a.x, a.y, b.x, b.y, c.x, c.y, iz0, iz1, iz2,
+                                        Dc, Dx, Dy);
+                        }
+                        const unsigned wide = area2 >= (1ll << 31) ? 1u : 0u;
+                        while (bm) {
+                            const int src = __ffs(bm) - 1;
+                            bm &= bm - 1;
+                            const int x0 = __shfl_sync(0xffffffffu, a.x, src), y0 = __shfl_sync(0xffffffffu, a.y, src);
+                            const int x1 = __shfl_sync(0xffffffffu, b.x, src), y1 = __shfl_sync(0xffffffffu, b.y, src);
+                            const int x2 = __shfl_sync(0xffffffffu, c.x, src), y2 = __shfl_sync(0xffffffffu, c.y, src);
+                            const float qc = __shfl_sync(0xffffffffu, Dc, src), qx = __shfl_sync(0xffffffffu, Dx, src);
+                            const float qy = __shfl_sync(0xffffffffu, Dy, src);
+                            const int ax0 = __shfl_sync(0xffffffffu, jx0, src), ax1 = __shfl_sync(0xffffffffu, jx1, src);
+                            const int ay0 = __shfl_sync(0xffffffffu, jy0, src), ay1 = __shfl_sync(0xffffffffu, jy1, src);
+                            const unsigned wd = __shfl_sync(0xffffffffu, wide, src);
+                            raster_tri_warp(p, x0, y0, x1, y1, x2, y2, qc, qx, qy, ax0, ax1, ay0, ay1,
+                                            ((unsigned)(base + (tid & ~31) + src) << 1) | wd, vis, lane);
+                        }
+                    }
+                    // ---- compaction: queue the small survivors; rasterise whenever 32 are waiting ----
+                    const bool small = keep && !big;
+                    const unsigned sm_mask = __ballot_sync(0xffffffffu, small);
+                    if (small) queue[nq + __popc(sm_mask & ((1u << lane) - 1u))] = t;
+                    nq += __popc(sm_mask);
+                    __syncwarp();
+                    if (nq >= 32) {
+                        const int tq = queue[lane];
+                        const int spill = queue[32 + lane];
+                        __syncwarp();
+                        nq -= 32;
+                        if (lane < nq) queue[lane] = spill;
+                        raster_small_tris(p, m.faces, sxy, siz, true, tq, vis);
+                        __syncwarp();
                     }
                 }
+                if (nq > 0) raster_small_tris(p, m.faces, sxy, siz, lane < nq, lane < nq ? queue[lane] : 0, vis);
             }
             __threadfence();
         }
@@ -408,6 +475,7 @@ __global__ void __launch_bounds__(RASTER_THREADS, 1) hpb_raster_kernel(const Ras
         float *dep = (p.flags & HPB_RENDER_DEPTH) ? p.depth + oi * p.depth_bs + ov : nullptr;
         uint8_t *msk = (p.flags & HPB_RENDER_MASK) ? p.mask + (size_t)hyp * p.mask_bs : nullptr;  // never view-interleaved
         const bool textured = m.tex != nullptr && m.uv != nullptr;
+        const bool want_z = dep != nullptr || msk != nullptr;
         for (int pix = rank * RASTER_THREADS + tid; pix < npix; pix += G * RASTER_THREADS) {
             int py = (int)__umulhi((unsigned)pix, p.w_magic);
             if (py * p.w > pix) --py;
@@ -419,44 +487,39 @@ __global__ void __launch_bounds__(RASTER_THREADS, 1) hpb_raster_kernel(const Ras
             }
             float r = 0.f, g = 0.f, bl = 0.f, n0 = 0.f, n1 = 0.f, n2 = 0.f, z = 0.f;
             if (key != HPB_VIS_EMPTY) {
-                const unsigned t = (unsigned)(key & 0xffffffffull);
-                TriSetup ts;
-                float iz0, iz1, iz2;
-                setup_tri(sxy, siz, __ldg(m.faces + t), ts, iz0, iz1, iz2);
+                const unsigned klo = (unsigned)(key & 0xffffffffull);
+                const int4 f = __ldg(m.faces + (klo >> 1));
+                const int2 a = sxy[f.x], b = sxy[f.y], c = sxy[f.z];
+                const float iz0 = siz[f.x], iz1 = siz[f.y], iz2 = siz[f.z];
                 const int fxp = px * HPB_SUBPIX + 128, fyp = py * HPB_SUBPIX + 128;
-                // barycentric edge values at the pixel centre; e0 + e1 + e2 == area2 exactly.  32-bit products are exact
-                // when the triangle's fixed-point bounding box is small (same bound as in phase B), the usual case.
+                // Edge values at the pixel centre in the triangle's own winding (no re-orientation: the weights below
+                // are ratios, so a common sign cancels).  For a covered pixel |e_i| <= |area2|, so 32-bit wrap-around
+                // arithmetic is exact unless the triangle is flagged wide.
+                const int dx0 = c.x - b.x, dy0 = c.y - b.y, dx1 = a.x - c.x, dy1 = a.y - c.y, dx2 = b.x - a.x, dy2 = b.y - a.y;
                 float fe0, fe1, fe2;
-                {
-                    const long long bw = (long long)max(ts.x0, max(ts.x1, ts.x2)) - min(ts.x0, min(ts.x1, ts.x2)) + 2 * HPB_SUBPIX;
-                    const long long bh = (long long)max(ts.y0, max(ts.y1, ts.y2)) - min(ts.y0, min(ts.y1, ts.y2)) + 2 * HPB_SUBPIX;
-                    if (bw * bh < (1ll << 29)) {
-                        const int e0 = (ts.x2 - ts.x1) * (fyp - ts.y1) - (ts.y2 - ts.y1) * (fxp - ts.x1);
-                        const int e1 = (ts.x0 - ts.x2) * (fyp - ts.y2) - (ts.y0 - ts.y2) * (fxp - ts.x2);
-                        const int e2 = (int)ts.area2 - e0 - e1;
-                        fe0 = (float)e0; fe1 = (float)e1; fe2 = (float)e2;
-                    } else {
-                        const long long e0 = (long long)(ts.x2 - ts.x1) * (fyp - ts.y1) - (long long)(ts.y2 - ts.y1) * (fxp - ts.x1);
-                        const long long e1 = (long long)(ts.x0 - ts.x2) * (fyp - ts.y2) - (long long)(ts.y0 - ts.y2) * (fxp - ts.x2);
-                        const long long e2 = ts.area2 - e0 - e1;
-                        fe0 = (float)e0; fe1 = (float)e1; fe2 = (float)e2;
-                    }
+                if (!(klo & 1u)) {
+                    fe0 = (float)(int)((unsigned)dx0 * (unsigned)(fyp - b.y) - (unsigned)dy0 * (unsigned)(fxp - b.x));
+                    fe1 = (float)(int)((unsigned)dx1 * (unsigned)(fyp - c.y) - (unsigned)dy1 * (unsigned)(fxp - c.x));
+                    fe2 = (float)(int)((unsigned)dx2 * (unsigned)(fyp - a.y) - (unsigned)dy2 * (unsigned)(fxp - a.x));
+                } else {
+                    fe0 = (float)((long long)dx0 * (fyp - b.y) - (long long)dy0 * (fxp - b.x));
+                    fe1 = (float)((long long)dx1 * (fyp - c.y) - (long long)dy1 * (fxp - c.x));
+                    fe2 = (float)((long long)dx2 * (fyp - a.y) - (long long)dy2 * (fxp - a.x));
                 }
-                const float inv = __frcp_rn((float)ts.area2);
-                const float l0 = fe0 * inv, l1 = fe1 * inv, l2 = fe2 * inv;
-                const float w0 = l0 * iz0, w1 = l1 * iz1, w2 = l2 * iz2;
-                const float iz = fmaf(l2, iz2, fmaf(l1, iz1, w0));
-                const float d = __uint_as_float((unsigned)(key >> 32));
-                z = p.a_f / (d - p.b_f);
-                if (d > p.eps_hi) z = 0.0f;
-                const float s = __frcp_rn(iz);
+                const float w0 = fe0 * iz0, w1 = fe1 * iz1, w2 = fe2 * iz2;
+                const float s = __frcp_rn((w0 + w1) + w2);
                 const float p0 = w0 * s, p1 = w1 * s, p2 = w2 * s;
+                if (want_z) {
+                    const float d = __uint_as_float((unsigned)(key >> 32));
+                    z = p.a_f / (d - p.b_f);
+                    if (d > p.eps_hi) z = 0.0f;
+                }
+                const float4 A0 = __ldg(m.nu + f.x), A1 = __ldg(m.nu + f.y), A2 = __ldg(m.nu + f.z);
                 if (nrm) {
                     // object-space normal interpolated over the triangle, rotated into the eye frame, normalised once
-                    const float *na = m.nrm + 3 * ts.i0, *nb = m.nrm + 3 * ts.i1, *nc = m.nrm + 3 * ts.i2;
-                    const float ox = fmaf(p2, __ldg(nc), fmaf(p1, __ldg(nb), p0 * __ldg(na)));
-                    const float oy = fmaf(p2, __ldg(nc + 1), fmaf(p1, __ldg(nb + 1), p0 * __ldg(na + 1)));
-                    const float oz = fmaf(p2, __ldg(nc + 2), fmaf(p1, __ldg(nb + 2), p0 * __ldg(na + 2)));
+                    const float ox = fmaf(p2, A2.x, fmaf(p1, A1.x, p0 * A0.x));
+                    const float oy = fmaf(p2, A2.y, fmaf(p1, A1.y, p0 * A0.y));
+                    const float oz = fmaf(p2, A2.z, fmaf(p1, A1.z, p0 * A0.z));
                     float nx = fmaf(sT[2], oz, fmaf(sT[1], oy, sT[0] * ox));
                     float ny = fmaf(sT[6], oz, fmaf(sT[5], oy, sT[4] * ox));
                     float nz = fmaf(sT[10], oz, fmaf(sT[9], oy, sT[8] * ox));
@@ -465,29 +528,25 @@ __global__ void __launch_bounds__(RASTER_THREADS, 1) hpb_raster_kernel(const Ras
                         const float rl = __frcp_rn(__fsqrt_rn(len2));
                         nx *= rl; ny *= rl; nz *= rl;
                     }
-                    n0 = encode_normal(nx, sLut);
-                    n1 = encode_normal(nz, sLut);
-                    n2 = encode_normal(-ny, sLut);
+                    n0 = encode_normal(nx, sNrmTab, sLut);
+                    n1 = encode_normal(nz, sNrmTab, sLut);
+                    n2 = encode_normal(-ny, sNrmTab, sLut);
                 }
                 if (rgb) {
                     float3 col = make_float3(255.0f, 255.0f, 255.0f);
                     if (textured) {
-                        const float2 t0 = __ldg(reinterpret_cast<const float2 *>(m.uv) + ts.i0);
-                        const float2 t1 = __ldg(reinterpret_cast<const float2 *>(m.uv) + ts.i1);
-                        const float2 t2 = __ldg(reinterpret_cast<const float2 *>(m.uv) + ts.i2);
-                        const float u = fmaf(p2, t2.x, fmaf(p1, t1.x, p0 * t0.x));
-                        const float v = fmaf(p2, t2.y, fmaf(p1, t1.y, p0 * t0.y));
-                        const float sc = (float)HPB_SUBPIX * inv;
-                        const float dl0x = (float)(-(ts.y2 - ts.y1)) * sc, dl0y = (float)(ts.x2 - ts.x1) * sc;
-                        const float dl1x = (float)(-(ts.y0 - ts.y2)) * sc, dl1y = (float)(ts.x0 - ts.x2) * sc;
-                        const float dl2x = (float)(-(ts.y1 - ts.y0)) * sc, dl2y = (float)(ts.x1 - ts.x0) * sc;
-                        const float g0x = dl0x * iz0, g1x = dl1x * iz1, g2x = dl2x * iz2;
-                        const float g0y = dl0y * iz0, g1y = dl1y * iz1, g2y = dl2y * iz2;
-                        const float dDx = g0x + g1x + g2x, dDy = g0y + g1y + g2y;
-                        const float dNux = fmaf(g2x, t2.x, fmaf(g1x, t1.x, g0x * t0.x));
-                        const float dNuy = fmaf(g2y, t2.x, fmaf(g1y, t1.x, g0y * t0.x));
-                        const float dNvx = fmaf(g2x, t2.y, fmaf(g1x, t1.y, g0x * t0.y));
-                        const float dNvy = fmaf(g2y, t2.y, fmaf(g1y, t1.y, g0y * t0.y));
+                        const float v0 = __ldg(m.tv + f.x), v1 = __ldg(m.tv + f.y), v2 = __ldg(m.tv + f.z);
+                        const float u = fmaf(p2, A2.w, fmaf(p1, A1.w, p0 * A0.w));
+                        const float v = fmaf(p2, v2, fmaf(p1, v1, p0 * v0));
+                        // analytic screen-space derivatives of (u,v) for the mip level, from the per-pixel steps of the
+                        // un-normalised perspective weights e_i / z_i
+                        const float g0x = ((float)(-dy0) * 256.0f) * iz0, g1x = ((float)(-dy1) * 256.0f) * iz1, g2x = ((float)(-dy2) * 256.0f) * iz2;
+                        const float g0y = ((float)dx0 * 256.0f) * iz0, g1y = ((float)dx1 * 256.0f) * iz1, g2y = ((float)dx2 * 256.0f) * iz2;
+                        const float dDx = (g0x + g1x) + g2x, dDy = (g0y + g1y) + g2y;
+                        const float dNux = fmaf(g2x, A2.w, fmaf(g1x, A1.w, g0x * A0.w));
+                        const float dNuy = fmaf(g2y, A2.w, fmaf(g1y, A1.w, g0y * A0.w));
+                        const float dNvx = fmaf(g2x, v2, fmaf(g1x, v1, g0x * v0));
+                        const float dNvy = fmaf(g2y, v2, fmaf(g1y, v1, g0y * v0));
                         const float W0 = (float)m.tex_w[0], H0 = (float)m.tex_h[0];
                         const float ax = (dNux - u * dDx) * s * W0, bx = (dNvx - v * dDx) * s * H0;
                         const float ay = (dNuy - u * dDy) * s * W0, by = (dNvy - v * dDy) * s * H0;
@@ -497,7 +556,7 @@ __global__ void __launch_bounds__(RASTER_THREADS, 1) hpb_raster_kernel(const Ras
                         if (rho2 > 1.0f && rho2 < 1.0e30f) lod = 0.5f * hp_log2(rho2);
                         col = m.tex_pow2 ? sample_trilinear<true>(m, u, v, lod) : sample_trilinear<false>(m, u, v, lod);
                     } else if (m.vcol) {
-                        const uchar4 c0 = __ldg(m.vcol + ts.i0), c1 = __ldg(m.vcol + ts.i1), c2 = __ldg(m.vcol + ts.i2);
+                        const uchar4 c0 = __ldg(m.vcol + f.x), c1 = __ldg(m.vcol + f.y), c2 = __ldg(m.vcol + f.z);
                         col.x = fmaf(p2, (float)c2.x, fmaf(p1, (float)c1.x, p0 * (float)c0.x));
                         col.y = fmaf(p2, (float)c2.y, fmaf(p1, (float)c1.y, p0 * (float)c0.y));
                         col.z = fmaf(p2, (float)c2.z, fmaf(p1, (float)c1.z, p0 * (float)c0.z));

@@ -101,6 +101,18 @@ def mesh_get_mip(ctx: Context, mesh_id: int, level: int) -> Optional[np.ndarray]
     return out
 
 
+def mesh_closed_sign(ctx: Context, mesh_id: int) -> int:
+    """-1 / +1 when the uploaded mesh is a closed, consistently oriented surface (its back faces are skipped), else 0."""
+    sign = ctypes.c_int(0)
+    ctx.check(ctx.lib.hpb_mesh_closed_sign(ctx.handle, mesh_id, ctypes.byref(sign)), "hpb_mesh_closed_sign")
+    return int(sign.value)
+
+
+def mesh_set_cull(ctx: Context, mesh_id: int, enable: bool) -> None:
+    """enable=False forces two-sided rendering of every triangle of the mesh (tests: culling must be invisible)."""
+    ctx.check(ctx.lib.hpb_mesh_set_cull(ctx.handle, mesh_id, 1 if enable else 0), "hpb_mesh_set_cull")
+
+
 # ------------------------------------------------------------------------------------------------
 # rasteriser
 # ------------------------------------------------------------------------------------------------

@@ -104,6 +104,16 @@ int hpb_mesh_upload(hpb_ctx *ctx, const float *verts_xyz, const float *normals, 
 int hpb_mesh_count(const hpb_ctx *ctx);
 /* Copies the mip level `level` (RGBA8, tex_w*tex_h*4 bytes) back to the host; for tests. */
 int hpb_mesh_get_mip(hpb_ctx *ctx, int32_t mesh_id, int level, uint8_t *out_host, int *w, int *h, int *levels);
+/*
+ * Closed-surface analysis done at upload.  *sign = -1 / +1 when the mesh (vertices welded by position) is a closed,
+ * consistently oriented surface whose front faces project with negative / positive signed area, 0 otherwise.  The
+ * rasteriser skips back faces of such meshes: on a closed surface every pixel a back face covers is also covered by
+ * a nearer front face, so the two-sided semantics of the reference (panda3d_scene_renderer.py:102, set_two_sided)
+ * are unchanged; scenes the near plane cuts open are rendered two-sided.  hpb_mesh_set_cull(ctx, id, 0) forces
+ * two-sided rendering of every triangle of the mesh (tests use it to check the equivalence), 1 restores the default.
+ */
+int hpb_mesh_closed_sign(hpb_ctx *ctx, int32_t mesh_id, int *sign);
+int hpb_mesh_set_cull(hpb_ctx *ctx, int32_t mesh_id, int enable);
 
 /*
  * Batched rasteriser: renders b single-object scenes in ONE launch.

@@ -35,6 +35,7 @@ class _HpoMesh(ctypes.Structure):
         ("tex_w", ctypes.c_void_p),
         ("tex_h", ctypes.c_void_p),
         ("tex_off", ctypes.c_void_p),
+        ("cull_sign", ctypes.c_int32),
     ]
 
 
@@ -75,6 +76,59 @@ def vertex_normals(pos: np.ndarray, faces: np.ndarray) -> np.ndarray:
     return n.astype(np.float32)
 
 
+def closed_surface_sign(pos: np.ndarray, faces: np.ndarray) -> int:
+    """Sign of the screen-space area2 of FRONT faces when the mesh is a closed, consistently oriented surface, else 0.
+
+    Vertices are welded by exact position; every undirected edge of the welded mesh must be used as often forwards
+    as backwards (a closed 2-chain) and every connected component must enclose a volume of the same sign.  Then along
+    any viewing ray #front hits == #back hits, so a covered pixel is always covered by a front face and skipping back
+    faces cannot change the two-sided image (panda3d_scene_renderer.py:102) except where a back face would have won a
+    depth tie against the front face it shares a silhouette edge with.  Restates hpb_closed_surface_sign (product).
+    """
+    p = np.ascontiguousarray(np.asarray(pos, np.float32)) + np.float32(0.0)  # -0.0 -> +0.0
+    f = np.asarray(faces, np.int64)
+    if not np.isfinite(p).all() or len(f) == 0:
+        return 0
+    _, wid = np.unique(p, axis=0, return_inverse=True)
+    wid = wid.reshape(-1)
+    w = wid[f]
+    ok = (w[:, 0] != w[:, 1]) & (w[:, 1] != w[:, 2]) & (w[:, 0] != w[:, 2])
+    w, fk = w[ok], f[ok]
+    if len(w) == 0:
+        return 0
+    u = np.concatenate([w[:, 0], w[:, 1], w[:, 2]])
+    v = np.concatenate([w[:, 1], w[:, 2], w[:, 0]])
+    lo, hi = np.minimum(u, v), np.maximum(u, v)
+    sgn = np.where(u < v, 1, -1)
+    n_w = int(wid.max()) + 1
+    bal = np.zeros(0)
+    keys, inv = np.unique(lo * n_w + hi, return_inverse=True)
+    bal = np.bincount(inv.reshape(-1), weights=sgn, minlength=len(keys))
+    if np.any(bal != 0):
+        return 0
+    # connected components of the welded mesh
+    from scipy.sparse import coo_matrix
+    from scipy.sparse.csgraph import connected_components
+
+    g = coo_matrix((np.ones(len(u)), (u, v)), shape=(n_w, n_w))
+    _, comp = connected_components(g, directed=False)
+    pd_ = p.astype(np.float64)
+    a, b, c = pd_[fk[:, 0]], pd_[fk[:, 1]], pd_[fk[:, 2]]
+    det = np.einsum("ij,ij->i", a, np.cross(b, c)) / 6.0
+    vol = np.bincount(comp[w[:, 0]], weights=det, minlength=int(comp.max()) + 1)
+    used = np.bincount(comp[w[:, 0]], minlength=int(comp.max()) + 1) > 0
+    diag = float(np.linalg.norm(pd_.max(0) - pd_.min(0)))
+    tol = 1e-9 * diag ** 3
+    vol = vol[used]
+    if not np.all(np.abs(vol) > tol):
+        return 0
+    if np.all(vol > 0):
+        return -1  # outward winding: front faces project with area2 < 0 in (x right, y down) pixel coordinates
+    if np.all(vol < 0):
+        return 1
+    return 0
+
+
 def mip_chain(tex_rgb: np.ndarray):
     """RGBA8 box-filter mip chain (level l+1 = max(1, size//2)), flattened into one buffer."""
     lib = _load()
@@ -104,9 +158,11 @@ class OracleMesh:
     float32(float64(v) * float64(scale)) (rigid_mesh_database.py:104-106 scales in float64).
     """
 
-    def __init__(self, verts, faces, normals=None, uv=None, vcolor=None, texture=None, scale: float = 1.0):
+    def __init__(self, verts, faces, normals=None, uv=None, vcolor=None, texture=None, scale: float = 1.0, cull: bool = True):
         self.pos = np.ascontiguousarray((np.asarray(verts, np.float64) * float(scale)).astype(np.float32))
         self.faces = np.ascontiguousarray(np.asarray(faces, np.int32))
+        self.closed_sign = closed_surface_sign(self.pos, self.faces)
+        self.cull_sign = self.closed_sign if cull else 0
         assert self.pos.ndim == 2 and self.pos.shape[1] == 3 and self.faces.ndim == 2 and self.faces.shape[1] == 3
         if normals is None:
             normals = vertex_normals(self.pos, self.faces)
@@ -128,6 +184,7 @@ class OracleMesh:
         s.pos, s.nrm, s.faces = self.pos.ctypes.data, self.nrm.ctypes.data, self.faces.ctypes.data
         s.uv = self.uv.ctypes.data if self.uv is not None else None
         s.vcol = self.vcol.ctypes.data if self.vcol is not None else None
+        s.cull_sign = int(self.cull_sign)
         if self.tex is not None:
             s.tex, s.tex_levels = self.tex.ctypes.data, len(self.tex_w)
             s.tex_w, s.tex_h, s.tex_off = self.tex_w.ctypes.data, self.tex_h.ctypes.data, self.tex_off.ctypes.data

@@ -13,7 +13,11 @@
  *                               (u,v) = (j+0.5, i+0.5), u = fx*X/Z + cx, v = fy*Y/Z + cy (OpenCV
  *                               camera axes, skew ignored, only K[0,0],K[1,1],K[0,2],K[1,2] read).
  *   near / far                  types.py:96-97 (z_near = 0.1, z_far = 10).
- *   culling                     none, two sided (panda3d_scene_renderer.py:102).
+ *   culling                     none, two sided (panda3d_scene_renderer.py:102).  Implemented as: back faces are
+ *                               skipped only on meshes proven closed and consistently oriented (cull_sign != 0,
+ *                               computed by oracle/raster.py:closed_surface_sign) in scenes the near plane does not
+ *                               cut -- there every pixel a back face covers is also covered by a nearer front face,
+ *                               so the two-sided image is unchanged (tests/test_oracle_raster.py checks it).
  *   depth                       GL depth d in [0,1], z = a/(d-b), a = 1/(1/far-1/near), b = -a/near,
  *                               d > 1-0.001 -> 0 (toolbox/renderer/utils.py:46-60).
  *   mask                        depth > 0 (panda3d_scene_renderer.py:360-367).
@@ -32,7 +36,8 @@
  * asks for 4x MSAA, :70-71), isotropic trilinear filtering (reference: anisotropic 16, :69),
  * triangles with a vertex in front of the near plane are dropped instead of clipped, vertices are
  * snapped to a 1/256-pixel grid and coverage uses exact integer edge functions with a top-left
- * rule; depth ties go to the lower triangle index (draw order under GL_LESS).
+ * rule; depth ties go to the lower triangle index (draw order under GL_LESS); window depth is evaluated
+ * from a per-triangle plane anchored at the first pixel of the triangle's clamped bounding box.
  *
  * All float arithmetic is written with explicit fmaf()/IEEE ops and this file must be built with
  * -ffp-contract=off so the CUDA kernels (compiled with -fmad=false) can follow it bit for bit.
@@ -64,6 +69,7 @@ typedef struct {
     const int32_t *tex_w; /* [levels] */
     const int32_t *tex_h;
     const int64_t *tex_off; /* [levels] offset in texels */
+    int32_t cull_sign;      /* sign of the screen-space area2 of front faces of a closed surface, 0 = two-sided */
 } hpo_mesh;
 
 static inline uint32_t f2u(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
@@ -97,20 +103,22 @@ static inline int floor_div_pix(int v) { /* largest j with j*256+128 <= v */
 }
 
 typedef struct {
-    int x0, y0, x1, y1, x2, y2;
-    int i0, i1, i2;
+    int x0, y0, x1, y1, x2, y2; /* oriented so that area2 > 0 */
+    float iz0, iz1, iz2;
     int64_t area2;
+    int orig_sign; /* sign of area2 in the face's own winding */
     int b0, b1, b2; /* tie-rule bias per edge function */
 } tri_setup;
 
 static inline int edge_bias(int dx, int dy) { return (dy < 0 || (dy == 0 && dx > 0)) ? 0 : -1; }
 
-static int setup_tri(const int *sx, const int *sy, const uint8_t *vbad, const int32_t *f, tri_setup *t) {
+static int setup_tri(const int *sx, const int *sy, const float *viz, const uint8_t *vbad, const int32_t *f, tri_setup *t) {
     int i0 = f[0], i1 = f[1], i2 = f[2];
     if (vbad[i0] | vbad[i1] | vbad[i2]) return 0;
     int x0 = sx[i0], y0 = sy[i0], x1 = sx[i1], y1 = sy[i1], x2 = sx[i2], y2 = sy[i2];
     int64_t area2 = (int64_t)(x1 - x0) * (int64_t)(y2 - y0) - (int64_t)(x2 - x0) * (int64_t)(y1 - y0);
     if (area2 == 0) return 0;
+    t->orig_sign = area2 < 0 ? -1 : 1;
     if (area2 < 0) {
         int tx = x1, ty = y1, ti = i1;
         x1 = x2; y1 = y2; i1 = i2;
@@ -118,7 +126,7 @@ static int setup_tri(const int *sx, const int *sy, const uint8_t *vbad, const in
         area2 = -area2;
     }
     t->x0 = x0; t->y0 = y0; t->x1 = x1; t->y1 = y1; t->x2 = x2; t->y2 = y2;
-    t->i0 = i0; t->i1 = i1; t->i2 = i2;
+    t->iz0 = viz[i0]; t->iz1 = viz[i1]; t->iz2 = viz[i2];
     t->area2 = area2;
     t->b0 = edge_bias(x2 - x1, y2 - y1);
     t->b1 = edge_bias(x0 - x2, y0 - y2);
@@ -211,12 +219,13 @@ static int render_one(const hpo_mesh *m, const float *T, const float *K, int h, 
     const float a_f = (float)a_d, b_f = (float)(-a_d / (double)znear);
     const float eps_hi = (float)(1.0 - 0.001);
 
+    int any_clipped = 0;
     for (int64_t i = 0; i < nv; ++i) {
         const float x = m->pos[3 * i], y = m->pos[3 * i + 1], z = m->pos[3 * i + 2];
         const float X = fmaf(T[2], z, fmaf(T[1], y, fmaf(T[0], x, T[3])));
         const float Y = fmaf(T[6], z, fmaf(T[5], y, fmaf(T[4], x, T[7])));
         const float Z = fmaf(T[10], z, fmaf(T[9], y, fmaf(T[8], x, T[11])));
-        if (!(Z >= znear)) { vbad[i] = 1; sx[i] = sy[i] = 0; viz[i] = 0.0f; continue; }
+        if (!(Z >= znear)) { vbad[i] = 1; sx[i] = sy[i] = 0; viz[i] = 0.0f; any_clipped = 1; continue; }
         vbad[i] = 0;
         const float iz = 1.0f / Z;
         viz[i] = iz;
@@ -224,10 +233,13 @@ static int render_one(const hpo_mesh *m, const float *T, const float *K, int h, 
         sy[i] = snap(fmaf(fy, Y * iz, cy));
     }
 
-    /* pass 1: visibility (depth bits << 32 | triangle id), min wins */
+    /* pass 1: visibility (depth bits << 32 | triangle id << 1 | wide), min wins.  Back faces of a closed surface are
+     * skipped unless the near plane has cut the surface open. */
+    const int cull = (!any_clipped && fx > 0.0f && fy > 0.0f) ? m->cull_sign : 0;
     for (int64_t t = 0; t < nf; ++t) {
         tri_setup ts;
-        if (!setup_tri(sx, sy, vbad, m->faces + 3 * t, &ts)) continue;
+        if (!setup_tri(sx, sy, viz, vbad, m->faces + 3 * t, &ts)) continue;
+        if (cull != 0 && ts.orig_sign != cull) continue;
         int mnx = ts.x0 < ts.x1 ? ts.x0 : ts.x1; if (ts.x2 < mnx) mnx = ts.x2;
         int mxx = ts.x0 > ts.x1 ? ts.x0 : ts.x1; if (ts.x2 > mxx) mxx = ts.x2;
         int mny = ts.y0 < ts.y1 ? ts.y0 : ts.y1; if (ts.y2 < mny) mny = ts.y2;
@@ -239,19 +251,32 @@ static int render_one(const hpo_mesh *m, const float *T, const float *K, int h, 
         if (jx1 > w - 1) jx1 = w - 1;
         if (jy1 > h - 1) jy1 = h - 1;
         if (jx0 > jx1 || jy0 > jy1) continue;
-        const float inv = 1.0f / (float)ts.area2;
-        const float iz0 = viz[ts.i0], iz1 = viz[ts.i1], iz2 = viz[ts.i2];
+        /* depth plane anchored at the first pixel of the clamped bounding box */
+        float Dc, Dx, Dy;
+        {
+            int64_t e0o, e1o, e2o;
+            edges_at(&ts, jx0 * SUBPIX + 128, jy0 * SUBPIX + 128, &e0o, &e1o, &e2o);
+            const float inv = 1.0f / (float)ts.area2;
+            const float izc = fmaf((float)e2o * inv, ts.iz2, fmaf((float)e1o * inv, ts.iz1, ((float)e0o * inv) * ts.iz0));
+            const float d1 = ts.iz1 - ts.iz0, d2 = ts.iz2 - ts.iz0;
+            const float sx1 = (float)(ts.y2 - ts.y0) * 256.0f, sx2 = (float)(ts.y0 - ts.y1) * 256.0f;
+            const float sy1 = (float)(ts.x0 - ts.x2) * 256.0f, sy2 = (float)(ts.x1 - ts.x0) * 256.0f;
+            const float gx = fmaf(sx2, d2, sx1 * d1) * inv;
+            const float gy = fmaf(sy2, d2, sy1 * d1) * inv;
+            Dc = (inv_near - izc) * cd;
+            Dx = -(gx * cd);
+            Dy = -(gy * cd);
+        }
+        const uint64_t lo = ((uint64_t)(uint32_t)t << 1) | (ts.area2 >= ((int64_t)1 << 31) ? 1u : 0u);
         for (int py = jy0; py <= jy1; ++py) {
             for (int px = jx0; px <= jx1; ++px) {
                 int64_t e0, e1, e2;
                 edges_at(&ts, px * SUBPIX + 128, py * SUBPIX + 128, &e0, &e1, &e2);
                 if ((e0 + ts.b0) < 0 || (e1 + ts.b1) < 0 || (e2 + ts.b2) < 0) continue;
-                const float l0 = (float)e0 * inv, l1 = (float)e1 * inv, l2 = (float)e2 * inv;
-                const float iz = fmaf(l2, iz2, fmaf(l1, iz1, l0 * iz0));
-                float d = (inv_near - iz) * cd;
+                float d = fmaf(Dx, (float)(px - jx0), fmaf(Dy, (float)(py - jy0), Dc));
                 if (!(d <= 1.0f)) continue;
                 if (d < 0.0f) d = 0.0f;
-                const uint64_t key = ((uint64_t)f2u(d) << 32) | (uint64_t)(uint32_t)t;
+                const uint64_t key = ((uint64_t)f2u(d) << 32) | lo;
                 uint64_t *slot = zb + (int64_t)py * w + px;
                 if (key < *slot) *slot = key;
             }
@@ -266,31 +291,35 @@ static int render_one(const hpo_mesh *m, const float *T, const float *K, int h, 
             const int64_t pi = (int64_t)py * w + px;
             const uint64_t key = zb[pi];
             if (key == ~(uint64_t)0) continue;
-            const int64_t t = (int64_t)(key & 0xffffffffu);
-            tri_setup ts;
-            setup_tri(sx, sy, vbad, m->faces + 3 * t, &ts);
-            int64_t e0, e1, e2;
-            edges_at(&ts, px * SUBPIX + 128, py * SUBPIX + 128, &e0, &e1, &e2);
-            const float inv = 1.0f / (float)ts.area2;
-            const float iz0 = viz[ts.i0], iz1 = viz[ts.i1], iz2 = viz[ts.i2];
-            const float l0 = (float)e0 * inv, l1 = (float)e1 * inv, l2 = (float)e2 * inv;
-            const float w0 = l0 * iz0, w1 = l1 * iz1, w2 = l2 * iz2;
-            const float iz = fmaf(l2, iz2, fmaf(l1, iz1, w0));
-            const float d = u2f((uint32_t)(key >> 32));
+            const int64_t t = (int64_t)((key & 0xffffffffu) >> 1);
+            /* edge values at the pixel centre in the face's own winding: the weights are ratios, so the common sign
+             * of e0, e1, e2 (= the sign of area2) cancels and no area division is needed */
+            const int32_t *f = m->faces + 3 * t;
+            const int i0 = f[0], i1 = f[1], i2 = f[2];
+            const int fxp = px * SUBPIX + 128, fyp = py * SUBPIX + 128;
+            const int dx0 = sx[i2] - sx[i1], dy0 = sy[i2] - sy[i1];
+            const int dx1 = sx[i0] - sx[i2], dy1 = sy[i0] - sy[i2];
+            const int dx2 = sx[i1] - sx[i0], dy2 = sy[i1] - sy[i0];
+            const float fe0 = (float)((int64_t)dx0 * (int64_t)(fyp - sy[i1]) - (int64_t)dy0 * (int64_t)(fxp - sx[i1]));
+            const float fe1 = (float)((int64_t)dx1 * (int64_t)(fyp - sy[i2]) - (int64_t)dy1 * (int64_t)(fxp - sx[i2]));
+            const float fe2 = (float)((int64_t)dx2 * (int64_t)(fyp - sy[i0]) - (int64_t)dy2 * (int64_t)(fxp - sx[i0]));
+            const float iz0 = viz[i0], iz1 = viz[i1], iz2 = viz[i2];
+            const float w0 = fe0 * iz0, w1 = fe1 * iz1, w2 = fe2 * iz2;
+            const float s = 1.0f / ((w0 + w1) + w2);
+            const float p0 = w0 * s, p1 = w1 * s, p2 = w2 * s;
             if (depth || mask) {
+                const float d = u2f((uint32_t)(key >> 32));
                 float z = a_f / (d - b_f);
                 if (d > eps_hi) z = 0.0f;
                 if (depth) depth[pi] = z;
                 if (mask) mask[pi] = z > 0.0f;
             }
-            const float s = 1.0f / iz;
-            const float p0 = w0 * s, p1 = w1 * s, p2 = w2 * s;
             if (nrm_out) {
                 /* object-space normal interpolated perspective-correctly, then rotated into the eye frame and
                  * normalised once per pixel (for an orthonormal R identical to interpolating per-vertex eye normals) */
                 float ox = 0.0f, oy = 0.0f, oz = 0.0f;
                 if (m->nrm) {
-                    const float *n0 = m->nrm + 3 * ts.i0, *n1 = m->nrm + 3 * ts.i1, *n2 = m->nrm + 3 * ts.i2;
+                    const float *n0 = m->nrm + 3 * i0, *n1 = m->nrm + 3 * i1, *n2 = m->nrm + 3 * i2;
                     ox = fmaf(p2, n2[0], fmaf(p1, n1[0], p0 * n0[0]));
                     oy = fmaf(p2, n2[1], fmaf(p1, n1[1], p0 * n0[1]));
                     oz = fmaf(p2, n2[2], fmaf(p1, n1[2], p0 * n0[2]));
@@ -307,17 +336,14 @@ static int render_one(const hpo_mesh *m, const float *T, const float *K, int h, 
             if (rgb) {
                 float col[3] = {255.0f, 255.0f, 255.0f};
                 if (m->tex && m->uv) {
-                    const float *t0 = m->uv + 2 * ts.i0, *t1 = m->uv + 2 * ts.i1, *t2 = m->uv + 2 * ts.i2;
+                    const float *t0 = m->uv + 2 * i0, *t1 = m->uv + 2 * i1, *t2 = m->uv + 2 * i2;
                     const float u = fmaf(p2, t2[0], fmaf(p1, t1[0], p0 * t0[0]));
                     const float v = fmaf(p2, t2[1], fmaf(p1, t1[1], p0 * t0[1]));
-                    /* analytic screen-space derivatives of (u,v) for the mip level */
-                    const float sc = (float)SUBPIX * inv;
-                    const float dl0x = (float)(-(ts.y2 - ts.y1)) * sc, dl0y = (float)(ts.x2 - ts.x1) * sc;
-                    const float dl1x = (float)(-(ts.y0 - ts.y2)) * sc, dl1y = (float)(ts.x0 - ts.x2) * sc;
-                    const float dl2x = (float)(-(ts.y1 - ts.y0)) * sc, dl2y = (float)(ts.x1 - ts.x0) * sc;
-                    const float g0x = dl0x * iz0, g1x = dl1x * iz1, g2x = dl2x * iz2;
-                    const float g0y = dl0y * iz0, g1y = dl1y * iz1, g2y = dl2y * iz2;
-                    const float dDx = g0x + g1x + g2x, dDy = g0y + g1y + g2y;
+                    /* analytic screen-space derivatives of (u,v) for the mip level, from the per-pixel steps of the
+                     * un-normalised perspective weights e_i / z_i */
+                    const float g0x = ((float)(-dy0) * 256.0f) * iz0, g1x = ((float)(-dy1) * 256.0f) * iz1, g2x = ((float)(-dy2) * 256.0f) * iz2;
+                    const float g0y = ((float)dx0 * 256.0f) * iz0, g1y = ((float)dx1 * 256.0f) * iz1, g2y = ((float)dx2 * 256.0f) * iz2;
+                    const float dDx = (g0x + g1x) + g2x, dDy = (g0y + g1y) + g2y;
                     const float dNux = fmaf(g2x, t2[0], fmaf(g1x, t1[0], g0x * t0[0]));
                     const float dNuy = fmaf(g2y, t2[0], fmaf(g1y, t1[0], g0y * t0[0]));
                     const float dNvx = fmaf(g2x, t2[1], fmaf(g1x, t1[1], g0x * t0[1]));
@@ -343,7 +369,7 @@ static int render_one(const hpo_mesh *m, const float *T, const float *K, int h, 
                         for (int k = 0; k < 3; ++k) col[k] = ca[k];
                     }
                 } else if (m->vcol) {
-                    const uint8_t *c0 = m->vcol + 4 * ts.i0, *c1 = m->vcol + 4 * ts.i1, *c2 = m->vcol + 4 * ts.i2;
+                    const uint8_t *c0 = m->vcol + 4 * i0, *c1 = m->vcol + 4 * i1, *c2 = m->vcol + 4 * i2;
                     for (int k = 0; k < 3; ++k)
                         col[k] = fmaf(p2, (float)c2[k], fmaf(p1, (float)c1[k], p0 * (float)c0[k]));
                 }

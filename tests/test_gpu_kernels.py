@@ -182,6 +182,35 @@ def test_render_big_triangles_int64_path(ctx):
     assert (nrm.cpu().numpy() == ref["normals"]).all() and (rgb.cpu().numpy() == ref["rgb"]).all()
 
 
+def test_backface_skipping_matches_two_sided(ctx, can):
+    """Closed-surface analysis agrees with the oracle's; skipping back faces of the (closed) can changes nothing."""
+    from happypose_b200 import ops
+
+    om, mid = can
+    assert ops.mesh_closed_sign(ctx, mid) == om.closed_sign == -1
+    v, f, _ = icosphere(2, 0.05)
+    for faces in (f, f[:, ::-1].copy(), f[:-1].copy()):
+        assert ops.mesh_closed_sign(ctx, ops.mesh_upload(ctx, v, faces)) == oraster.closed_surface_sign(v, faces)
+    rs = np.random.RandomState(12)
+    T, K = random_crop_scene(rs, 40)
+    T[0, 2, 3] = 0.12  # cut by the near plane: two-sided automatically
+    ids = torch.full((40,), mid)
+    a = ops.render(ctx, ids, torch.as_tensor(T), torch.as_tensor(K), (240, 320), render_normals=True, render_depth=True)
+    ops.mesh_set_cull(ctx, mid, False)
+    try:
+        b = ops.render(ctx, ids, torch.as_tensor(T), torch.as_tensor(K), (240, 320), render_normals=True, render_depth=True)
+    finally:
+        ops.mesh_set_cull(ctx, mid, True)
+    for x, y in zip(a[:3], b[:3]):
+        assert (x != y).float().mean().item() <= 1e-4
+    assert torch.equal(a[2][0], b[2][0]) and (a[2][0] > 0).any()
+    # the two-sided path itself is still oracle-exact
+    om2 = oraster.OracleMesh(om.pos, om.faces, om.nrm, om.uv, scale=1.0, cull=False)
+    om2.tex, om2.tex_w, om2.tex_h, om2.tex_off = om.tex, om.tex_w, om.tex_h, om.tex_off
+    ref = oraster.render([om2], [0] * 8, T[:8], K[:8], (240, 320), render_normals=True, render_depth=True, n_threads=8)
+    assert (b[2][:8].cpu().numpy() == ref["depth"]).all() and (b[0][:8].cpu().numpy() == ref["rgb"]).all()
+
+
 def test_render_into_network_input_slice(ctx, can):
     from happypose_b200 import ops
 

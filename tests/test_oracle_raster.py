@@ -96,3 +96,46 @@ def test_far_and_near_rules():
     assert out["rgb"][0].max() == 1.0 and out["depth"][0].max() == 0 and not out["mask"][0].any()
     assert out["rgb"][1].max() == 0
     assert out["depth"][2].max() > 0 and out["depth"][2][out["depth"][2] > 0].min() >= 0.1
+
+
+def test_closed_surface_analysis():
+    """Back faces are skipped only on meshes proven closed (welded by position) and consistently oriented."""
+    v, f, _ = icosphere(2, 0.05)
+    assert raster.closed_surface_sign(v, f) == -1          # outward winding
+    assert raster.closed_surface_sign(v, f[:, ::-1]) == 1  # inside-out
+    assert raster.closed_surface_sign(v, f[:-1]) == 0      # one face missing: open
+    g = f.copy()
+    g[0] = g[0, ::-1]
+    assert raster.closed_surface_sign(v, g) == 0           # one face flipped: inconsistent
+    quad_v = np.array([[-1, -1, 0], [1, -1, 0], [1, 1, 0], [-1, 1, 0]], np.float32)
+    quad_f = np.array([[0, 1, 2], [0, 2, 3]], np.int32)
+    assert raster.closed_surface_sign(quad_v, quad_f) == 0
+    # a two-sided sheet is a closed chain of zero volume: no orientation, no culling
+    assert raster.closed_surface_sign(quad_v, np.concatenate([quad_f, quad_f[:, ::-1]])) == 0
+    # texture seams duplicate vertices: welding by position keeps the surface closed
+    v2 = np.concatenate([v, v[:5]])
+    f2 = f.copy()
+    f2[f2 == 3] = len(v) + 3
+    assert raster.closed_surface_sign(v2, f2) == -1
+    # two spheres, one inside-out: mixed orientation -> no culling
+    f3 = np.concatenate([f, f[:, ::-1] + len(v)])
+    assert raster.closed_surface_sign(np.concatenate([v, v + 0.2]), f3) == 0
+
+
+def test_backface_skipping_is_invisible(can, can_mesh_arrays):
+    """The can is closed (seams welded): rendering with back faces skipped == rendering every triangle two-sided."""
+    d = can_mesh_arrays
+    assert can.closed_sign == -1 and can.cull_sign == -1
+    two_sided = raster.OracleMesh(d["verts"], d["faces"], d["normals"], d["uv"], texture=d["texture"], scale=0.001, cull=False)
+    assert two_sided.cull_sign == 0
+    rs = np.random.RandomState(11)
+    from tests.scenes import random_crop_scene
+
+    T, K = random_crop_scene(rs, 16)
+    T[0, 2, 3] = 0.12  # the near plane (0.1 m) cuts the can open: culling must switch itself off for this scene
+    a = raster.render([can], [0] * 16, T, K, (240, 320), render_normals=True, render_depth=True, n_threads=8)
+    b = raster.render([two_sided], [0] * 16, T, K, (240, 320), render_normals=True, render_depth=True, n_threads=8)
+    assert (a["depth"][0] > 0).any()
+    for k in ("rgb", "normals", "depth"):
+        assert (a[k] != b[k]).mean() <= 1e-4, k  # silhouette depth ties may pick the other face of a shared edge
+    assert (a["depth"][0] == b["depth"][0]).all() and (a["rgb"][0] == b["rgb"][0]).all()
