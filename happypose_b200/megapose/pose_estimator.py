@@ -164,9 +164,9 @@ class PoseEstimator(torch.nn.Module):
                 for k, v in zip(keys, (o.TCO_output, o.TCO_input, o.K_crop, o.K, o.boxes_rend, o.boxes_crop)):
                     chunks[n][k].append(v)
 
-        def make_infos(cache=[]):  # one frame shared by all iterations, built when first looked at
+        def make_infos(cache=[]):  # one column set shared by all iterations, built when first looked at
             if not cache:
-                cache.append(data_TCO_input.infos.assign(refiner_batch_idx=batch_idx_col, refiner_instance_idx=inst_idx_col))
+                cache.append(tc.cols_assign(data_TCO_input._cols(), refiner_batch_idx=batch_idx_col, refiner_instance_idx=inst_idx_col))
             return cache[0]
 
         row_tensors = {"obj_ids": obj_ids, "mesh_ids": mesh_ids, "im_ids": im_ids}
@@ -242,13 +242,14 @@ class PoseEstimator(torch.nn.Module):
         ids = self._row_ids(self.coarse_model, data_TCO, observation.images.device)
         logits, scores, render_time, model_time, n_batches, debug_data = self._score_rows(
             observation, ids, data_TCO.poses, cuda_timer, return_debug_data)
-        both = torch.stack([logits.reshape(n, -1)[:, 0], scores.reshape(n, -1)[:, 0]])
+        # the stage's single D2H copy: enqueued here, awaited when the frame is looked at
+        both = tc.HostCopy(torch.stack([logits.reshape(n, -1)[:, 0], scores.reshape(n, -1)[:, 0]]))
 
-        def add_scores(df, both=both):  # the stage's single D2H copy, taken when the frame is looked at
-            host = both.cpu().numpy()
-            return df.assign(pose_logit=host[0], pose_score=host[1])
+        def add_scores(cols, both=both):
+            host = both.numpy()
+            return tc.cols_assign(cols, pose_logit=host[0], pose_score=host[1])
 
-        data_TCO.map_infos(add_scores)  # in place, like the reference (df["pose_logit"] = ...; data_TCO.infos = df)
+        data_TCO.map_cols(add_scores)  # in place, like the reference (df["pose_logit"] = ...; data_TCO.infos = df)
 
         elapsed = time.time() - start_time
         timing_str = f"time: {elapsed:.2f}, model_time: {model_time:.2f}, render_time: {render_time:.2f}"
@@ -303,14 +304,15 @@ class PoseEstimator(torch.nn.Module):
             H, W = dbg["images_crop"].shape[2:]
             debug_data = {"images_crop": dbg["images_crop"].reshape([B, M, -1, H, W]), "renders": dbg["renders"].reshape([B, M, -1, H, W])}
 
-        both = torch.stack([logits.flatten(), scores.flatten()])
+        # the stage's single D2H copy: enqueued here, awaited when the frame is looked at
+        both = tc.HostCopy(torch.stack([logits.flatten(), scores.flatten()]))
 
         def make_infos(df=df, both=both):
-            host = both.cpu().numpy()  # the stage's single D2H copy, taken when the frame is looked at
             pos = np.repeat(np.arange(B), M)
-            df_h = df.iloc[pos].reset_index(drop=True)
-            return df_h.assign(hypothesis_id=np.tile(np.arange(M), B), bbox_id=np.repeat(df.index.to_numpy(), M),
-                               coarse_logit=host[0], coarse_score=host[1])
+            cols = tc.cols_take(tc.cols_of(df), pos)
+            host = both.numpy()
+            return tc.cols_assign(cols, hypothesis_id=np.tile(np.arange(M), B), bbox_id=np.repeat(df.index.to_numpy(), M),
+                                  coarse_logit=host[0], coarse_score=host[1])
 
         elapsed = time.time() - start_time
         timing_str = f"time: {elapsed:.2f}, model_time: {model_time:.2f}, render_time: {render_time:.2f}"

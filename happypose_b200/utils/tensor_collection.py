@@ -13,6 +13,52 @@ import pandas as pd
 import torch
 
 
+class HostCopy:
+    """Device -> pinned-host copy enqueued NOW on the current stream, read later: `.numpy()` waits for this copy's
+    event only, not for everything the caller has enqueued since.  Lets a stage's deferred DataFrame be built while the
+    GPU is still busy with the next stages (CPU tensors pass straight through)."""
+
+    def __init__(self, t: torch.Tensor):
+        t = t.detach()
+        if t.is_cuda:
+            self.buf = torch.empty(t.shape, dtype=t.dtype, device="cpu", pin_memory=True)
+            self.buf.copy_(t, non_blocking=True)
+            self.event = torch.cuda.Event()
+            self.event.record()
+        else:
+            self.buf, self.event = t, None
+
+    def numpy(self) -> np.ndarray:
+        if self.event is not None:
+            self.event.synchronize()
+            self.event = None
+        return self.buf.numpy()
+
+
+# Deferred frames travel between stages as plain {column: array} dicts ("cols"): a take / an added column is then a
+# numpy operation, and ONE DataFrame is constructed when somebody looks at `.infos` (pandas spends ~0.4 ms per
+# iloc / assign / constructor call on even a one-row frame, which used to be the tail of every pipeline call).
+def cols_of(df: pd.DataFrame) -> dict:
+    return {c: df[c]._values for c in df.columns}
+
+
+def cols_take(cols: dict, ids: np.ndarray) -> dict:
+    ids = np.asarray(ids)
+    return {c: v.take(ids) for c, v in cols.items()}
+
+
+def cols_assign(cols: dict, **new) -> dict:
+    out = dict(cols)
+    out.update(new)
+    return out
+
+
+def cols_to_frame(cols: dict, n_rows: int) -> pd.DataFrame:
+    if not cols:
+        return pd.DataFrame(index=pd.RangeIndex(n_rows))
+    return pd.DataFrame(cols, copy=False)
+
+
 class TensorCollection:
     def __init__(self, **tensors):
         self.__dict__["_tensors"] = {}
@@ -102,6 +148,7 @@ class PandasTensorCollection(TensorCollection):
         super().__init__(**tensors)
         self.__dict__["_infos"] = None
         self.__dict__["_infos_thunk"] = None
+        self.__dict__["_cols_cache"] = None
         self.__dict__["_n_rows"] = None
         self.__dict__["_row_tensors"] = dict(row_tensors) if row_tensors else {}
         if callable(infos) and not isinstance(infos, pd.DataFrame):
@@ -113,20 +160,39 @@ class PandasTensorCollection(TensorCollection):
         self.__dict__["meta"] = {}
 
     # -- deferred DataFrame -----------------------------------------------------------------------
+    def _cols(self) -> dict:
+        """Column dict of the frame (runs the deferred thunk once; thunks may return a DataFrame or a column dict)."""
+        d = self.__dict__
+        if d.get("_cols_cache") is None:
+            if d["_infos"] is not None:
+                d["_cols_cache"] = cols_of(d["_infos"])
+            else:
+                res = d["_infos_thunk"]()
+                if isinstance(res, pd.DataFrame):
+                    res = res.reset_index(drop=True)
+                    assert len(res) == d["_n_rows"], (len(res), d["_n_rows"])
+                    d["_infos"] = res
+                    res = cols_of(res)
+                d["_cols_cache"] = res
+                d["_infos_thunk"] = None
+        return d["_cols_cache"]
+
     @property
     def infos(self) -> pd.DataFrame:
-        if self.__dict__["_infos"] is None:
-            thunk = self.__dict__["_infos_thunk"]
-            df = thunk().reset_index(drop=True)
-            assert len(df) == self.__dict__["_n_rows"], (len(df), self.__dict__["_n_rows"])
-            self.__dict__["_infos"] = df
-            self.__dict__["_infos_thunk"] = None
-        return self.__dict__["_infos"]
+        d = self.__dict__
+        if d["_infos"] is None:
+            cols = self._cols()
+            if d["_infos"] is None:
+                df = cols_to_frame(cols, d["_n_rows"])
+                assert len(df) == d["_n_rows"], (len(df), d["_n_rows"])
+                d["_infos"] = df
+        return d["_infos"]
 
     @infos.setter
     def infos(self, df: pd.DataFrame) -> None:
         self.__dict__["_infos"] = df
         self.__dict__["_infos_thunk"] = None
+        self.__dict__["_cols_cache"] = None
         self.__dict__["_n_rows"] = None
 
     def __setattr__(self, name, value):
@@ -135,20 +201,36 @@ class PandasTensorCollection(TensorCollection):
         else:
             super().__setattr__(name, value)
 
+    def map_cols(self, fn) -> None:
+        """In-place, deferred `columns = fn(columns)` on the column dict (the row count must not change)."""
+        d = self.__dict__
+        n = len(self)
+        if d.get("_cols_cache") is not None:
+            old = d["_cols_cache"]
+            source = lambda: old  # noqa: E731
+        elif d["_infos"] is not None:
+            frame = d["_infos"]
+            source = lambda: cols_of(frame.reset_index(drop=True))  # noqa: E731
+        else:
+            thunk = d["_infos_thunk"]
+
+            def source():
+                res = thunk()
+                return cols_of(res.reset_index(drop=True)) if isinstance(res, pd.DataFrame) else res
+
+        d["_infos"] = None
+        d["_cols_cache"] = None
+        d["_infos_thunk"] = lambda: fn(source())
+        d["_n_rows"] = n
+
     def map_infos(self, fn) -> None:
         """In-place, deferred `self.infos = fn(self.infos)` (the row count must not change)."""
-        if self.infos_ready:
-            old, n = self.__dict__["_infos"], len(self.__dict__["_infos"])
-            source = lambda: old  # noqa: E731
-        else:
-            source, n = self.__dict__["_infos_thunk"], self.__dict__["_n_rows"]
-        self.__dict__["_infos"] = None
-        self.__dict__["_infos_thunk"] = lambda: fn(source().reset_index(drop=True))
-        self.__dict__["_n_rows"] = n
+        n = len(self)
+        self.map_cols(lambda cols: fn(cols_to_frame(cols, n)))
 
     @property
     def infos_ready(self) -> bool:
-        return self.__dict__["_infos"] is not None
+        return self.__dict__["_infos"] is not None or self.__dict__.get("_cols_cache") is not None
 
     @property
     def row_tensors(self) -> dict:
@@ -181,7 +263,8 @@ class PandasTensorCollection(TensorCollection):
             if ids.dtype != torch.bool:
                 # deferred: the index tensor is read back only when somebody looks at the frame
                 parent = self
-                return PandasTensorCollection(lambda: parent.infos.iloc[ids.detach().cpu().numpy()], n_rows=int(ids.numel()),
+                host_ids = HostCopy(ids)  # the copy is enqueued now, awaited when the frame is looked at
+                return PandasTensorCollection(lambda: cols_take(parent._cols(), host_ids.numpy()), n_rows=int(ids.numel()),
                                               row_tensors=rt, **tensors)
             return PandasTensorCollection(self.infos.iloc[ids.detach().cpu().numpy()], row_tensors=rt, **tensors)
         rt = {}
@@ -192,7 +275,7 @@ class PandasTensorCollection(TensorCollection):
 
     def __len__(self):
         n = self.__dict__["_n_rows"]
-        return n if (n is not None and not self.infos_ready) else len(self.infos)
+        return n if n is not None else len(self.infos)
 
     def gather_distributed(self, tmp_dir=None):
         """Reference: pickle files in tmp_dir + barriers (tensor_collection.py:166-187).  Here: all_gather_object
