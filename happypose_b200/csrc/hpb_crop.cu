@@ -22,10 +22,8 @@
 namespace {
 
 constexpr int CROP_SPAN = 4;       // dense tap span handled by the fast path
-constexpr int CROP_BAND_MAX = 48;
-constexpr int CROP_CHUNK = 8;    // output rows per chunk of the column march
-constexpr int CROP_SROWS = 20;   // filtered source rows staged per chunk (8 rows * bin_h <= 1.9 + 4 taps)  // most output rows one CTA handles (fewer when the batch is small)
-constexpr int CROP_MAX_THREADS = 384;  // output widths beyond this take the generic path
+constexpr int CROP_BAND_MAX = 120;  // most output rows one CTA handles (fewer when the batch is small)
+constexpr int CROP_MAX_THREADS = 320;  // output columns per CTA (wider outputs use several column tiles, blockIdx.z)
 
 struct CropBoxParams {
     const float *points;
@@ -166,52 +164,60 @@ __device__ __forceinline__ AxisTap axis_tap(float c, int n) {
 // Dense tap weights of the 4 samples of output bin `i` along one axis.  Returns false when the span exceeds
 // CROP_SPAN (heavy down-sampling): the caller then takes the generic path.
 __device__ __forceinline__ bool axis_weights(float start, float bin, int i, int n, int &base, float (&wt)[CROP_SPAN]) {
-#pragma unroll
-    for (int k = 0; k < CROP_SPAN; ++k) wt[k] = 0.0f;
-    AxisTap taps[4];
+    AxisTap t0 = axis_tap(start + (float)i * bin + (0.0f + 0.5f) * bin / 4.0f, n);
+    AxisTap t1 = axis_tap(start + (float)i * bin + (1.0f + 0.5f) * bin / 4.0f, n);
+    AxisTap t2 = axis_tap(start + (float)i * bin + (2.0f + 0.5f) * bin / 4.0f, n);
+    AxisTap t3 = axis_tap(start + (float)i * bin + (3.0f + 0.5f) * bin / 4.0f, n);
     int lo_min = 0x7fffffff, hi_max = -1;
-#pragma unroll
-    for (int s = 0; s < 4; ++s) {
-        const float c = start + (float)i * bin + ((float)s + 0.5f) * bin / 4.0f;
-        taps[s] = axis_tap(c, n);
-        if (taps[s].valid) {
-            lo_min = min(lo_min, taps[s].lo);
-            hi_max = max(hi_max, taps[s].hi);
-        }
-    }
+    if (t0.valid) { lo_min = min(lo_min, t0.lo); hi_max = max(hi_max, t0.hi); }
+    if (t1.valid) { lo_min = min(lo_min, t1.lo); hi_max = max(hi_max, t1.hi); }
+    if (t2.valid) { lo_min = min(lo_min, t2.lo); hi_max = max(hi_max, t2.hi); }
+    if (t3.valid) { lo_min = min(lo_min, t3.lo); hi_max = max(hi_max, t3.hi); }
+    float w0 = 0.0f, w1 = 0.0f, w2 = 0.0f, w3 = 0.0f;
+    wt[0] = wt[1] = wt[2] = wt[3] = 0.0f;
     if (hi_max < 0) {  // no valid sample: all-zero weights
         base = 0;
         return true;
     }
     if (hi_max - lo_min >= CROP_SPAN) return false;
     base = lo_min;
-#pragma unroll
-    for (int s = 0; s < 4; ++s) {
-        if (!taps[s].valid) continue;
-#pragma unroll
-        for (int k = 0; k < CROP_SPAN; ++k) {
-            if (taps[s].lo - lo_min == k) wt[k] += 0.25f * taps[s].wlo;
-            if (taps[s].hi - lo_min == k) wt[k] += 0.25f * taps[s].whi;
-        }
-    }
+    // scatter-add of the 8 (tap, weight) pairs written as selects on scalars: keeps everything in registers (an indexed
+    // wt[lo - base] += ... is turned into local-memory loads/stores by the compiler)
+    auto add = [&](int d, float v) {
+        w0 += d == 0 ? v : 0.0f;
+        w1 += d == 1 ? v : 0.0f;
+        w2 += d == 2 ? v : 0.0f;
+        w3 += d == 3 ? v : 0.0f;
+    };
+    if (t0.valid) { add(t0.lo - lo_min, 0.25f * t0.wlo); add(t0.hi - lo_min, 0.25f * t0.whi); }
+    if (t1.valid) { add(t1.lo - lo_min, 0.25f * t1.wlo); add(t1.hi - lo_min, 0.25f * t1.whi); }
+    if (t2.valid) { add(t2.lo - lo_min, 0.25f * t2.wlo); add(t2.hi - lo_min, 0.25f * t2.whi); }
+    if (t3.valid) { add(t3.lo - lo_min, 0.25f * t3.wlo); add(t3.hi - lo_min, 0.25f * t3.whi); }
+    wt[0] = w0; wt[1] = w1; wt[2] = w2; wt[3] = w3;
     return true;
 }
 
 // One thread per output COLUMN, marching down the band's rows.  roi_align's 4x4 samples per output pixel are separable:
-// the thread keeps its 4 column-tap weights in registers for the whole band, and a rolling window of 4 horizontally
-// filtered source rows (per channel); every output pixel is then a 4-tap vertical combination of the window.  Going
-// down one output row advances the window by floor/ceil(bin_h) source rows, so (when up-sampling, the usual case) a
-// pixel costs < 1 new filtered row = 4 loads per channel, instead of 64 taps per channel.
+// the thread keeps its 4 column-tap weights in registers for the whole band and a window of 4 horizontally filtered
+// source rows (per channel); every output pixel is then a 4-tap vertical combination of the window.  Going down one
+// output row advances the window by floor/ceil(bin_h) source rows, so (when up-sampling, the usual case) a pixel costs
+// < 1 new filtered row = 4 loads per channel, instead of 64 taps per channel.
+//
+// The window never moves in registers: source row s always lives in slot (s & 3), and the prologue stores every output
+// row's 4 vertical weights already permuted to slot order, so the vertical combination is the same straight-line code
+// for every row.  The raw taps of the NEXT source row are prefetched one step ahead.  ncu (profiles/): the kernel is
+// bound by L1 bandwidth (4 overlapping 16-byte taps per thread per source row), not by issue slots or DRAM.
 template <int C, bool PACKED>
 __global__ void __launch_bounds__(CROP_MAX_THREADS, 3) hpb_crop_pixels_kernel(const CropPixParams p) {
     constexpr int NCH = C == 4 ? 5 : C;  // RGB-D: the depth-validity map is resampled as a 5th channel
+    constexpr int NRAW = PACKED ? 4 : C;
     const int n = blockIdx.y;
     const int band = p.band;
     const int row0 = blockIdx.x * band;
     const int tid = threadIdx.x;
-    extern __shared__ float sm[];
-    float *sWY = sm;                                             // [band][CROP_SPAN]
-    int *sBY = reinterpret_cast<int *>(sWY + band * CROP_SPAN);  // [band]
+    extern __shared__ __align__(16) float sm[];
+    float *sWY = sm;                                             // [band][CROP_SPAN], in SLOT order
+    int *sBY = reinterpret_cast<int *>(sWY + band * CROP_SPAN);  // [band] first source row of the window, -1 = all-zero row
     __shared__ int sGeneric;
 
     const float *bx = p.boxes + (size_t)n * 4;
@@ -225,17 +231,24 @@ __global__ void __launch_bounds__(CROP_MAX_THREADS, 3) hpb_crop_pixels_kernel(co
         float wt[CROP_SPAN];
         int base = 0;
         if (!axis_weights(y1, bin_h, row0 + i, p.H, base, wt)) sGeneric = 1;
-        sBY[i] = base;
-        *reinterpret_cast<float4 *>(sWY + i * CROP_SPAN) = make_float4(wt[0], wt[1], wt[2], wt[3]);
+        const bool zero = wt[0] == 0.f && wt[1] == 0.f && wt[2] == 0.f && wt[3] == 0.f;
+        sBY[i] = zero ? -1 : base;
+        float ws[CROP_SPAN];
+#pragma unroll
+        for (int q = 0; q < CROP_SPAN; ++q) {  // slot q holds source row base + ((q - base) & 3)
+            const int r = (q - base) & 3;
+            ws[q] = r == 0 ? wt[0] : r == 1 ? wt[1] : r == 2 ? wt[2] : wt[3];
+        }
+        *reinterpret_cast<float4 *>(sWY + i * CROP_SPAN) = make_float4(ws[0], ws[1], ws[2], ws[3]);
     }
-    // column taps of this thread's columns (registers); a span over CROP_SPAN anywhere sends the CTA to the generic path
+    // column taps of this thread's column (registers); a span over CROP_SPAN anywhere sends the CTA to the generic path
     float wx[CROP_SPAN] = {0.f, 0.f, 0.f, 0.f};
     int bxx = 0;
-    const int j0 = tid;
+    const int j0 = blockIdx.z * blockDim.x + tid;
     if (j0 < p.w) {
         if (!axis_weights(x1, bin_w, j0, p.W, bxx, wx)) sGeneric = 1;
     }
-    if (tid + (int)blockDim.x < p.w || p.W < CROP_SPAN) sGeneric = 1;  // more columns than threads / tiny frames: generic path
+    if (p.W < CROP_SPAN) sGeneric = 1;  // tiny frames: generic path
     __syncthreads();
     const bool generic = sGeneric != 0;
     const int im = p.im_ids[n];
@@ -264,76 +277,92 @@ __global__ void __launch_bounds__(CROP_MAX_THREADS, 3) hpb_crop_pixels_kernel(co
                 bxx -= over;
             }
         }
-        const int xo0 = bxx, xo1 = bxx + 1, xo2 = bxx + 2, xo3 = bxx + 3;
-        const float4 *col4 = PACKED ? p.packed + (size_t)im * p.H * p.W + xo0 : nullptr;  // taps at col4[0..3]
-        float hwin[CROP_SPAN][NCH];  // horizontally filtered source rows win_base .. win_base+3
+        const float4 *base4 = PACKED ? p.packed + (size_t)im * p.H * p.W + bxx : nullptr;
+        const float *base1 = img + bxx;
+        const float4 *pp4 = base4;  // first tap of row min(prow, H-1)
+        const float *pp1 = base1;
+        const int Wst = p.W, Hm1 = p.H - 1;
+        float raw[CROP_SPAN][NRAW];  // raw taps of source row `prow` (prefetched)
+        float hw[CROP_SPAN][NCH];    // horizontally filtered source rows, slot = row & 3
 #pragma unroll
         for (int r = 0; r < CROP_SPAN; ++r)
 #pragma unroll
-            for (int c = 0; c < NCH; ++c) hwin[r][c] = 0.f;
-        int win_base = -0x40000000;
-        auto filter_row = [&](int yy, float (&dst)[NCH]) {
+            for (int c = 0; c < NCH; ++c) hw[r][c] = 0.f;
+        int prow = 0;                   // row held in `raw`
+        int loaded_hi = -0x40000000;    // last row filtered into the window
+        auto fetch = [&]() {
             if (PACKED) {
-                const float4 *src = col4 + (size_t)min(yy, p.H - 1) * p.W;
-                const float4 v0 = __ldg(src), v1 = __ldg(src + 1), v2 = __ldg(src + 2), v3 = __ldg(src + 3);
-                dst[0] = fmaf(wx[3], v3.x, fmaf(wx[2], v2.x, fmaf(wx[1], v1.x, wx[0] * v0.x)));
-                dst[1] = fmaf(wx[3], v3.y, fmaf(wx[2], v2.y, fmaf(wx[1], v1.y, wx[0] * v0.y)));
-                dst[2] = fmaf(wx[3], v3.z, fmaf(wx[2], v2.z, fmaf(wx[1], v1.z, wx[0] * v0.z)));
-                if (C == 4) {
-                    dst[3] = fmaf(wx[3], v3.w, fmaf(wx[2], v2.w, fmaf(wx[1], v1.w, wx[0] * v0.w)));
-                    dst[NCH - 1] = fmaf(wx[3], v3.w > 0.f ? 1.f : 0.f, fmaf(wx[2], v2.w > 0.f ? 1.f : 0.f,
-                                        fmaf(wx[1], v1.w > 0.f ? 1.f : 0.f, wx[0] * (v0.w > 0.f ? 1.f : 0.f))));
-                }
-                return;
-            }
-            const float *src = img + (size_t)min(yy, p.H - 1) * p.W;
 #pragma unroll
-            for (int c = 0; c < C; ++c) {
-                const float *pl = src + c * plane_in;
-                const float v0 = __ldg(pl + xo0), v1 = __ldg(pl + xo1), v2 = __ldg(pl + xo2), v3 = __ldg(pl + xo3);
-                dst[c] = fmaf(wx[3], v3, fmaf(wx[2], v2, fmaf(wx[1], v1, wx[0] * v0)));
-                if (C == 4 && c == 3)
-                    dst[NCH - 1] = fmaf(wx[3], v3 > 0.f ? 1.f : 0.f, fmaf(wx[2], v2 > 0.f ? 1.f : 0.f,
-                                        fmaf(wx[1], v1 > 0.f ? 1.f : 0.f, wx[0] * (v0 > 0.f ? 1.f : 0.f))));
+                for (int k = 0; k < CROP_SPAN; ++k) {
+                    const float4 v = __ldg(pp4 + k);
+                    raw[k][0] = v.x; raw[k][1] = v.y; raw[k][2] = v.z; raw[k][3] = v.w;
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < C; ++c)
+#pragma unroll
+                    for (int k = 0; k < CROP_SPAN; ++k) raw[k][c] = __ldg(pp1 + c * plane_in + k);
             }
         };
-        float *o = out + (size_t)row0 * p.w + j0;
-        for (int i = 0; i < rows; ++i, o += p.w) {
-            const float4 wy = *reinterpret_cast<const float4 *>(sWY + i * CROP_SPAN);
+        auto filter_into = [&](float (&dst)[NCH]) {
+#pragma unroll
+            for (int c = 0; c < C; ++c)
+                dst[c] = fmaf(wx[3], raw[3][c], fmaf(wx[2], raw[2][c], fmaf(wx[1], raw[1][c], wx[0] * raw[0][c])));
+            if (C == 4)
+                dst[NCH - 1] = fmaf(wx[3], raw[3][3] > 0.f ? 1.f : 0.f, fmaf(wx[2], raw[2][3] > 0.f ? 1.f : 0.f,
+                                    fmaf(wx[1], raw[1][3] > 0.f ? 1.f : 0.f, wx[0] * (raw[0][3] > 0.f ? 1.f : 0.f))));
+        };
+        float *optr[C];  // one output pointer per plane, bumped by one row per iteration
+#pragma unroll
+        for (int c = 0; c < C; ++c) optr[c] = out + c * plane_out + (size_t)row0 * p.w + j0;
+        const int wout = p.w;
+        for (int i = 0; i < rows; ++i) {
+            const int by = sBY[i];  // uniform over the CTA
             float acc[NCH];
 #pragma unroll
             for (int c = 0; c < NCH; ++c) acc[c] = 0.f;
-            if (wy.x != 0.f || wy.y != 0.f || wy.z != 0.f || wy.w != 0.f) {  // uniform over the CTA
-                const int by = sBY[i];
-                int shift = by - win_base;
-                if (shift < 0 || shift >= CROP_SPAN) {  // (re)fill the whole window
-#pragma unroll
-                    for (int r = 0; r < CROP_SPAN; ++r) filter_row(by + r, hwin[r]);
-                } else {
-                    for (; shift > 0; --shift) {
-#pragma unroll
-                        for (int r = 0; r + 1 < CROP_SPAN; ++r)
-#pragma unroll
-                            for (int c = 0; c < NCH; ++c) hwin[r][c] = hwin[r + 1][c];
-                        filter_row(by - shift + CROP_SPAN, hwin[CROP_SPAN - 1]);
-                    }
+            if (by >= 0) {
+                const float4 wq = *reinterpret_cast<const float4 *>(sWY + i * CROP_SPAN);
+                if (by > loaded_hi + 1 || by < loaded_hi - 3) {  // first row of the band / a jump: restart the window at `by`
+                    prow = by;
+                    pp4 = base4 + (size_t)min(by, Hm1) * Wst;
+                    pp1 = base1 + (size_t)min(by, Hm1) * Wst;
+                    fetch();
+                    loaded_hi = by - 1;
                 }
-                win_base = by;
+                while (loaded_hi < by + 3) {
+                    ++loaded_hi;  // == prow
+                    switch (loaded_hi & 3) {
+                        case 0: filter_into(hw[0]); break;
+                        case 1: filter_into(hw[1]); break;
+                        case 2: filter_into(hw[2]); break;
+                        default: filter_into(hw[3]); break;
+                    }
+                    const int step = prow < Hm1 ? Wst : 0;  // rows past the frame repeat the last row (their weights are zero)
+                    if (PACKED) pp4 += step;
+                    else pp1 += step;
+                    ++prow;
+                    fetch();
+                }
 #pragma unroll
                 for (int c = 0; c < NCH; ++c)
-                    acc[c] = fmaf(wy.w, hwin[3][c], fmaf(wy.z, hwin[2][c], fmaf(wy.y, hwin[1][c], wy.x * hwin[0][c])));
+                    acc[c] = fmaf(wq.w, hw[3][c], fmaf(wq.z, hw[2][c], fmaf(wq.y, hw[1][c], wq.x * hw[0][c])));
             }
             if (C == 4 && acc[NCH - 1] < 0.99f) acc[3] = 0.0f;  // cropping.py:191-195
 #pragma unroll
-            for (int c = 0; c < C; ++c) __stcs(o + c * plane_out, acc[c]);
+            for (int c = 0; c < C; ++c) {
+                __stcs(optr[c], acc[c]);
+                optr[c] += wout;
+            }
         }
         return;
     }
 
     // generic roi_align: 4x4 samples, 4 taps each (heavy down-sampling: crop box wider than ~1.7x the output)
-    const int npx = rows * p.w;
+    const int jlo = blockIdx.z * blockDim.x, ncol = min((int)blockDim.x, p.w - jlo);  // this CTA's column tile
+    const int npx = rows * ncol;
     for (int q = tid; q < npx; q += blockDim.x) {
-        const int i = q / p.w, j = q - i * p.w;
+        const int i = q / ncol, j = jlo + (q - i * ncol);
         const int oy = row0 + i;
         float acc[C];
 #pragma unroll
@@ -416,7 +445,7 @@ int hpb_launch_crop_pixels(hpb_ctx *ctx, const float *images, int n_im, int C, i
     p.band = band;
     const int threads = w >= CROP_MAX_THREADS ? CROP_MAX_THREADS : ((w + 31) / 32) * 32;  // one thread per output column
     const size_t smem = (size_t)band * CROP_SPAN * sizeof(float) + (size_t)band * sizeof(int);
-    dim3 grid((h + band - 1) / band, b);
+    dim3 grid((h + band - 1) / band, b, (w + threads - 1) / threads);
     if (C == 3) {
         if (p.packed) hpb_crop_pixels_kernel<3, true><<<grid, threads, smem, stream>>>(p);
         else hpb_crop_pixels_kernel<3, false><<<grid, threads, smem, stream>>>(p);

@@ -121,9 +121,17 @@ class FoldedResNet:
             for blk in layer:
                 assert type(blk).__name__ == "BasicBlock", "only BasicBlock ResNets (ResNet-18/34) are folded"
                 down = None
+                c2 = _Conv(blk.conv2, blk.bn2, dtype)
                 if blk.downsample is not None:
+                    # out = relu(conv2(.) + b2 + down(x) + b_down): the projection's (folded) bias is moved into conv2's
+                    # bias (summed in float32), so the 1x1 projection is a bias-free convolution -- no separate
+                    # elementwise bias-add pass over the projected feature map
                     down = _Conv(blk.downsample[0], blk.downsample[1], dtype)
-                self.blocks.append((_Conv(blk.conv1, blk.bn1, dtype), _Conv(blk.conv2, blk.bn2, dtype), down))
+                    _, b2 = fold_conv_bn(blk.conv2, blk.bn2)
+                    _, bd = fold_conv_bn(blk.downsample[0], blk.downsample[1])
+                    c2.bias = (b2 + bd).to(dtype).contiguous()
+                    down.bias = None
+                self.blocks.append((_Conv(blk.conv1, blk.bn1, dtype), c2, down))
         self.fc_w = net.fc.weight.detach().to(dtype)
         self.fc_b = net.fc.bias.detach().to(dtype)
 
