@@ -461,16 +461,28 @@ def run_ours(args):
                      "frac": rk["gbps"] / peak, "peak_source": peak_src, "traffic": None,
                      "launches_timed": rk["launches"], "avg_launch_ms": rk["ms_avg"], "algorithmic_bytes_per_launch": rk["bytes_avg"],
                      "share_of_step": rk["ms_total"] / ms_bracketed if ms_bracketed > 0 else None,
-                     "bracketed_ms_per_step": ms_bracketed / args.steps},
+                     "bracketed_ms_per_step": ms_bracketed / args.steps,
+                     # the same figure for the largest launch class alone (the 576-scene coarse launch; the average above
+                     # also contains the 4..16-scene refiner / scoring launches, which cannot fill 148 SMs)
+                     "largest_launch": ({"scenes_bytes": rk["largest"]["bytes"], "launches": rk["largest"]["launches"],
+                                         "avg_launch_ms": rk["largest"]["ms_avg"], "achieved": rk["largest"]["gbps"],
+                                         "frac": rk["largest"]["gbps"] / peak} if "largest" in rk else None)},
         "kernels": {k: {"gbps": v["gbps"], "frac": v["gbps"] / peak, "avg_launch_ms": v["ms_avg"], "launches": v["launches"],
-                        "share_of_step": v["ms_total"] / ms_bracketed} for k, v in ksum.items()},
+                        "share_of_step": v["ms_total"] / ms_bracketed,
+                        "largest_launch_gbps": v["largest"]["gbps"], "largest_launch_frac": v["largest"]["gbps"] / peak,
+                        "largest_launch_ms": v["largest"]["ms_avg"]} for k, v in ksum.items()},
         "hyps": {"metric": "rendered_hyps_per_sec", "value": hyps_per_s, "unit": "hyps/s", "b": b, "ms_per_launch_pair": ms_hyp / hyp_iters,
                  "gbps": b * 9 * H_R * W_R * 4 / 1e9 / (ms_hyp / hyp_iters / 1e3), "frac": b * 9 * H_R * W_R * 4 / 1e9 / (ms_hyp / hyp_iters / 1e3) / peak},
     }
     traffic_file = os.path.join(ROOT, "profiles", "raster_traffic.json")
     if os.path.exists(traffic_file):
         try:
-            line["roofline"]["traffic"] = json.load(open(traffic_file)).get("traffic_bytes_per_launch")
+            tr = json.load(open(traffic_file))
+            # dram bytes of ONE ncu --set full capture of the 576-scene launch, scaled to this run's average launch by
+            # the measured traffic / algorithmic ratio (1.07: mesh + texture reads on top of the image writes)
+            line["roofline"]["traffic"] = tr["traffic_over_algorithmic"] * rk["bytes_avg"]
+            line["roofline"]["traffic_capture"] = {"launch": "576 scenes", "dram_bytes": tr["traffic_bytes_per_launch"],
+                                                   "algorithmic_bytes": tr["algorithmic_bytes_of_that_launch"]}
         except Exception:
             pass
     if world == 1 and not args.no_cpu_baseline:

@@ -51,7 +51,6 @@ struct RasterParams {
     const float *K;
     const float *ambient;
     int b, h, w;
-    unsigned w_magic;  // floor(2^32 / w) + 1
     float z_near;
     float inv_near, cd, a_f, b_f, eps_hi;
     uint32_t flags;
@@ -63,10 +62,11 @@ struct RasterParams {
     int views;            // scene i writes at base + (i / views) * bstride + (i % views) * view_stride
     long long view_stride;
     unsigned long long *vis;      // [clusters][h*w]
-    unsigned char *vert_scratch;  // [CTAs][max_nv * 12] when vertices do not fit in shared memory
-    int max_nv;
-    int verts_in_smem;
+    unsigned char *vert_scratch;  // [CTAs][max_nv * 12]: screen-space vertices of the meshes that do not fit in shared memory
+    int max_nv;                   // largest (even-padded) vertex count of any uploaded mesh = scratch slice size / 12
+    int smem_verts;               // vertices the dynamic shared memory holds; bigger meshes use the CTA's scratch slice
     int G;  // CTAs per cluster
+    unsigned span_magic;  // floor(2^32 / ceil(w / 32)) + 1
 };
 
 __device__ __forceinline__ int snap_fixed(float u) {
@@ -166,8 +166,16 @@ __device__ __forceinline__ float3 sample_bilinear(const uchar4 *tex, int Wi, int
     if (!(yf > -1.0e9f)) yf = -1.0e9f;
     if (yf > 1.0e9f) yf = 1.0e9f;
     const int x0 = (int)xf, y0 = (int)yf;
-    const uchar4 c00 = fetch_texel<POW2>(tex, Wi, Hi, x0, y0), c01 = fetch_texel<POW2>(tex, Wi, Hi, x0 + 1, y0);
-    const uchar4 c10 = fetch_texel<POW2>(tex, Wi, Hi, x0, y0 + 1), c11 = fetch_texel<POW2>(tex, Wi, Hi, x0 + 1, y0 + 1);
+    uchar4 c00, c01, c10, c11;
+    if (POW2) {  // wrap = bit mask; the two row offsets and the two column indices are shared by the four texels
+        const unsigned xa = (unsigned)x0 & (unsigned)(Wi - 1), xb = (unsigned)(x0 + 1) & (unsigned)(Wi - 1);
+        const unsigned ra = ((unsigned)y0 & (unsigned)(Hi - 1)) * (unsigned)Wi, rb = ((unsigned)(y0 + 1) & (unsigned)(Hi - 1)) * (unsigned)Wi;
+        c00 = __ldg(tex + (ra + xa)); c01 = __ldg(tex + (ra + xb));
+        c10 = __ldg(tex + (rb + xa)); c11 = __ldg(tex + (rb + xb));
+    } else {
+        c00 = fetch_texel<POW2>(tex, Wi, Hi, x0, y0); c01 = fetch_texel<POW2>(tex, Wi, Hi, x0 + 1, y0);
+        c10 = fetch_texel<POW2>(tex, Wi, Hi, x0, y0 + 1); c11 = fetch_texel<POW2>(tex, Wi, Hi, x0 + 1, y0 + 1);
+    }
     return make_float3(bilerp(fx, fy, c00.x, c01.x, c10.x, c11.x), bilerp(fx, fy, c00.y, c01.y, c10.y, c11.y),
                        bilerp(fx, fy, c00.z, c01.z, c10.z, c11.z));
 }
@@ -281,6 +289,19 @@ __device__ __forceinline__ void raster_small_tris(const RasterParams &p, const i
     }
 }
 
+// Debug build only (-DHPB_PHASE_CLOCKS, scripts/raster_phases.py): SM clocks thread 0 of every CTA spends in each phase.
+#ifdef HPB_PHASE_CLOCKS
+__device__ unsigned long long g_phase_clk[8];
+#define HPB_PHASE_MARK(i)                                                             \
+    if (tid == 0) {                                                                   \
+        const long long t_now = clock64();                                            \
+        atomicAdd(&g_phase_clk[i], (unsigned long long)(t_now - t_prev));             \
+        t_prev = t_now;                                                               \
+    }
+#else
+#define HPB_PHASE_MARK(i)
+#endif
+
 __global__ void __launch_bounds__(RASTER_THREADS, 1) hpb_raster_kernel(const RasterParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ HpbMeshDev sM;
@@ -300,9 +321,6 @@ __global__ void __launch_bounds__(RASTER_THREADS, 1) hpb_raster_kernel(const Ras
     const int group = blockIdx.x / G, n_groups = gridDim.x / G;
     const int npix = p.h * p.w;
     unsigned long long *vis = p.vis + (size_t)group * npix;
-    unsigned char *vbase = p.verts_in_smem ? smem_raw : p.vert_scratch + (size_t)blockIdx.x * p.max_nv * 12;
-    int2 *sxy = reinterpret_cast<int2 *>(vbase);
-    float *siz = reinterpret_cast<float *>(vbase + (size_t)p.max_nv * 8);
     int *queue = sQueue[warp];
 
     if (tid < 256) sLut[tid] = (float)tid / 255.0f;
@@ -310,6 +328,9 @@ __global__ void __launch_bounds__(RASTER_THREADS, 1) hpb_raster_kernel(const Ras
         const int T0 = (tid * 255) >> 5, T1 = (((tid + 1) & 31) * 255) >> 5;
         sNrmTab[tid] = make_float2((float)T0, (float)T1 - (float)T0);
     }
+#ifdef HPB_PHASE_CLOCKS
+    long long t_prev = clock64();
+#endif
     for (int hyp = group; hyp < p.b; hyp += n_groups) {
         {
             const int *src = reinterpret_cast<const int *>(p.meshes + p.mesh_ids[hyp]);
@@ -340,9 +361,16 @@ __global__ void __launch_bounds__(RASTER_THREADS, 1) hpb_raster_kernel(const Ras
             sAmb[tid - 25] = a;
         }
         __syncthreads();
+        HPB_PHASE_MARK(0)  // scene set-up
         const bool finite = sFinite != 0;
         const HpbMeshDev &m = sM;
         const int nv = m.nv, nf = m.nf;
+        // screen-space vertex arrays of THIS scene's mesh: shared memory when it fits (decided per scene, so one huge
+        // mesh in the database does not push the small ones out of shared memory), else the CTA's global scratch slice
+        const int nvp = (nv + 1) & ~1;  // keeps the float array behind the int2 array 8-byte aligned
+        unsigned char *vbase = nvp <= p.smem_verts ? smem_raw : p.vert_scratch + (size_t)blockIdx.x * p.max_nv * 12;
+        int2 *sxy = reinterpret_cast<int2 *>(vbase);
+        float *siz = reinterpret_cast<float *>(vbase + (size_t)nvp * 8);
         int bx0 = 1, bx1 = 0, by0 = 1, by1 = 0;  // pixel bounding box of the scene (empty by default)
 
         if (finite) {
@@ -377,6 +405,7 @@ __global__ void __launch_bounds__(RASTER_THREADS, 1) hpb_raster_kernel(const Ras
             }
             if (__any_sync(0xffffffffu, clipped) && lane == 0) sClipped = 1;
             __syncthreads();
+            HPB_PHASE_MARK(1)  // phase A
             if (sBox[0] <= sBox[2]) {
                 bx0 = max(ceil_div_pix(sBox[0]), 0); bx1 = min(floor_div_pix(sBox[2]), p.w - 1);
                 by0 = max(ceil_div_pix(sBox[1]), 0); by1 = min(floor_div_pix(sBox[3]), p.h - 1);
@@ -465,8 +494,10 @@ __global__ void __launch_bounds__(RASTER_THREADS, 1) hpb_raster_kernel(const Ras
             }
             __threadfence();
         }
+        HPB_PHASE_MARK(2)  // phase B, thread 0's own share
         if (G > 1) cg::this_cluster().sync();
         else __syncthreads();
+        HPB_PHASE_MARK(3)  // wait for the slowest warp of phase B
 
         // ---------------- phase C: resolve ----------------
         const size_t oi = (size_t)(hyp / p.views), ov = (size_t)(hyp % p.views) * p.view_stride;
@@ -476,12 +507,40 @@ __global__ void __launch_bounds__(RASTER_THREADS, 1) hpb_raster_kernel(const Ras
         uint8_t *msk = (p.flags & HPB_RENDER_MASK) ? p.mask + (size_t)hyp * p.mask_bs : nullptr;  // never view-interleaved
         const bool textured = m.tex != nullptr && m.uv != nullptr;
         const bool want_z = dep != nullptr || msk != nullptr;
-        for (int pix = rank * RASTER_THREADS + tid; pix < npix; pix += G * RASTER_THREADS) {
-            int py = (int)__umulhi((unsigned)pix, p.w_magic);
-            if (py * p.w > pix) --py;
-            const int px = pix - py * p.w;
+        // Work unit = one 32-pixel span of one row, dealt to the warps of the cluster round-robin (fine-grained, so the
+        // shaded and the empty spans spread evenly).  The row / span arithmetic is per warp, not per pixel; spans that
+        // miss the scene's bounding box are zero-filled without touching the visibility buffer.
+        const int nspan = (p.w + 31) >> 5;
+        const int n_units = p.h * nspan;
+        const int sp0 = bx0 >> 5, sp1 = bx1 >> 5;
+        for (int u = rank * RASTER_WARPS + warp; u < n_units; u += G * RASTER_WARPS) {
+            int py = (int)__umulhi((unsigned)u, p.span_magic);
+            if (py * nspan > u) --py;
+            const int sp = u - py * nspan;
+            const int px = (sp << 5) + lane;
+            const int pix = py * p.w + px;
+            const bool in_row = px < p.w;
+            float *rgb_row = rgb ? rgb + pix : nullptr;  // this lane's pixel in plane 0
+            float *nrm_row = nrm ? nrm + pix : nullptr;
+            if (py < by0 || py > by1 || sp < sp0 || sp > sp1) {  // warp-uniform: background span
+                if (in_row) {
+                    if (rgb) {
+                        __stcs(rgb_row, 0.f);
+                        __stcs(rgb_row + (unsigned)npix, 0.f);
+                        __stcs(rgb_row + (unsigned)(2 * npix), 0.f);
+                    }
+                    if (nrm) {
+                        __stcs(nrm_row, 0.f);
+                        __stcs(nrm_row + (unsigned)npix, 0.f);
+                        __stcs(nrm_row + (unsigned)(2 * npix), 0.f);
+                    }
+                    if (dep) __stcs(dep + pix, 0.f);
+                    if (msk) msk[pix] = 0;
+                }
+                continue;
+            }
             unsigned long long key = HPB_VIS_EMPTY;
-            if (px >= bx0 && px <= bx1 && py >= by0 && py <= by1) {
+            if (in_row && px >= bx0 && px <= bx1) {
                 key = __ldcg(vis + pix);
                 if (key != HPB_VIS_EMPTY) __stcg(vis + pix, HPB_VIS_EMPTY);  // re-arm for the next scene
             }
@@ -566,23 +625,27 @@ __global__ void __launch_bounds__(RASTER_THREADS, 1) hpb_raster_kernel(const Ras
                     bl = quant8(col.z * sAmb[2], sLut);
                 }
             }
-            if (rgb) {
-                __stcs(rgb + pix, r);
-                __stcs(rgb + npix + pix, g);
-                __stcs(rgb + 2 * (size_t)npix + pix, bl);
+            if (in_row) {
+                if (rgb) {
+                    __stcs(rgb_row, r);
+                    __stcs(rgb_row + (unsigned)npix, g);
+                    __stcs(rgb_row + (unsigned)(2 * npix), bl);
+                }
+                if (nrm) {
+                    __stcs(nrm_row, n0);
+                    __stcs(nrm_row + (unsigned)npix, n1);
+                    __stcs(nrm_row + (unsigned)(2 * npix), n2);
+                }
+                if (dep) __stcs(dep + pix, z);
+                if (msk) msk[pix] = z > 0.0f ? 1 : 0;
             }
-            if (nrm) {
-                __stcs(nrm + pix, n0);
-                __stcs(nrm + npix + pix, n1);
-                __stcs(nrm + 2 * (size_t)npix + pix, n2);
-            }
-            if (dep) __stcs(dep + pix, z);
-            if (msk) msk[pix] = z > 0.0f ? 1 : 0;
         }
+        HPB_PHASE_MARK(4)  // phase C, thread 0's own share
         // the next scene's phase A overwrites the vertex stage, and its phase B (from any CTA of the cluster) writes
         // the visibility buffer this CTA has just re-armed
         if (G > 1) cg::this_cluster().sync();
         else __syncthreads();
+        HPB_PHASE_MARK(5)  // wait for the slowest warp of phase C
     }
 }
 
@@ -619,6 +682,15 @@ __global__ void hpb_fill_u64_kernel(unsigned long long *p, size_t n, unsigned lo
 
 }  // namespace
 
+#ifdef HPB_PHASE_CLOCKS
+extern "C" int hpb_debug_phase_clocks(unsigned long long *out) {
+    unsigned long long zero[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (cudaMemcpyFromSymbol(out, g_phase_clk, sizeof(zero)) != cudaSuccess) return -1;
+    if (cudaMemcpyToSymbol(g_phase_clk, zero, sizeof(zero)) != cudaSuccess) return -1;
+    return 0;
+}
+#endif
+
 int hpb_launch_mip(const uchar4 *src, int sw, int sh, uchar4 *dst, int dw, int dh, cudaStream_t stream) {
     dim3 blk(32, 8), grd((dw + 31) / 32, (dh + 7) / 8);
     hpb_mip_kernel<<<grd, blk, 0, stream>>>(src, sw, sh, dst, dw, dh);
@@ -640,9 +712,16 @@ int hpb_launch_raster(hpb_ctx *ctx, const int32_t *mesh_ids, const float *TCO, c
     const int npix = h * w;
     const int nv_pad = (ctx->max_nv + 1) & ~1;  // keeps the int2 array 8-byte aligned in every CTA's slice
     const size_t smem_need = (size_t)nv_pad * 12;
-    const size_t smem_cap = (size_t)ctx->max_smem_optin > 4096 ? (size_t)ctx->max_smem_optin - 2048 : 0;
+    static size_t static_smem = 0;  // the kernel's own __shared__ variables count against the per-block opt-in limit
+    if (static_smem == 0) {
+        cudaFuncAttributes fa;
+        HPB_CUDA_OK(cudaFuncGetAttributes(&fa, hpb_raster_kernel));
+        static_smem = fa.sharedSizeBytes + 256;
+    }
+    const size_t smem_cap = (size_t)ctx->max_smem_optin > static_smem ? (size_t)ctx->max_smem_optin - static_smem : 0;
     const int verts_in_smem = smem_need <= smem_cap;
-    const size_t smem = verts_in_smem ? smem_need : 0;
+    // when some mesh does not fit, the others still use as much shared memory as there is (per-scene choice in the kernel)
+    const size_t smem = verts_in_smem ? smem_need : (smem_cap / 24) * 24;
     HPB_CUDA_OK(cudaFuncSetAttribute(hpb_raster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 
     // how many clusters of 1/2/4/8 CTAs can be co-resident (one CTA per SM); queried once per shared-memory size
@@ -702,7 +781,6 @@ int hpb_launch_raster(hpb_ctx *ctx, const int32_t *mesh_ids, const float *TCO, c
     p.K = K;
     p.ambient = ambient;
     p.b = b; p.h = h; p.w = w;
-    p.w_magic = (unsigned)((1ull << 32) / (unsigned)w) + 1u;
     p.z_near = z_near;
     p.inv_near = 1.0f / z_near;
     const float inv_far = 1.0f / z_far;
@@ -718,8 +796,9 @@ int hpb_launch_raster(hpb_ctx *ctx, const int32_t *mesh_ids, const float *TCO, c
     p.vis = ctx->vis;
     p.vert_scratch = ctx->vert_scratch;
     p.max_nv = nv_pad;
-    p.verts_in_smem = verts_in_smem;
+    p.smem_verts = (int)(smem / 12);
     p.G = G;
+    p.span_magic = (unsigned)((1ull << 32) / (unsigned)((w + 31) / 32)) + 1u;
 
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(n_ctas, 1, 1);

@@ -37,6 +37,12 @@ class KernelTimer:
             tot = sum(ms)
             out[name] = {"launches": len(recs), "ms_total": tot, "ms_avg": tot / len(recs), "bytes_avg": sum(byts) / len(recs),
                          "gbps": (sum(byts) / 1e9) / (tot / 1e3) if tot > 0 else 0.0}
+            # the launches of the largest size on their own (the step mixes one big coarse launch with many tiny
+            # refiner launches that cannot fill the machine)
+            big = max(byts)
+            sel = [m for m, c in zip(ms, byts) if c == big]
+            out[name]["largest"] = {"launches": len(sel), "bytes": big, "ms_avg": sum(sel) / len(sel),
+                                    "gbps": big / 1e9 / (sum(sel) / len(sel) / 1e3) if sum(sel) > 0 else 0.0}
         return out
 
 

@@ -182,6 +182,36 @@ def test_render_big_triangles_int64_path(ctx):
     assert (nrm.cpu().numpy() == ref["normals"]).all() and (rgb.cpu().numpy() == ref["rgb"]).all()
 
 
+def test_render_gso_scale_mesh_uses_global_vertex_scratch(can_mesh_arrays):
+    """BASELINE config #5 class: a mesh whose 12 B / vertex screen-space arrays exceed shared memory (40 962 vertices,
+    81 920 triangles) is staged in the CTA's global scratch slice; a small mesh in the same launch keeps using shared
+    memory (the choice is per scene).  Own context: the scratch buffer is sized by the largest mesh of a context."""
+    from happypose_b200 import ops
+    from happypose_b200._capi import Context
+
+    ctx = Context(torch.device("cuda:0"))
+    v, f, n = icosphere(6, 0.06)
+    rs = np.random.RandomState(21)
+    bump = 1.0 + 0.04 * np.sin(9 * n[:, :1]) * np.cos(7 * n[:, 1:2]) + 0.01 * rs.randn(len(v), 1).astype(np.float32)
+    v = (v * bump).astype(np.float32)
+    colors = (rs.rand(len(v), 3) * 255).astype(np.uint8)
+    assert len(v) * 12 > 227 * 1024
+    big = oraster.OracleMesh(v, f, None, vcolor=colors)  # normals generated from the bumped surface
+    bid = ops.mesh_upload(ctx, big.pos, f, big.nrm, vcolor=colors)
+    d = can_mesh_arrays
+    om = oraster.OracleMesh(d["verts"], d["faces"], d["normals"], d["uv"], texture=d["texture"], scale=0.001)
+    mid = ops.mesh_upload(ctx, om.pos, d["faces"], d["normals"], d["uv"], texture=d["texture"])
+    T, K = random_crop_scene(rs, 5, res=(240, 320))
+    ids_o = [0, 1, 0, 0, 1]
+    ids_g = torch.tensor([bid, mid, bid, bid, mid])
+    ref = oraster.render([big, om], ids_o, T, K, (240, 320), render_normals=True, render_depth=True, render_binary_mask=True, n_threads=8)
+    rgb, nrm, dep, msk = ops.render(ctx, ids_g, torch.as_tensor(T), torch.as_tensor(K), (240, 320), render_normals=True, render_depth=True, render_binary_mask=True)
+    got = (rgb.cpu().numpy(), nrm.cpu().numpy(), dep.cpu().numpy(), msk.cpu().numpy())
+    assert (got[3] == ref["mask"]).all() and (got[2] == ref["depth"]).all()
+    assert got[3][0].mean() > 0.05
+    _check_render_parity(ref, got, "gso-scale mesh")
+
+
 def test_backface_skipping_matches_two_sided(ctx, can):
     """Closed-surface analysis agrees with the oracle's; skipping back faces of the (closed) can changes nothing."""
     from happypose_b200 import ops
@@ -294,6 +324,29 @@ def test_crop_vs_oracle_downsampling_and_out_of_frame(ctx, can_mesh_arrays):
     got = crops.cpu().numpy()
     np.testing.assert_allclose(got[:, :3], ref2[:, :3], atol=2e-5)
     assert (np.abs(got[:, 3] - ref2[:, 3]) > 1e-3).mean() < 2e-3
+
+
+def test_crop_wide_output_uses_column_tiles(ctx, can_mesh_arrays):
+    """Outputs wider than one CTA's 320 columns (e.g. the 480x640 crops of a depth refiner) are split into column tiles
+    (blockIdx.z); odd widths leave a ragged last tile.  Up-sampling and mild down-sampling, few rows and many rows, packed
+    (many rows per frame) and planar (few rows per frame) source layouts."""
+    from happypose_b200 import ops
+
+    rs = np.random.RandomState(12)
+    pts = _mesh_points(can_mesh_arrays)[O.sample_point_ids(9951, 2000)]
+    for b, size in ((2, (96, 648)), (9, (50, 333)), (3, (480, 640))):
+        images = rs.rand(1, 3, 240, 320).astype(np.float32)
+        K = np.tile(np.array([[300.0, 0, 160], [0, 300, 120], [0, 0, 1]], np.float32), (b, 1, 1))
+        TCO = np.tile(np.eye(4, dtype=np.float32), (b, 1, 1))
+        TCO[:, :3, :3] = random_rotations(rs, b)
+        TCO[:, :3, 3] = np.stack([rs.uniform(-0.05, 0.05, b), rs.uniform(-0.05, 0.05, b), rs.uniform(0.25, 0.9, b)], 1)
+        tCR = TCO[:, :3, 3].copy()
+        im_ids = np.zeros(b, np.int64)
+        crops, K_crop, boxes_rend, boxes_crop = ops.crop(ctx, torch.as_tensor(images), torch.as_tensor(im_ids), torch.as_tensor(pts[None]),
+                                                         torch.zeros(b, dtype=torch.int32), K, TCO, tCR, size)
+        rois = np.concatenate([im_ids[:, None].astype(np.float32), boxes_crop.cpu().numpy()], 1)
+        ref = O.crop_images(images, rois, size, 4)
+        np.testing.assert_allclose(crops.cpu().numpy(), ref, atol=2e-5)
 
 
 def test_crop_boxes_multiview_200_points(ctx, can_mesh_arrays):
