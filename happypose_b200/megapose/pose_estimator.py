@@ -266,10 +266,16 @@ class PoseEstimator(torch.nn.Module):
         detections: DetectionsType,
         cuda_timer: bool = False,
         return_debug_data: bool = False,
+        _instance_ids_after_enqueue: bool = False,
     ) -> Tuple[PoseEstimatesType, dict]:
-        """SO(3)-grid hypotheses for every detection, scored by the coarse model (pose_estimator.py:328-485)."""
+        """SO(3)-grid hypotheses for every detection, scored by the coarse model (pose_estimator.py:328-485).
+
+        `_instance_ids_after_enqueue` (run_inference_pipeline): `instance_id` is added to the detections AFTER the coarse
+        stage has been enqueued -- the kernels only need labels, frame ids and boxes, so the pandas bookkeeping (instance
+        ids, top-K group ids) runs while the GPU is already busy instead of in front of an idle GPU."""
         start_time = time.time()
-        assert_detections_valid(detections)
+        if not _instance_ids_after_enqueue:
+            assert_detections_valid(detections)
         coarse_model = self.coarse_model
         dev = observation.images.device
         SO3_grid = self._SO3_grid.to(dev)
@@ -285,11 +291,6 @@ class PoseEstimator(torch.nn.Module):
         obj_ids, mesh_ids, im_ids = obj_ids_d[rep].contiguous(), mesh_ids_d[rep].contiguous(), im_ids_d[rep].contiguous()
         bboxes = detections.bboxes.to(dev)[rep].float()
         K_rows = observation.K[im_ids.long()]
-        # groups of the later top-K = (batch_im_id, label, instance_id); computed on the B detection rows
-        det_groups_np = tc.group_ids_from_columns(df, ["batch_im_id", "label", "instance_id"])
-        n_groups = int(det_groups_np.max()) + 1
-        det_groups = torch.as_tensor(det_groups_np).to(dev)
-        row_tensors = {"obj_ids": obj_ids, "mesh_ids": mesh_ids, "im_ids": im_ids, "group_ids": det_groups[rep].contiguous()}
         # initial poses of ALL rows on every rank (cheap; lets the top-K be replicated without exchanging poses)
         TCO = ops.tco_init(
             coarse_model._ctx(), _capi.TCO_INIT_AUTODEPTH_WITH_R, bboxes, K_rows, coarse_model.mesh_db.points, obj_ids,
@@ -297,6 +298,18 @@ class PoseEstimator(torch.nn.Module):
 
         logits, scores, render_time, model_time, n_batches, dbg = self._score_rows(
             observation, (obj_ids, mesh_ids, im_ids), TCO, cuda_timer, return_debug_data)
+        # ---- host bookkeeping, behind the enqueued coarse stage ----
+        if _instance_ids_after_enqueue:
+            detections = add_instance_id(detections)
+            assert_detections_valid(detections)
+            df = detections.infos
+        # groups of the later top-K = (batch_im_id, label, instance_id); computed on the B detection rows
+        det_groups_np = tc.group_ids_from_columns(df, ["batch_im_id", "label", "instance_id"])
+        n_groups = int(det_groups_np.max()) + 1
+        # pinned + non_blocking: a pageable H2D copy would block the host until the coarse stage enqueued above has run
+        det_groups = torch.as_tensor(det_groups_np)
+        det_groups = (det_groups.pin_memory().to(dev, non_blocking=True) if dev.type == "cuda" else det_groups.to(dev))
+        row_tensors = {"obj_ids": obj_ids, "mesh_ids": mesh_ids, "im_ids": im_ids, "group_ids": det_groups[rep].contiguous()}
         logits = logits.reshape([B, M])
         scores = scores.reshape([B, M])
         debug_data = {}
@@ -371,9 +384,9 @@ class PoseEstimator(torch.nn.Module):
             if labels_to_keep is not None:
                 detections = filter_detections(detections, labels_to_keep)
             assert len(detections) > 0, "TOFIX: currently, dealing with absence of detections is not supported"
-            detections = add_instance_id(detections)
+            # detections = add_instance_id(detections) (pose_estimator.py:578) happens inside, behind the coarse enqueue
             data_TCO_coarse, coarse_extra_data = self.forward_coarse_model(
-                observation=observation, detections=detections, cuda_timer=cuda_timer)
+                observation=observation, detections=detections, cuda_timer=cuda_timer, _instance_ids_after_enqueue=True)
             timing_str += f"coarse={coarse_extra_data['time']:.2f}, "
             data_TCO_filtered = filter_top_pose_estimates(
                 data_TCO_coarse, top_K=n_pose_hypotheses, group_cols=group_cols, filter_field="coarse_logit",
