@@ -301,7 +301,7 @@ def run_reference(args):
         "note": "Panda3D/OpenGL cannot be installed offline, so the reference arm is the CPU oracle port of the same path "
                 "(it omits the reference's worker-process IPC and GL read-back, i.e. it is a faster baseline than the real one)",
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -490,11 +490,33 @@ def run_ours(args):
         pipe.sample()
         t_pose = min(pipe.sample() for _ in range(2))
         line["cpu_baseline"] = {"value": 1.0 / t_pose, "unit": UNIT, "cores": pipe.cores, "kind": "port", "sample": pipe.describe()}
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_JSON_FD = None
+
+
+def _reserve_stdout():
+    """stdout must carry exactly ONE JSON line: anything a library prints to fd 1 (NCCL's version banner, cuDNN notices)
+    is sent to stderr instead, and emit() writes the line to the original stdout."""
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
 
 
 def main():
     args = parse_args()
+    _reserve_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
