@@ -172,15 +172,16 @@ class PoseEstimator(torch.nn.Module):
         row_tensors = {"obj_ids": obj_ids, "mesh_ids": mesh_ids, "im_ids": im_ids}
         if "group_ids" in data_TCO_input.row_tensors:
             row_tensors["group_ids"] = data_TCO_input.row_tensors["group_ids"]
+        shape_tail = {"poses": (4, 4), "poses_input": (4, 4), "K_crop": (3, 3), "K": (3, 3), "boxes_rend": (4,), "boxes_crop": (4,)}
+        local = {(n, k): (torch.cat(chunks[n][k], dim=0) if chunks[n][k] else torch.zeros((0,) + shape_tail[k], device=dev))
+                 for n in range(1, n_iterations + 1) for k in keys}
+        if hdist.is_distributed() and self.shard_across_ranks:
+            # ONE all-gather for the whole stage: every (iteration, tensor) of this rank's rows packed side by side
+            # ([rows, n_iterations * 58] floats) instead of one collective per tensor per iteration
+            local = hdist.all_gather_rows_packed(local, B)
         preds = {}
         for n in range(1, n_iterations + 1):
-            tensors = {}
-            for k in keys:
-                parts = chunks[n][k]
-                shape_tail = {"poses": (4, 4), "poses_input": (4, 4), "K_crop": (3, 3), "K": (3, 3), "boxes_rend": (4,), "boxes_crop": (4,)}[k]
-                local = torch.cat(parts, dim=0) if parts else torch.zeros((0,) + shape_tail, device=dev)
-                sharded = hdist.is_distributed() and self.shard_across_ranks
-                tensors[k] = hdist.all_gather_rows(local.contiguous(), B) if sharded else local
+            tensors = {k: local[(n, k)] for k in keys}
             preds[f"iteration={n}"] = PandasTensorCollection(make_infos, n_rows=B, row_tensors=row_tensors, **tensors)
             preds[f"iteration={n}"].meta.update(data_TCO_input.meta)
 

@@ -43,6 +43,16 @@ def _worker(rank, world, port, out_dir):
     both = [torch.zeros_like(flag) for _ in range(world)]
     dist.all_gather(both, flag)
     assert torch.equal(both[0], both[1])
+    # the refiner-stage exchange: a dict of row-aligned tensors through ONE collective
+    nrows = 5
+    lo, hi = hdist.shard_range(nrows)
+    full = {("it", 1, "poses"): torch.arange(nrows * 16, dtype=torch.float32).reshape(nrows, 4, 4),
+            ("it", 1, "K_crop"): torch.arange(nrows * 9, dtype=torch.float32).reshape(nrows, 3, 3) + 0.5,
+            ("it", 2, "boxes"): -torch.arange(nrows * 4, dtype=torch.float32).reshape(nrows, 4)}
+    got = hdist.all_gather_rows_packed({k: v[lo:hi].contiguous() for k, v in full.items()}, nrows)
+    assert list(got.keys()) == list(full.keys())
+    for k in full:
+        assert got[k].shape == full[k].shape and torch.equal(got[k], full[k]), k
     # collections: file-free gather_distributed
     coll = PandasTensorCollection(pd.DataFrame({"rank": [rank] * (rank + 1)}), poses=torch.full((rank + 1, 4, 4), float(rank)))
     allc = coll.gather_distributed()
