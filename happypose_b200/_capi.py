@@ -50,6 +50,7 @@ SIGNATURES = {
     "hpb_normalize_depth": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "hpb_pack_input_bf16": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
     "hpb_pack_input_s2d_bf16": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
+    "hpb_render_s2d_bf16": (c_int, [c_void_p] * 5 + [c_int, c_int, c_int, c_float, c_float, c_void_p, c_int64, c_void_p, c_int, c_void_p]),
     "hpb_maxpool3x3s2_bf16_nhwc": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "hpb_topk_segmented": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
 }

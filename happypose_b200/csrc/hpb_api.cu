@@ -375,6 +375,25 @@ int hpb_render(hpb_ctx *ctx, const int32_t *mesh_ids_dev, const float *TCO_dev, 
                              mask_bstride, views, view_stride, (cudaStream_t)stream);
 }
 
+int hpb_render_s2d_bf16(hpb_ctx *ctx, const int32_t *mesh_ids_dev, const float *TCO_dev, const float *K_dev,
+                        const float *ambient_dev, int b, int h, int w, float z_near, float z_far, const float *crops_dev,
+                        int64_t crops_bstride, void *out_dev, int C_padded, void *stream) {
+    HPB_REQUIRE(ctx, "NULL ctx");
+    HPB_REQUIRE(b >= 0 && h > 0 && w > 0 && (long long)h * w < (1ll << 30), "bad batch / resolution");
+    HPB_REQUIRE(h % 2 == 0 && w % 2 == 0, "space-to-depth output needs even height and width");
+    HPB_REQUIRE(C_padded >= 40 && C_padded % 8 == 0, "C_padded must be a multiple of 8 and hold 4 * 9 channels");
+    if (b == 0) return HPB_OK;
+    HPB_REQUIRE(mesh_ids_dev && TCO_dev && K_dev && crops_dev && out_dev, "NULL input");
+    HPB_REQUIRE((reinterpret_cast<uintptr_t>(out_dev) & 15u) == 0, "out_dev must be 16-byte aligned");
+    HPB_REQUIRE(crops_bstride >= 3ll * h * w, "crops_bstride smaller than 3 planes");
+    HPB_REQUIRE(z_near > 0.f && z_far > z_near, "bad near/far");
+    HPB_REQUIRE(!ctx->meshes.empty(), "no mesh uploaded");
+    HpbDeviceGuard guard(ctx->device);
+    return hpb_launch_raster(ctx, mesh_ids_dev, TCO_dev, K_dev, ambient_dev, b, h, w, z_near, z_far,
+                             HPB_RENDER_RGB | HPB_RENDER_NORMALS, nullptr, 0, nullptr, 0, nullptr, 0, nullptr, 0, 1, 0,
+                             (cudaStream_t)stream, crops_dev, crops_bstride, out_dev, C_padded);
+}
+
 int hpb_crop_boxes(hpb_ctx *ctx, int H, int W, const float *points_dev, int n_obj, int n_pts,
                    const int32_t *obj_ids_dev, const float *K_dev, const float *TCO_dev, const float *tCR_dev, int b,
                    int h, int w, float lamb, float *K_crop_dev, float *boxes_rend_dev, float *boxes_crop_dev,

@@ -32,6 +32,7 @@
 //            filtered from an RGBA8 mip chain.  Background pixels are written as zeros here, so the outputs need no
 //            separate clear pass.
 #include <cooperative_groups.h>
+#include <cuda_bf16.h>
 
 #include "hpb_common.cuh"
 
@@ -67,6 +68,12 @@ struct RasterParams {
     int smem_verts;               // vertices the dynamic shared memory holds; bigger meshes use the CTA's scratch slice
     int G;  // CTAs per cluster
     unsigned span_magic;  // floor(2^32 / ceil(w / 32)) + 1
+    // space-to-depth output mode (hpb_render_s2d_bf16): the resolve writes the stem's bf16 NHWC input directly
+    uint4 *s2d;           // [b][Hz][Wz][Cz8] uint4 (8 bf16 channels each) or nullptr
+    const float *crops;   // [b][3][h][w] float32: the crop channels of the network input
+    long long crops_bs;
+    int Hz, Wz, Cz8;      // Hz = h/2 + 3, Wz = w/2 + 3
+    unsigned wz_magic;    // floor(2^32 / Wz) + 1
 };
 
 __device__ __forceinline__ int snap_fixed(float u) {
@@ -302,6 +309,9 @@ __device__ unsigned long long g_phase_clk[8];
 #define HPB_PHASE_MARK(i)
 #endif
 
+// S2D = false: planar float32 outputs (hpb_render); true: bf16 space-to-depth network input (hpb_render_s2d_bf16).  Two
+// instantiations so that the packed-output state of the second does not cost the first any registers.
+template <bool S2D>
 __global__ void __launch_bounds__(RASTER_THREADS, 1) hpb_raster_kernel(const RasterParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ HpbMeshDev sM;
@@ -507,6 +517,92 @@ __global__ void __launch_bounds__(RASTER_THREADS, 1) hpb_raster_kernel(const Ras
         uint8_t *msk = (p.flags & HPB_RENDER_MASK) ? p.mask + (size_t)hyp * p.mask_bs : nullptr;  // never view-interleaved
         const bool textured = m.tex != nullptr && m.uv != nullptr;
         const bool want_z = dep != nullptr || msk != nullptr;
+        const bool do_rgb = (p.flags & HPB_RENDER_RGB) != 0, do_nrm = (p.flags & HPB_RENDER_NORMALS) != 0;
+        // shading of ONE visible pixel (shared by the planar resolve and the space-to-depth resolve below)
+        auto shade = [&](const unsigned long long key, const int px, const int py, float &r, float &g, float &bl, float &n0,
+                         float &n1, float &n2, float &z) {
+            if (key != HPB_VIS_EMPTY) {
+                const unsigned klo = (unsigned)(key & 0xffffffffull);
+                const int4 f = __ldg(m.faces + (klo >> 1));
+                const int2 a = sxy[f.x], b = sxy[f.y], c = sxy[f.z];
+                const float iz0 = siz[f.x], iz1 = siz[f.y], iz2 = siz[f.z];
+                const int fxp = px * HPB_SUBPIX + 128, fyp = py * HPB_SUBPIX + 128;
+                // Edge values at the pixel centre in the triangle's own winding (no re-orientation: the weights below
+                // are ratios, so a common sign cancels).  For a covered pixel |e_i| <= |area2|, so 32-bit wrap-around
+                // arithmetic is exact unless the triangle is flagged wide.
+                const int dx0 = c.x - b.x, dy0 = c.y - b.y, dx1 = a.x - c.x, dy1 = a.y - c.y, dx2 = b.x - a.x, dy2 = b.y - a.y;
+                float fe0, fe1, fe2;
+                if (!(klo & 1u)) {
+                    fe0 = (float)(int)((unsigned)dx0 * (unsigned)(fyp - b.y) - (unsigned)dy0 * (unsigned)(fxp - b.x));
+                    fe1 = (float)(int)((unsigned)dx1 * (unsigned)(fyp - c.y) - (unsigned)dy1 * (unsigned)(fxp - c.x));
+                    fe2 = (float)(int)((unsigned)dx2 * (unsigned)(fyp - a.y) - (unsigned)dy2 * (unsigned)(fxp - a.x));
+                } else {
+                    fe0 = (float)((long long)dx0 * (fyp - b.y) - (long long)dy0 * (fxp - b.x));
+                    fe1 = (float)((long long)dx1 * (fyp - c.y) - (long long)dy1 * (fxp - c.x));
+                    fe2 = (float)((long long)dx2 * (fyp - a.y) - (long long)dy2 * (fxp - a.x));
+                }
+                const float w0 = fe0 * iz0, w1 = fe1 * iz1, w2 = fe2 * iz2;
+                const float s = __frcp_rn((w0 + w1) + w2);
+                const float p0 = w0 * s, p1 = w1 * s, p2 = w2 * s;
+                if (want_z) {
+                    const float d = __uint_as_float((unsigned)(key >> 32));
+                    z = p.a_f / (d - p.b_f);
+                    if (d > p.eps_hi) z = 0.0f;
+                }
+                const float4 A0 = __ldg(m.nu + f.x), A1 = __ldg(m.nu + f.y), A2 = __ldg(m.nu + f.z);
+                if (do_nrm) {
+                    // object-space normal interpolated over the triangle, rotated into the eye frame, normalised once
+                    const float ox = fmaf(p2, A2.x, fmaf(p1, A1.x, p0 * A0.x));
+                    const float oy = fmaf(p2, A2.y, fmaf(p1, A1.y, p0 * A0.y));
+                    const float oz = fmaf(p2, A2.z, fmaf(p1, A1.z, p0 * A0.z));
+                    float nx = fmaf(sT[2], oz, fmaf(sT[1], oy, sT[0] * ox));
+                    float ny = fmaf(sT[6], oz, fmaf(sT[5], oy, sT[4] * ox));
+                    float nz = fmaf(sT[10], oz, fmaf(sT[9], oy, sT[8] * ox));
+                    const float len2 = fmaf(nz, nz, fmaf(ny, ny, nx * nx));
+                    if (len2 > 0.0f) {
+                        const float rl = __frcp_rn(__fsqrt_rn(len2));
+                        nx *= rl; ny *= rl; nz *= rl;
+                    }
+                    n0 = encode_normal(nx, sNrmTab, sLut);
+                    n1 = encode_normal(nz, sNrmTab, sLut);
+                    n2 = encode_normal(-ny, sNrmTab, sLut);
+                }
+                if (do_rgb) {
+                    float3 col = make_float3(255.0f, 255.0f, 255.0f);
+                    if (textured) {
+                        const float v0 = __ldg(m.tv + f.x), v1 = __ldg(m.tv + f.y), v2 = __ldg(m.tv + f.z);
+                        const float u = fmaf(p2, A2.w, fmaf(p1, A1.w, p0 * A0.w));
+                        const float v = fmaf(p2, v2, fmaf(p1, v1, p0 * v0));
+                        // analytic screen-space derivatives of (u,v) for the mip level, from the per-pixel steps of the
+                        // un-normalised perspective weights e_i / z_i
+                        const float g0x = ((float)(-dy0) * 256.0f) * iz0, g1x = ((float)(-dy1) * 256.0f) * iz1, g2x = ((float)(-dy2) * 256.0f) * iz2;
+                        const float g0y = ((float)dx0 * 256.0f) * iz0, g1y = ((float)dx1 * 256.0f) * iz1, g2y = ((float)dx2 * 256.0f) * iz2;
+                        const float dDx = (g0x + g1x) + g2x, dDy = (g0y + g1y) + g2y;
+                        const float dNux = fmaf(g2x, A2.w, fmaf(g1x, A1.w, g0x * A0.w));
+                        const float dNuy = fmaf(g2y, A2.w, fmaf(g1y, A1.w, g0y * A0.w));
+                        const float dNvx = fmaf(g2x, v2, fmaf(g1x, v1, g0x * v0));
+                        const float dNvy = fmaf(g2y, v2, fmaf(g1y, v1, g0y * v0));
+                        const float W0 = (float)m.tex_w[0], H0 = (float)m.tex_h[0];
+                        const float ax = (dNux - u * dDx) * s * W0, bx = (dNvx - v * dDx) * s * H0;
+                        const float ay = (dNuy - u * dDy) * s * W0, by = (dNvy - v * dDy) * s * H0;
+                        const float r2x = fmaf(ax, ax, bx * bx), r2y = fmaf(ay, ay, by * by);
+                        const float rho2 = r2x > r2y ? r2x : r2y;
+                        float lod = 0.0f;
+                        if (rho2 > 1.0f && rho2 < 1.0e30f) lod = 0.5f * hp_log2(rho2);
+                        col = m.tex_pow2 ? sample_trilinear<true>(m, u, v, lod) : sample_trilinear<false>(m, u, v, lod);
+                    } else if (m.vcol) {
+                        const uchar4 c0 = __ldg(m.vcol + f.x), c1 = __ldg(m.vcol + f.y), c2 = __ldg(m.vcol + f.z);
+                        col.x = fmaf(p2, (float)c2.x, fmaf(p1, (float)c1.x, p0 * (float)c0.x));
+                        col.y = fmaf(p2, (float)c2.y, fmaf(p1, (float)c1.y, p0 * (float)c0.y));
+                        col.z = fmaf(p2, (float)c2.z, fmaf(p1, (float)c1.z, p0 * (float)c0.z));
+                    }
+                    r = quant8(col.x * sAmb[0], sLut);
+                    g = quant8(col.y * sAmb[1], sLut);
+                    bl = quant8(col.z * sAmb[2], sLut);
+                }
+            }
+        };
+        if constexpr (!S2D) {
         // Work unit = one 32-pixel span of one row, dealt to the warps of the cluster round-robin (fine-grained, so the
         // shaded and the empty spans spread evenly).  The row / span arithmetic is per warp, not per pixel; spans that
         // miss the scene's bounding box are zero-filled without touching the visibility buffer.
@@ -545,86 +641,7 @@ __global__ void __launch_bounds__(RASTER_THREADS, 1) hpb_raster_kernel(const Ras
                 if (key != HPB_VIS_EMPTY) __stcg(vis + pix, HPB_VIS_EMPTY);  // re-arm for the next scene
             }
             float r = 0.f, g = 0.f, bl = 0.f, n0 = 0.f, n1 = 0.f, n2 = 0.f, z = 0.f;
-            if (key != HPB_VIS_EMPTY) {
-                const unsigned klo = (unsigned)(key & 0xffffffffull);
-                const int4 f = __ldg(m.faces + (klo >> 1));
-                const int2 a = sxy[f.x], b = sxy[f.y], c = sxy[f.z];
-                const float iz0 = siz[f.x], iz1 = siz[f.y], iz2 = siz[f.z];
-                const int fxp = px * HPB_SUBPIX + 128, fyp = py * HPB_SUBPIX + 128;
-                // Edge values at the pixel centre in the triangle's own winding (no re-orientation: the weights below
-                // are ratios, so a common sign cancels).  For a covered pixel |e_i| <= |area2|, so 32-bit wrap-around
-                // arithmetic is exact unless the triangle is flagged wide.
-                const int dx0 = c.x - b.x, dy0 = c.y - b.y, dx1 = a.x - c.x, dy1 = a.y - c.y, dx2 = b.x - a.x, dy2 = b.y - a.y;
-                float fe0, fe1, fe2;
-                if (!(klo & 1u)) {
-                    fe0 = (float)(int)((unsigned)dx0 * (unsigned)(fyp - b.y) - (unsigned)dy0 * (unsigned)(fxp - b.x));
-                    fe1 = (float)(int)((unsigned)dx1 * (unsigned)(fyp - c.y) - (unsigned)dy1 * (unsigned)(fxp - c.x));
-                    fe2 = (float)(int)((unsigned)dx2 * (unsigned)(fyp - a.y) - (unsigned)dy2 * (unsigned)(fxp - a.x));
-                } else {
-                    fe0 = (float)((long long)dx0 * (fyp - b.y) - (long long)dy0 * (fxp - b.x));
-                    fe1 = (float)((long long)dx1 * (fyp - c.y) - (long long)dy1 * (fxp - c.x));
-                    fe2 = (float)((long long)dx2 * (fyp - a.y) - (long long)dy2 * (fxp - a.x));
-                }
-                const float w0 = fe0 * iz0, w1 = fe1 * iz1, w2 = fe2 * iz2;
-                const float s = __frcp_rn((w0 + w1) + w2);
-                const float p0 = w0 * s, p1 = w1 * s, p2 = w2 * s;
-                if (want_z) {
-                    const float d = __uint_as_float((unsigned)(key >> 32));
-                    z = p.a_f / (d - p.b_f);
-                    if (d > p.eps_hi) z = 0.0f;
-                }
-                const float4 A0 = __ldg(m.nu + f.x), A1 = __ldg(m.nu + f.y), A2 = __ldg(m.nu + f.z);
-                if (nrm) {
-                    // object-space normal interpolated over the triangle, rotated into the eye frame, normalised once
-                    const float ox = fmaf(p2, A2.x, fmaf(p1, A1.x, p0 * A0.x));
-                    const float oy = fmaf(p2, A2.y, fmaf(p1, A1.y, p0 * A0.y));
-                    const float oz = fmaf(p2, A2.z, fmaf(p1, A1.z, p0 * A0.z));
-                    float nx = fmaf(sT[2], oz, fmaf(sT[1], oy, sT[0] * ox));
-                    float ny = fmaf(sT[6], oz, fmaf(sT[5], oy, sT[4] * ox));
-                    float nz = fmaf(sT[10], oz, fmaf(sT[9], oy, sT[8] * ox));
-                    const float len2 = fmaf(nz, nz, fmaf(ny, ny, nx * nx));
-                    if (len2 > 0.0f) {
-                        const float rl = __frcp_rn(__fsqrt_rn(len2));
-                        nx *= rl; ny *= rl; nz *= rl;
-                    }
-                    n0 = encode_normal(nx, sNrmTab, sLut);
-                    n1 = encode_normal(nz, sNrmTab, sLut);
-                    n2 = encode_normal(-ny, sNrmTab, sLut);
-                }
-                if (rgb) {
-                    float3 col = make_float3(255.0f, 255.0f, 255.0f);
-                    if (textured) {
-                        const float v0 = __ldg(m.tv + f.x), v1 = __ldg(m.tv + f.y), v2 = __ldg(m.tv + f.z);
-                        const float u = fmaf(p2, A2.w, fmaf(p1, A1.w, p0 * A0.w));
-                        const float v = fmaf(p2, v2, fmaf(p1, v1, p0 * v0));
-                        // analytic screen-space derivatives of (u,v) for the mip level, from the per-pixel steps of the
-                        // un-normalised perspective weights e_i / z_i
-                        const float g0x = ((float)(-dy0) * 256.0f) * iz0, g1x = ((float)(-dy1) * 256.0f) * iz1, g2x = ((float)(-dy2) * 256.0f) * iz2;
-                        const float g0y = ((float)dx0 * 256.0f) * iz0, g1y = ((float)dx1 * 256.0f) * iz1, g2y = ((float)dx2 * 256.0f) * iz2;
-                        const float dDx = (g0x + g1x) + g2x, dDy = (g0y + g1y) + g2y;
-                        const float dNux = fmaf(g2x, A2.w, fmaf(g1x, A1.w, g0x * A0.w));
-                        const float dNuy = fmaf(g2y, A2.w, fmaf(g1y, A1.w, g0y * A0.w));
-                        const float dNvx = fmaf(g2x, v2, fmaf(g1x, v1, g0x * v0));
-                        const float dNvy = fmaf(g2y, v2, fmaf(g1y, v1, g0y * v0));
-                        const float W0 = (float)m.tex_w[0], H0 = (float)m.tex_h[0];
-                        const float ax = (dNux - u * dDx) * s * W0, bx = (dNvx - v * dDx) * s * H0;
-                        const float ay = (dNuy - u * dDy) * s * W0, by = (dNvy - v * dDy) * s * H0;
-                        const float r2x = fmaf(ax, ax, bx * bx), r2y = fmaf(ay, ay, by * by);
-                        const float rho2 = r2x > r2y ? r2x : r2y;
-                        float lod = 0.0f;
-                        if (rho2 > 1.0f && rho2 < 1.0e30f) lod = 0.5f * hp_log2(rho2);
-                        col = m.tex_pow2 ? sample_trilinear<true>(m, u, v, lod) : sample_trilinear<false>(m, u, v, lod);
-                    } else if (m.vcol) {
-                        const uchar4 c0 = __ldg(m.vcol + f.x), c1 = __ldg(m.vcol + f.y), c2 = __ldg(m.vcol + f.z);
-                        col.x = fmaf(p2, (float)c2.x, fmaf(p1, (float)c1.x, p0 * (float)c0.x));
-                        col.y = fmaf(p2, (float)c2.y, fmaf(p1, (float)c1.y, p0 * (float)c0.y));
-                        col.z = fmaf(p2, (float)c2.z, fmaf(p1, (float)c1.z, p0 * (float)c0.z));
-                    }
-                    r = quant8(col.x * sAmb[0], sLut);
-                    g = quant8(col.y * sAmb[1], sLut);
-                    bl = quant8(col.z * sAmb[2], sLut);
-                }
-            }
+            if (key != HPB_VIS_EMPTY) shade(key, px, py, r, g, bl, n0, n1, n2, z);
             if (in_row) {
                 if (rgb) {
                     __stcs(rgb_row, r);
@@ -638,6 +655,76 @@ __global__ void __launch_bounds__(RASTER_THREADS, 1) hpb_raster_kernel(const Ras
                 }
                 if (dep) __stcs(dep + pix, z);
                 if (msk) msk[pix] = z > 0.0f ? 1 : 0;
+            }
+        }
+        } else {
+            // ---- space-to-depth resolve: 4 lanes per CELL of the stem's input, one pixel per lane ----
+            // z[n][I][J][(r*2+s)*9 + c] = xpad[n][c][2I + r][2J + s], xpad = the 9-channel network input (3 crop channels
+            // read from `crops`, 6 rendered channels shaded here) zero-padded by 3 pixels; channels >= 36 are zero.
+            // Lane l of a warp shades sub-pixel (r,s) = l & 3 of cell l >> 2 of the warp's 8 consecutive cells, so the
+            // shading runs once per iteration exactly as in the planar resolve.  A cell's 36 bf16 values are 72 contiguous
+            // bytes whose 16-byte groups straddle the sub-pixels: lane `sub` assembles group `sub` from its own 9 values
+            // and the last `sub` values of its left neighbour (two shuffles), so a warp store writes 8 x 64 contiguous
+            // bytes -- whole sectors; a second store per lane covers bytes 64..127 of the cell (4 values + zeros).
+            const int n_cells = p.Hz * p.Wz;
+            uint4 *zbase = p.s2d + (size_t)hyp * n_cells * p.Cz8;
+            const float *crop = p.crops + (size_t)hyp * p.crops_bs;
+            const int sub = lane & 3;
+            for (int q0 = (rank * RASTER_WARPS + warp) * 8; q0 < n_cells; q0 += G * RASTER_WARPS * 8) {
+                const int q = q0 + (lane >> 2);
+                const bool cell_ok = q < n_cells;
+                int I = (int)__umulhi((unsigned)q, p.wz_magic);
+                if (I * p.Wz > q) --I;
+                const int J = q - I * p.Wz;
+                const int py = 2 * I + (sub >> 1) - 3, px = 2 * J + (sub & 1) - 3;
+                float v[9];
+#pragma unroll
+                for (int c = 0; c < 9; ++c) v[c] = 0.f;
+                if (cell_ok && py >= 0 && py < p.h && px >= 0 && px < p.w) {
+                    const int pix = py * p.w + px;
+                    v[0] = __ldcs(crop + pix);
+                    v[1] = __ldcs(crop + npix + pix);
+                    v[2] = __ldcs(crop + 2 * npix + pix);
+                    if (py >= by0 && py <= by1 && px >= bx0 && px <= bx1) {
+                        const unsigned long long key = __ldcg(vis + pix);
+                        if (key != HPB_VIS_EMPTY) {
+                            __stcg(vis + pix, HPB_VIS_EMPTY);  // re-arm for the next scene
+                            float zz = 0.f;
+                            shade(key, px, py, v[3], v[4], v[5], v[6], v[7], v[8], zz);
+                        }
+                    }
+                }
+                // own values o0..o8 as bf16 pairs, even alignment: e0 = (o0,o1) .. e3 = (o6,o7), e4 = (o8,0)
+                unsigned e[5];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * k], v[2 * k + 1]);
+                    e[k] = *reinterpret_cast<const unsigned *>(&h2);
+                }
+                e[4] = (unsigned)__bfloat16_as_ushort(__float2bfloat16_rn(v[8]));
+                // left neighbour's tail: t0 = (p6,p7), t1 = (p8,0)
+                const unsigned t0 = __shfl_up_sync(0xffffffffu, e[3], 1), t1 = __shfl_up_sync(0xffffffffu, e[4], 1);
+                // halfword string S = p6 p7 p8 o0 .. o8; group `sub` of the cell = S[3 - sub .. 10 - sub]
+                const unsigned A0 = t0;                                   // (p6,p7)
+                const unsigned A1 = (t1 & 0xffffu) | (e[0] << 16);        // (p8,o0)
+                const unsigned A2 = __funnelshift_r(e[0], e[1], 16);      // (o1,o2)
+                const unsigned A3 = __funnelshift_r(e[1], e[2], 16);      // (o3,o4)
+                const unsigned A4 = __funnelshift_r(e[2], e[3], 16);      // (o5,o6)
+                const unsigned A5 = __funnelshift_r(e[3], e[4], 16);      // (o7,o8)
+                const unsigned B0 = __funnelshift_r(t0, t1, 16);          // (p7,p8)
+                uint4 g0;
+                if (sub == 0) g0 = make_uint4(e[0], e[1], e[2], e[3]);
+                else if (sub == 1) g0 = make_uint4(A1, A2, A3, A4);
+                else if (sub == 2) g0 = make_uint4(B0, e[0], e[1], e[2]);
+                else g0 = make_uint4(A0, A1, A2, A3);
+                const uint4 g1 = sub == 3 ? make_uint4(A4, A5, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);  // values 32..35, then zeros
+                if (cell_ok) {
+                    uint4 *cell = zbase + (size_t)q * p.Cz8;
+                    __stcs(cell + sub, g0);
+                    const int e1i = 4 + ((sub + 1) & 3);  // lane 3 -> group 4, lanes 0..2 -> groups 5..7
+                    if (e1i < p.Cz8) __stcs(cell + e1i, g1);
+                    for (int x = 8 + sub; x < p.Cz8; x += 4) __stcs(cell + x, make_uint4(0u, 0u, 0u, 0u));
+                }
             }
         }
         HPB_PHASE_MARK(4)  // phase C, thread 0's own share
@@ -707,7 +794,8 @@ int hpb_launch_tex_expand(const uint8_t *src, int n, int c, uchar4 *dst, cudaStr
 int hpb_launch_raster(hpb_ctx *ctx, const int32_t *mesh_ids, const float *TCO, const float *K, const float *ambient,
                       int b, int h, int w, float z_near, float z_far, uint32_t flags, float *rgb, int64_t rgb_bs,
                       float *nrm, int64_t nrm_bs, float *depth, int64_t depth_bs, uint8_t *mask, int64_t mask_bs,
-                      int views, int64_t view_stride, cudaStream_t stream) {
+                      int views, int64_t view_stride, cudaStream_t stream, const float *crops, int64_t crops_bs,
+                      void *s2d_out, int Cz) {
     if (b == 0) return HPB_OK;
     const int npix = h * w;
     const int nv_pad = (ctx->max_nv + 1) & ~1;  // keeps the int2 array 8-byte aligned in every CTA's slice
@@ -715,14 +803,15 @@ int hpb_launch_raster(hpb_ctx *ctx, const int32_t *mesh_ids, const float *TCO, c
     static size_t static_smem = 0;  // the kernel's own __shared__ variables count against the per-block opt-in limit
     if (static_smem == 0) {
         cudaFuncAttributes fa;
-        HPB_CUDA_OK(cudaFuncGetAttributes(&fa, hpb_raster_kernel));
+        HPB_CUDA_OK(cudaFuncGetAttributes(&fa, hpb_raster_kernel<false>));
         static_smem = fa.sharedSizeBytes + 256;
     }
     const size_t smem_cap = (size_t)ctx->max_smem_optin > static_smem ? (size_t)ctx->max_smem_optin - static_smem : 0;
     const int verts_in_smem = smem_need <= smem_cap;
     // when some mesh does not fit, the others still use as much shared memory as there is (per-scene choice in the kernel)
     const size_t smem = verts_in_smem ? smem_need : (smem_cap / 24) * 24;
-    HPB_CUDA_OK(cudaFuncSetAttribute(hpb_raster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    void (*kern)(const RasterParams) = s2d_out ? hpb_raster_kernel<true> : hpb_raster_kernel<false>;
+    HPB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 
     // how many clusters of 1/2/4/8 CTAs can be co-resident (one CTA per SM); queried once per shared-memory size
     if (ctx->max_clusters_smem != smem) {
@@ -739,7 +828,7 @@ int hpb_launch_raster(hpb_ctx *ctx, const int32_t *mesh_ids, const float *TCO, c
             cfg.numAttrs = 1;
             int n = 0;
             if (G == 1) n = ctx->sm_count;
-            else if (cudaOccupancyMaxActiveClusters(&n, hpb_raster_kernel, &cfg) != cudaSuccess) { n = 0; cudaGetLastError(); }
+            else if (cudaOccupancyMaxActiveClusters(&n, hpb_raster_kernel<false>, &cfg) != cudaSuccess) { n = 0; cudaGetLastError(); }
             ctx->max_clusters[k] = n;
         }
         ctx->max_clusters_smem = smem;
@@ -799,6 +888,13 @@ int hpb_launch_raster(hpb_ctx *ctx, const int32_t *mesh_ids, const float *TCO, c
     p.smem_verts = (int)(smem / 12);
     p.G = G;
     p.span_magic = (unsigned)((1ull << 32) / (unsigned)((w + 31) / 32)) + 1u;
+    p.s2d = reinterpret_cast<uint4 *>(s2d_out);
+    p.crops = crops;
+    p.crops_bs = crops_bs;
+    p.Hz = h / 2 + 3;
+    p.Wz = w / 2 + 3;
+    p.Cz8 = Cz / 8;
+    p.wz_magic = (unsigned)((1ull << 32) / (unsigned)p.Wz) + 1u;
 
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(n_ctas, 1, 1);
@@ -810,7 +906,7 @@ int hpb_launch_raster(hpb_ctx *ctx, const int32_t *mesh_ids, const float *TCO, c
     at[0].val.clusterDim.x = G; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = G > 1 ? 1 : 0;
-    HPB_CUDA_OK(cudaLaunchKernelEx(&cfg, hpb_raster_kernel, p));
+    HPB_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, p));
     ctx->launches++;
     return HPB_OK;
 }

@@ -157,15 +157,23 @@ class FoldedResNet:
         x = x.to(dtype=self.dtype, memory_format=torch.channels_last)
         return self.stem.relu(x, fused)
 
-    def __call__(self, x: torch.Tensor) -> torch.Tensor:
+    @property
+    def accepts_s2d(self) -> bool:
+        """True when the stem runs as the 4x4 convolution over the space-to-depth input, i.e. when a caller may hand in
+        that tensor directly (ops.render_s2d_bf16) instead of the float32 planar network input."""
+        return self.stem_s2d is not None
+
+    def __call__(self, x: torch.Tensor, packed_s2d: bool = False) -> torch.Tensor:
+        """x: the float32 planar network input, or (packed_s2d=True) its bf16 space-to-depth form [b,s2d_channels,H/2+3,W/2+3]."""
         fused = self.fused
+        stem = (lambda t, f: self.stem_s2d.relu(t, f)) if packed_s2d else self._stem
         try:
-            y = self._stem(x, fused)
+            y = stem(x, fused)
         except RuntimeError:
             if not fused:
                 raise
             self.fused = fused = False  # this cuDNN build has no fused kernel for the dtype: plain conv + relu_
-            y = self._stem(x, fused)
+            y = stem(x, fused)
         x = y
         if self.fast_pool and x.is_contiguous(memory_format=torch.channels_last) and x.shape[1] % 8 == 0:
             from .. import ops

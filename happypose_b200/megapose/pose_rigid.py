@@ -145,6 +145,7 @@ class PosePredictor(nn.Module):
         self.debug_data = PosePredictorDebugData()
         self._net_ready = False
         self._folded = None
+        self.use_direct_s2d = True  # forward_coarse: rasteriser writes the stem's bf16 input directly (see _direct_s2d_ok)
         # replay launch-bound batches as CUDA graphs (utils/cuda_graphs.py); off by default, PoseEstimator turns it on
         self.use_cuda_graphs = False
         self.graph_max_batch = 64
@@ -187,6 +188,20 @@ class PosePredictor(nn.Module):
         if K.shape[0] == bsz and im_ids is None:
             return K
         return K[torch.as_tensor(im_ids).to(K.device).long()]
+
+    def _direct_s2d_ok(self, images: torch.Tensor, return_debug_data: bool, cuda_timer: bool) -> bool:
+        """The coarse / scoring forward may skip the float32 network input when nobody asks for it (debug data) and the
+        network is the folded bf16 ResNet with the space-to-depth stem: RGB frame, rgb + normals renders, one view."""
+        if return_debug_data or cuda_timer or self.debug or not images.is_cuda or not self.use_direct_s2d:
+            return False
+        if (self.input_depth or self.render_depth or not self.render_normals or self.n_rendered_views != 1
+                or images.shape[1] != 3 or self.n_input_channels != 3 or self._n_single_render_channels != 6):
+            return False
+        h, w = self.render_size
+        if h % 2 or w % 2:
+            return False
+        self._prepare_net(images)
+        return self._folded is not None and self._folded.accepts_s2d and self._folded.s2d_channels >= 40
 
     def _alloc_input(self, bsz: int, device) -> torch.Tensor:
         C = self.n_input_channels + self._n_single_render_channels * self.n_rendered_views
@@ -476,6 +491,21 @@ class PosePredictor(nn.Module):
 
         TCO_input = ops.normalize_T(ctx, TCO_input).detach()
         tCR = TCO_input[..., :3, 3].contiguous()
+        if self._direct_s2d_ok(images, return_debug_data, cuda_timer):
+            # fused hand-off: the rasteriser's resolve writes the stem's bf16 space-to-depth input itself (crop channels
+            # read from the crop kernel's planes): no float32 [b,9,h,w] network input, no packing pass
+            crops, K_crop, _, _ = ops.crop(
+                ctx, images, im_ids, self.mesh_db.points_subset(2000), obj_ids, K, TCO_input, tCR, self.render_size)
+            render_start = time.time()
+            z = ops.render_s2d_bf16(ctx, mesh_ids, TCO_input, K_crop, crops, self._folded.s2d_channels)
+            render_time = time.time() - render_start
+            start = time.time()
+            feat = self._folded(z, packed_s2d=True)
+            logits = self.heads["renderings_logits"](feat).float()
+            out = {"logits": logits, "scores": torch.sigmoid(logits), "time": time.time() - start}
+            out["render_time"] = render_time
+            out["model_time"] = out["time"]
+            return out
         x = self._alloc_input(bsz, device)
         images_crop, K_crop, boxes_rend, boxes_crop = ops.crop(
             ctx, images, im_ids, self.mesh_db.points_subset(2000), obj_ids, K, TCO_input, tCR, self.render_size, out=x)

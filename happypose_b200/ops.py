@@ -376,6 +376,37 @@ def pack_input_s2d_bf16(ctx: Context, x: torch.Tensor, c_padded: int) -> torch.T
     return out
 
 
+def render_s2d_bf16(ctx: Context, mesh_ids: torch.Tensor, TCO: torch.Tensor, K: torch.Tensor, crops: torch.Tensor, c_padded: int,
+                    ambient: Optional[torch.Tensor] = None, z_near: float = 0.1, z_far: float = 10.0) -> torch.Tensor:
+    """Renders rgb + normals of b scenes and writes the stem's input directly: z [b,c_padded,h/2+3,w/2+3] bfloat16
+    channels_last = pack_input_s2d_bf16(cat(crops, rgb, normals)) without the float32 network input or the packing pass
+    (hpb_render_s2d_bf16).  crops: [b,3,h,w] float32 (a contiguous tensor or the first 3 channels of a wider one)."""
+    dev = ctx.device
+    TCO = _f32(TCO, dev).reshape(-1, 16)
+    K = _f32(K, dev).reshape(-1, 9)
+    b = TCO.shape[0]
+    assert K.shape[0] == b, "K and TCO batch sizes differ"
+    mesh_ids = _i32(mesh_ids, dev)
+    assert mesh_ids.numel() == b
+    assert crops.dtype == torch.float32 and crops.dim() == 4 and crops.shape[0] == b and crops.shape[1] == 3
+    h, w = int(crops.shape[2]), int(crops.shape[3])
+    assert crops.stride(3) == 1 and crops.stride(2) == w and crops.stride(1) == h * w, "crop planes must be dense"
+    amb = None if ambient is None else _f32(ambient, dev).reshape(b, 3)
+    out = torch.empty((b, c_padded, h // 2 + 3, w // 2 + 3), dtype=torch.bfloat16, device=dev, memory_format=torch.channels_last)
+    ev = None
+    if _kernel_timer is not None:
+        # algorithmic bytes = the float32-equivalent render (6 planes per view, SURVEY 8d) so the figure stays comparable
+        # with hpb_render; the bytes actually written (bf16 cells incl. padding) are b * (h/2+3) * (w/2+3) * c_padded * 2
+        ev = _kernel_timer.bracket("hpb_raster_kernel", b * 6 * h * w * 4)
+        ev[0].record()
+    rc = ctx.lib.hpb_render_s2d_bf16(ctx.handle, ptr(mesh_ids), ptr(TCO), ptr(K), ptr(amb), b, h, w, z_near, z_far,
+                                     ptr(crops), crops.stride(0), ptr(out), c_padded, stream_ptr(dev))
+    if ev is not None:
+        ev[1].record()
+    ctx.check(rc, "hpb_render_s2d_bf16")
+    return out
+
+
 def maxpool3x3s2_bf16(ctx: Context, x: torch.Tensor) -> torch.Tensor:
     """F.max_pool2d(x, 3, 2, 1) for a bfloat16 channels_last [b,C,H,W] tensor (C % 8 == 0); returns channels_last."""
     assert x.dtype == torch.bfloat16 and x.dim() == 4 and x.is_contiguous(memory_format=torch.channels_last)

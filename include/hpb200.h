@@ -210,6 +210,19 @@ int hpb_pack_input_s2d_bf16(hpb_ctx *ctx, const float *x_dev, int64_t x_bstride,
                             int C_padded, void *stream);
 
 /*
+ * hpb_render (rgb + normals, one view per row) fused with hpb_pack_input_s2d_bf16 for the 9-channel coarse / scoring
+ * network input of PosePredictor.forward_coarse (pose_rigid.py:708-788: x = cat(images_crop, renders), then the stem
+ * of net_forward :352-374): renders the b scenes and writes out_dev [b, h/2+3, w/2+3, C_padded] bfloat16 with
+ *   out[n, I, J, (r*2+s)*9 + c] = xpad[n, c, 2I+r, 2J+s],   xpad = zero-padded-by-3 9-channel input whose channels 0..2
+ * are crops_dev [b, 3, h, w] float32 (row stride crops_bstride floats; the output of hpb_crop) and channels 3..8 the
+ * rendered rgb + normals; channels 36.. are zero.  Bit-identical to hpb_crop -> hpb_render into x -> hpb_pack_input_s2d_bf16,
+ * without ever materialising the float32 network input.  h and w even, C_padded >= 40 and a multiple of 8.
+ */
+int hpb_render_s2d_bf16(hpb_ctx *ctx, const int32_t *mesh_ids_dev, const float *TCO_dev, const float *K_dev,
+                        const float *ambient_dev, int b, int h, int w, float z_near, float z_far, const float *crops_dev,
+                        int64_t crops_bstride, void *out_dev, int C_padded, void *stream);
+
+/*
  * nn.MaxPool2d(kernel_size=3, stride=2, padding=1) of the ResNet stem (torchvision_resnet.py:215) on bfloat16
  * pixel-interleaved activations: in_dev [b,H,W,C] -> out_dev [b,(H-1)/2+1,(W-1)/2+1,C], C a multiple of 8.
  * Bit-identical to torch.nn.functional.max_pool2d (max is exact; NaN propagates).

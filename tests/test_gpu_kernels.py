@@ -501,6 +501,36 @@ def test_pack_input_s2d_matches_torch_statement(ctx):
         assert torch.equal(got, ref)
 
 
+def test_render_s2d_bf16_equals_render_then_pack(ctx, can):
+    """hpb_render_s2d_bf16 (the rasteriser writing the stem's bf16 space-to-depth input itself) is bit-identical to
+    hpb_crop -> hpb_render into the float32 network input -> hpb_pack_input_s2d_bf16, including the zero border, the
+    zero pad channels, a scene with a non-finite pose (zero render, crop still present) and > #SM scenes."""
+    from happypose_b200 import ops
+
+    om, mid = can
+    rs = np.random.RandomState(31)
+    for b, res in ((5, (240, 320)), (160, (60, 80)), (3, (118, 162))):
+        T, K = random_crop_scene(rs, b, res=res)
+        if b == 5:
+            T[3, 0, 3] = np.nan
+        crops = torch.as_tensor(rs.rand(b, 3, *res).astype(np.float32)).cuda()
+        ids = torch.full((b,), mid, dtype=torch.int32)
+        x = torch.empty((b, 9, *res), device="cuda")
+        x[:, :3] = crops
+        ops.render(ctx, ids, torch.as_tensor(T), torch.as_tensor(K), res, render_normals=True, out=x, out_channel_offset=3)
+        want = ops.pack_input_s2d_bf16(ctx, x, 64)
+        got = ops.render_s2d_bf16(ctx, ids, torch.as_tensor(T), torch.as_tensor(K), crops, 64)
+        assert got.shape == want.shape and got.is_contiguous(memory_format=torch.channels_last)
+        assert torch.equal(got.view(torch.int16), want.view(torch.int16)), f"b={b} res={res}"
+        # crops given as the first 3 channels of a wider tensor (row stride 9 planes), 40 padded channels
+        want40 = ops.pack_input_s2d_bf16(ctx, x, 40)
+        got40 = ops.render_s2d_bf16(ctx, ids, torch.as_tensor(T), torch.as_tensor(K), x[:, :3], 40)
+        assert torch.equal(got40.view(torch.int16), want40.view(torch.int16))
+        # a second call: the visibility buffer must have been re-armed by the first
+        again = ops.render_s2d_bf16(ctx, ids, torch.as_tensor(T), torch.as_tensor(K), crops, 64)
+        assert torch.equal(again.view(torch.int16), want.view(torch.int16))
+
+
 def test_maxpool_bf16_nhwc_is_bit_exact(ctx):
     from happypose_b200 import ops
 

@@ -260,6 +260,13 @@ def test_pipeline_bf16_runs_and_is_close_to_fp32(models):
     assert e16["logits"].dtype == torch.float32
     # bf16 carries 8 mantissa bits (1 ulp at |logit| ~ 13 is 0.0625): a few ulps through 34 layers
     np.testing.assert_allclose(e16["logits"].cpu().numpy(), e32["logits"].cpu().numpy(), rtol=2e-2, atol=0.1)
+    # the fused hand-off (rasteriser writes the stem's bf16 space-to-depth input) feeds the network the very same tensor
+    # as crop -> render -> pack: identical logits
+    assert coarse16.use_direct_s2d and coarse16._direct_s2d_ok(obs.images, False, False)
+    coarse16.use_direct_s2d = False
+    _, e16_packed = est16.forward_coarse_model(obs, _add_ids(det))
+    coarse16.use_direct_s2d = True
+    assert torch.equal(e16["logits"], e16_packed["logits"])
     final, extra = est16.run_inference_pipeline(obs, detections=det, n_refiner_iterations=5, n_pose_hypotheses=1)
     assert len(final) == 1 and torch.isfinite(final.poses).all()
 
