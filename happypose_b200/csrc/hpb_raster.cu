@@ -811,7 +811,9 @@ int hpb_launch_raster(hpb_ctx *ctx, const int32_t *mesh_ids, const float *TCO, c
     // when some mesh does not fit, the others still use as much shared memory as there is (per-scene choice in the kernel)
     const size_t smem = verts_in_smem ? smem_need : (smem_cap / 24) * 24;
     void (*kern)(const RasterParams) = s2d_out ? hpb_raster_kernel<true> : hpb_raster_kernel<false>;
-    HPB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // both instantiations get the attribute: the cluster-occupancy query below is made on <false> whichever runs first
+    HPB_CUDA_OK(cudaFuncSetAttribute(hpb_raster_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    HPB_CUDA_OK(cudaFuncSetAttribute(hpb_raster_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 
     // how many clusters of 1/2/4/8 CTAs can be co-resident (one CTA per SM); queried once per shared-memory size
     if (ctx->max_clusters_smem != smem) {

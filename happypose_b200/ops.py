@@ -23,26 +23,33 @@ class KernelTimer:
     def __init__(self):
         self.records = {}
 
-    def bracket(self, name: str, algorithmic_bytes: int):
+    def bracket(self, name: str, algorithmic_bytes: int, fp32_equivalent_bytes: Optional[int] = None):
+        """algorithmic_bytes: bytes the launch has to move; fp32_equivalent_bytes: what the reference's float32 layout of
+        the same result would be (differs only for the fused bf16 hand-off)."""
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        self.records.setdefault(name, []).append((e0, e1, int(algorithmic_bytes)))
+        eq = int(algorithmic_bytes if fp32_equivalent_bytes is None else fp32_equivalent_bytes)
+        self.records.setdefault(name, []).append((e0, e1, int(algorithmic_bytes), eq))
         return e0, e1
 
     def summary(self):
         """name -> dict(launches, ms_total, ms_avg, bytes_avg, gbps); call after torch.cuda.synchronize()."""
         out = {}
         for name, recs in self.records.items():
-            ms = [a.elapsed_time(b) for a, b, _ in recs]
-            byts = [c for _, _, c in recs]
+            ms = [r[0].elapsed_time(r[1]) for r in recs]
+            byts = [r[2] for r in recs]
+            eqs = [r[3] for r in recs]
             tot = sum(ms)
             out[name] = {"launches": len(recs), "ms_total": tot, "ms_avg": tot / len(recs), "bytes_avg": sum(byts) / len(recs),
-                         "gbps": (sum(byts) / 1e9) / (tot / 1e3) if tot > 0 else 0.0}
+                         "gbps": (sum(byts) / 1e9) / (tot / 1e3) if tot > 0 else 0.0,
+                         "fp32_equivalent_gbps": (sum(eqs) / 1e9) / (tot / 1e3) if tot > 0 else 0.0}
             # the launches of the largest size on their own (the step mixes one big coarse launch with many tiny
             # refiner launches that cannot fill the machine)
             big = max(byts)
             sel = [m for m, c in zip(ms, byts) if c == big]
+            big_eq = max(q for q, c in zip(eqs, byts) if c == big)
             out[name]["largest"] = {"launches": len(sel), "bytes": big, "ms_avg": sum(sel) / len(sel),
-                                    "gbps": big / 1e9 / (sum(sel) / len(sel) / 1e3) if sum(sel) > 0 else 0.0}
+                                    "gbps": big / 1e9 / (sum(sel) / len(sel) / 1e3) if sum(sel) > 0 else 0.0,
+                                    "fp32_equivalent_gbps": big_eq / 1e9 / (sum(sel) / len(sel) / 1e3) if sum(sel) > 0 else 0.0}
         return out
 
 
@@ -395,9 +402,10 @@ def render_s2d_bf16(ctx: Context, mesh_ids: torch.Tensor, TCO: torch.Tensor, K: 
     out = torch.empty((b, c_padded, h // 2 + 3, w // 2 + 3), dtype=torch.bfloat16, device=dev, memory_format=torch.channels_last)
     ev = None
     if _kernel_timer is not None:
-        # algorithmic bytes = the float32-equivalent render (6 planes per view) so the figure stays comparable
-        # with hpb_render; the bytes actually written (bf16 cells incl. padding) are b * (h/2+3) * (w/2+3) * c_padded * 2
-        ev = _kernel_timer.bracket("hpb_raster_kernel", b * 6 * h * w * 4)
+        # bytes this launch has to move: the bf16 cells of the stem input it writes (the layout the consumer needs, zero
+        # padding included) + the crop planes it reads; fp32-equivalent = the 6 float32 planes per view of hpb_render
+        ev = _kernel_timer.bracket("hpb_raster_kernel", b * ((h // 2 + 3) * (w // 2 + 3) * c_padded * 2 + 3 * h * w * 4),
+                                   fp32_equivalent_bytes=b * 6 * h * w * 4)
         ev[0].record()
     rc = ctx.lib.hpb_render_s2d_bf16(ctx.handle, ptr(mesh_ids), ptr(TCO), ptr(K), ptr(amb), b, h, w, z_near, z_far,
                                      ptr(crops), crops.stride(0), ptr(out), c_padded, stream_ptr(dev))

@@ -46,6 +46,11 @@ def main():
         gb = b * 6 * 240 * 320 * 4 / 1e9
         cov = float((x[:, 3:6].sum(1) > 0).float().mean())
         print(json.dumps({"kernel": "raster rgb+normals", "b": b, "ms": round(ms, 4), "hyps_per_s": round(b / ms * 1e3), "GBps": round(gb / ms * 1e3, 1), "frac": round(gb / ms * 1e3 / peak, 4), "coverage": round(cov, 3)}))
+        crops = x[:, :3]
+        ms = timeit(lambda: ops.render_s2d_bf16(ctx, ids, TCO, K_crop, crops, 64))
+        gb_moved = b * (123 * 163 * 64 * 2 + 3 * 240 * 320 * 4) / 1e9
+        print(json.dumps({"kernel": "raster rgb+normals -> bf16 s2d stem input (fused hand-off)", "b": b, "ms": round(ms, 4), "hyps_per_s": round(b / ms * 1e3),
+                          "GBps": round(gb_moved / ms * 1e3, 1), "frac": round(gb_moved / ms * 1e3 / peak, 4), "fp32_equivalent_GBps": round(gb / ms * 1e3, 1)}))
         ms = timeit(lambda: ops.crop(ctx, img, zero, pts, zero, K, TCO, tCR, (240, 320), out=x))
         gb = b * 3 * 240 * 320 * 4 / 1e9
         print(json.dumps({"kernel": "crop (boxes+pixels)", "b": b, "ms": round(ms, 4), "hyps_per_s": round(b / ms * 1e3), "GBps": round(gb / ms * 1e3, 1), "frac": round(gb / ms * 1e3 / peak, 4)}))
