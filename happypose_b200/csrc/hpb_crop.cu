@@ -9,14 +9,15 @@
 // Two kernels:
 //   hpb_crop_boxes_kernel   one CTA per hypothesis: projects the object's point set, reduces min/max, builds
 //                           boxes_rend, boxes_crop and K_crop on the device.
-//   hpb_crop_pixels_kernel  one CTA per (hypothesis, band of output rows), one THREAD per output column.  roi_align's
-//                           4x4 bilinear samples per output pixel are separable: the 4 row samples and the 4 column
-//                           samples of a bin fold into dense 4-tap row / column weights; a thread keeps a rolling
-//                           window of horizontally filtered source rows in registers while it marches down its
-//                           column, so a pixel costs ~bin_h * 4 loads per channel instead of 64.  The frame is
-//                           indexed by im_id: no per-hypothesis copy of the frame (the reference materialises
-//                           images[batch_im_ids], pose_estimator.py:390).  Stores are coalesced along x.  RGB-D frames also resample the depth-validity map and
-//                           zero depth where validity < 0.99 (cropping.py:181-195).
+//   hpb_crop_pixels_kernel  one CTA per (hypothesis, band of output rows[, column tile]), one THREAD per output column.
+//                           roi_align's 4x4 bilinear samples per output pixel are separable: the 4 row samples and the 4
+//                           column samples of a bin fold into dense 4-tap row / column weights; a thread keeps a window of
+//                           4 horizontally filtered source rows in registers (source row s in slot s & 3, the per-row
+//                           vertical weights stored pre-permuted, next row's taps prefetched) while it marches down its
+//                           column, so a pixel costs ~bin_h * 4 loads per channel instead of 64.  The frame is indexed by
+//                           im_id: no per-hypothesis copy of the frame (the reference materialises images[batch_im_ids],
+//                           pose_estimator.py:390).  Stores are coalesced along x.  RGB-D frames also resample the
+//                           depth-validity map and zero depth where validity < 0.99 (cropping.py:181-195).
 #include "hpb_common.cuh"
 
 namespace {

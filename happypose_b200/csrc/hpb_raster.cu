@@ -26,11 +26,14 @@
 //            (coverage mask, then one covered pixel per iteration).  Depth test = 64-bit atomicMin of
 //            (depth bits << 32 | triangle id << 1 | wide) on a per-cluster visibility buffer that stays resident in L2
 //            (re-armed in phase C, never re-cleared).  Big triangles are walked by the whole warp.
-//   phase C  resolve: the cluster's CTAs split the pixels; one thread per pixel, coalesced planar stores.  Only pixels
-//            inside the scene's bounding box read the visibility buffer; attributes are interpolated
-//            perspective-correctly from the un-normalised edge values (no area division), texture is trilinearly
-//            filtered from an RGBA8 mip chain.  Background pixels are written as zeros here, so the outputs need no
-//            separate clear pass.
+//   phase C  resolve: the cluster's warps split the image into 32-pixel span units; one lane per pixel, coalesced
+//            planar stores.  Spans that miss the scene's bounding box are zero-filled without reading the visibility
+//            buffer; attributes are interpolated perspective-correctly from the un-normalised edge values (no area
+//            division), texture is trilinearly filtered from an RGBA8 mip chain.  Background pixels are written as zeros
+//            here, so the outputs need no separate clear pass.
+//            Fused hand-off (hpb_render_s2d_bf16, template S2D = true): the same shading, but 4 lanes own one 2x2-pixel
+//            cell of the ResNet stem's space-to-depth input and the warp writes that bf16 NHWC tensor directly (crop
+//            channels read from the crop kernel's planes) -- the float32 network input and the packing pass disappear.
 #include <cooperative_groups.h>
 #include <cuda_bf16.h>
 
