@@ -269,6 +269,15 @@ def test_pipeline_bf16_runs_and_is_close_to_fp32(models):
     assert torch.equal(e16["logits"], e16_packed["logits"])
     final, extra = est16.run_inference_pipeline(obs, detections=det, n_refiner_iterations=5, n_pose_hypotheses=1)
     assert len(final) == 1 and torch.isfinite(final.poses).all()
+    # the same pipeline with the launch-bound stages captured / replayed as CUDA graphs (the fused hand-off of the scoring
+    # pass is then inside a graph): capture run, then a replay, both equal to the eager result
+    est16.use_cuda_graphs = True
+    for _ in range(2):
+        det_g, _, _ = _detections(1)
+        final_g, _ = est16.run_inference_pipeline(obs, detections=det_g, n_refiner_iterations=5, n_pose_hypotheses=1)
+        np.testing.assert_allclose(final_g.poses.cpu().numpy(), final.poses.cpu().numpy(), atol=1e-5)
+        np.testing.assert_allclose(final_g.infos["pose_logit"].to_numpy(), final.infos["pose_logit"].to_numpy(), atol=1e-4)
+    est16.use_cuda_graphs = False
 
 
 def _add_ids(det):
