@@ -40,6 +40,7 @@ SIGNATURES = {
     "hpb_crop": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p,
                          c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_int64, c_void_p,
                          c_void_p, c_void_p, c_void_p]),
+    "hpb_set_crop_tap_precision": (c_int, [c_void_p, c_int]),
     "hpb_crop_boxes": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
     "hpb_normalize_T": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p]),

@@ -428,6 +428,13 @@ int hpb_crop(hpb_ctx *ctx, const float *images_dev, int n_im, int C, int H, int 
     return HPB_OK;
 }
 
+int hpb_set_crop_tap_precision(hpb_ctx *ctx, int bits) {
+    HPB_REQUIRE(ctx, "NULL ctx");
+    HPB_REQUIRE(bits == 32 || bits == 16, "bits must be 32 or 16");
+    ctx->crop_tap_bits = bits;
+    return HPB_OK;
+}
+
 int hpb_normalize_T(hpb_ctx *ctx, const float *T_dev, int b, float *T_out_dev, void *stream) {
     HPB_REQUIRE(ctx && b >= 0, "bad argument");
     if (b == 0) return HPB_OK;

@@ -63,6 +63,7 @@ struct hpb_ctx {
     // crop workspace: pixel-interleaved copy of the observed frames
     void *frame_pack = nullptr;
     size_t frame_pack_bytes = 0;
+    int crop_tap_bits = 32;  // 16: the interleaved frame copy sampled by the crop kernel holds fp16 (hpb_set_crop_tap_precision)
     // top-k workspace
     void *topk_ws = nullptr;
     size_t topk_ws_bytes = 0;

@@ -18,6 +18,8 @@
 //                           im_id: no per-hypothesis copy of the frame (the reference materialises images[batch_im_ids],
 //                           pose_estimator.py:390).  Stores are coalesced along x.  RGB-D frames also resample the
 //                           depth-validity map and zero depth where validity < 0.99 (cropping.py:181-195).
+#include <cuda_fp16.h>
+
 #include "hpb_common.cuh"
 
 namespace {
@@ -120,6 +122,7 @@ struct CropPixParams {
     long long crops_bs;
     int band;  // output rows per CTA
     const float4 *packed;  // [n_im,H,W] pixel-interleaved copy of `images` (r,g,b,depth|0) or nullptr
+    const uint2 *packed_h;  // same in fp16 (r,g,b,0): 8-byte taps (hpb_set_crop_tap_precision(ctx, 16), RGB frames)
 };
 
 // Planar [n_im,C,H,W] -> pixel-interleaved float4 [n_im,H,W]: the crop then fetches all channels of a tap with ONE
@@ -134,6 +137,24 @@ __global__ void hpb_pack_frames_kernel(const float *images, long long n_px_per_i
         float4 v;
         v.x = __ldg(src); v.y = __ldg(src + n_px_per_im); v.z = __ldg(src + 2 * n_px_per_im);
         v.w = C == 4 ? __ldg(src + 3 * n_px_per_im) : 0.0f;
+        out[i] = v;
+    }
+}
+
+// fp16 variant (RGB frames): a tap is one 8-byte load, i.e. half the L1 sectors per tap request -- the crop kernel is
+// bound by L1 sector look-ups.  Values in [0,1] keep an absolute error <= 2.5e-4 (BASELINE bar for
+// crops: 1e-3); opt-in, used by the bf16 network path only.
+__global__ void hpb_pack_frames_half_kernel(const float *images, long long n_px_per_im, long long total, uint2 *out) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < total; i += stride) {
+        const long long im = i / n_px_per_im, px = i - im * n_px_per_im;
+        const float *src = images + im * 3 * n_px_per_im + px;
+        const __half2 rg = __floats2half2_rn(__ldg(src), __ldg(src + n_px_per_im));
+        const __half2 b0 = __floats2half2_rn(__ldg(src + 2 * n_px_per_im), 0.0f);
+        uint2 v;
+        v.x = *reinterpret_cast<const unsigned *>(&rg);
+        v.y = *reinterpret_cast<const unsigned *>(&b0);
         out[i] = v;
     }
 }
@@ -208,8 +229,10 @@ __device__ __forceinline__ bool axis_weights(float start, float bin, int i, int 
 // row's 4 vertical weights already permuted to slot order, so the vertical combination is the same straight-line code
 // for every row.  The raw taps of the NEXT source row are prefetched one step ahead.  ncu (profiles/): the kernel is
 // bound by L1 bandwidth (4 overlapping 16-byte taps per thread per source row), not by issue slots or DRAM.
-template <int C, bool PACKED>
+// MODE 0: taps from the planar float32 frame; 1: from the pixel-interleaved float4 copy; 2: from the fp16 copy (C == 3)
+template <int C, int MODE>
 __global__ void __launch_bounds__(CROP_MAX_THREADS, 3) hpb_crop_pixels_kernel(const CropPixParams p) {
+    constexpr bool PACKED = MODE != 0;
     constexpr int NCH = C == 4 ? 5 : C;  // RGB-D: the depth-validity map is resampled as a 5th channel
     constexpr int NRAW = PACKED ? 4 : C;
     const int n = blockIdx.y;
@@ -278,7 +301,9 @@ __global__ void __launch_bounds__(CROP_MAX_THREADS, 3) hpb_crop_pixels_kernel(co
                 bxx -= over;
             }
         }
-        const float4 *base4 = PACKED ? p.packed + (size_t)im * p.H * p.W + bxx : nullptr;
+        const float4 *base4 = MODE == 1 ? p.packed + (size_t)im * p.H * p.W + bxx : nullptr;
+        const uint2 *base8 = MODE == 2 ? p.packed_h + (size_t)im * p.H * p.W + bxx : nullptr;
+        const uint2 *pp8 = base8;
         const float *base1 = img + bxx;
         const float4 *pp4 = base4;  // first tap of row min(prow, H-1)
         const float *pp1 = base1;
@@ -292,7 +317,15 @@ __global__ void __launch_bounds__(CROP_MAX_THREADS, 3) hpb_crop_pixels_kernel(co
         int prow = 0;                   // row held in `raw`
         int loaded_hi = -0x40000000;    // last row filtered into the window
         auto fetch = [&]() {
-            if (PACKED) {
+            if (MODE == 2) {
+#pragma unroll
+                for (int k = 0; k < CROP_SPAN; ++k) {
+                    const uint2 v = __ldg(pp8 + k);
+                    const float2 rg = __half22float2(*reinterpret_cast<const __half2 *>(&v.x));
+                    const float2 b0 = __half22float2(*reinterpret_cast<const __half2 *>(&v.y));
+                    raw[k][0] = rg.x; raw[k][1] = rg.y; raw[k][2] = b0.x; raw[k][3] = 0.f;
+                }
+            } else if (MODE == 1) {
 #pragma unroll
                 for (int k = 0; k < CROP_SPAN; ++k) {
                     const float4 v = __ldg(pp4 + k);
@@ -327,6 +360,7 @@ __global__ void __launch_bounds__(CROP_MAX_THREADS, 3) hpb_crop_pixels_kernel(co
                 if (by > loaded_hi + 1 || by < loaded_hi - 3) {  // first row of the band / a jump: restart the window at `by`
                     prow = by;
                     pp4 = base4 + (size_t)min(by, Hm1) * Wst;
+                    pp8 = base8 + (size_t)min(by, Hm1) * Wst;
                     pp1 = base1 + (size_t)min(by, Hm1) * Wst;
                     fetch();
                     loaded_hi = by - 1;
@@ -340,7 +374,8 @@ __global__ void __launch_bounds__(CROP_MAX_THREADS, 3) hpb_crop_pixels_kernel(co
                         default: filter_into(hw[3]); break;
                     }
                     const int step = prow < Hm1 ? Wst : 0;  // rows past the frame repeat the last row (their weights are zero)
-                    if (PACKED) pp4 += step;
+                    if (MODE == 2) pp8 += step;
+                    else if (MODE == 1) pp4 += step;
                     else pp1 += step;
                     ++prow;
                     fetch();
@@ -423,8 +458,10 @@ int hpb_launch_crop_pixels(hpb_ctx *ctx, const float *images, int n_im, int C, i
     p.n_im = n_im; p.C = C; p.H = H; p.W = W; p.b = b; p.h = h; p.w = w;
     p.crops = crops; p.crops_bs = crops_bs;
     p.packed = nullptr;
-    // few distinct frames, many hypotheses: interleave the frames once so a tap is one 16-byte load
+    p.packed_h = nullptr;
+    // few distinct frames, many hypotheses: interleave the frames once so a tap is one 16-byte (fp16 copy: 8-byte) load
     const long long n_px = (long long)H * W, total = n_px * n_im;
+    const bool half_taps = ctx->crop_tap_bits == 16 && C == 3;
     if ((long long)n_im * 8 <= b && total * 16 <= (1ll << 28)) {
         if (ctx->frame_pack_bytes < (size_t)total * 16) {
             if (ctx->frame_pack) HPB_CUDA_OK(cudaFree(ctx->frame_pack));
@@ -434,11 +471,13 @@ int hpb_launch_crop_pixels(hpb_ctx *ctx, const float *images, int n_im, int C, i
             ctx->frame_pack_bytes = (size_t)total * 16;
         }
         const int blocks = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
-        if (C == 3) hpb_pack_frames_kernel<3><<<blocks, 256, 0, stream>>>(images, n_px, total, (float4 *)ctx->frame_pack);
+        if (half_taps) hpb_pack_frames_half_kernel<<<blocks, 256, 0, stream>>>(images, n_px, total, (uint2 *)ctx->frame_pack);
+        else if (C == 3) hpb_pack_frames_kernel<3><<<blocks, 256, 0, stream>>>(images, n_px, total, (float4 *)ctx->frame_pack);
         else hpb_pack_frames_kernel<4><<<blocks, 256, 0, stream>>>(images, n_px, total, (float4 *)ctx->frame_pack);
         HPB_CUDA_OK(cudaGetLastError());
         ctx->launches++;
-        p.packed = (const float4 *)ctx->frame_pack;
+        if (half_taps) p.packed_h = (const uint2 *)ctx->frame_pack;
+        else p.packed = (const float4 *)ctx->frame_pack;
     }
     // rows per CTA: enough CTAs to fill the machine for small batches, long bands (window fill amortised) otherwise
     int band = CROP_BAND_MAX;
@@ -448,11 +487,12 @@ int hpb_launch_crop_pixels(hpb_ctx *ctx, const float *images, int n_im, int C, i
     const size_t smem = (size_t)band * CROP_SPAN * sizeof(float) + (size_t)band * sizeof(int);
     dim3 grid((h + band - 1) / band, b, (w + threads - 1) / threads);
     if (C == 3) {
-        if (p.packed) hpb_crop_pixels_kernel<3, true><<<grid, threads, smem, stream>>>(p);
-        else hpb_crop_pixels_kernel<3, false><<<grid, threads, smem, stream>>>(p);
+        if (p.packed_h) hpb_crop_pixels_kernel<3, 2><<<grid, threads, smem, stream>>>(p);
+        else if (p.packed) hpb_crop_pixels_kernel<3, 1><<<grid, threads, smem, stream>>>(p);
+        else hpb_crop_pixels_kernel<3, 0><<<grid, threads, smem, stream>>>(p);
     } else {
-        if (p.packed) hpb_crop_pixels_kernel<4, true><<<grid, threads, smem, stream>>>(p);
-        else hpb_crop_pixels_kernel<4, false><<<grid, threads, smem, stream>>>(p);
+        if (p.packed) hpb_crop_pixels_kernel<4, 1><<<grid, threads, smem, stream>>>(p);
+        else hpb_crop_pixels_kernel<4, 0><<<grid, threads, smem, stream>>>(p);
     }
     HPB_CUDA_OK(cudaGetLastError());
     ctx->launches++;

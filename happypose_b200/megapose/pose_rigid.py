@@ -145,6 +145,7 @@ class PosePredictor(nn.Module):
         self.debug_data = PosePredictorDebugData()
         self._net_ready = False
         self._folded = None
+        self._crop_tap_bits: Optional[int] = None  # None = follow compute_dtype (see crop_tap_bits)
         self.use_direct_s2d = True  # forward_coarse: rasteriser writes the stem's bf16 input directly (see _direct_s2d_ok)
         # replay launch-bound batches as CUDA graphs (utils/cuda_graphs.py); off by default, PoseEstimator turns it on
         self.use_cuda_graphs = False
@@ -175,6 +176,20 @@ class PosePredictor(nn.Module):
     # ---- helpers -------------------------------------------------------------------------------
     def _ctx(self) -> Context:
         return self.renderer._ctx
+
+    @property
+    def crop_tap_bits(self) -> int:
+        """Precision of the frame samples of hpb_crop: float32 (the reference's arithmetic) when the network computes in
+        float32; fp16 taps of RGB frames (|error| <= 2.5e-4 on [0,1], BASELINE bar 1e-3) when the network input is
+        rounded to bf16 / fp16 anyway -- the crop kernel is bound by L1 sector look-ups, 8-byte taps halve them."""
+        if self._crop_tap_bits is not None:
+            return self._crop_tap_bits
+        return 16 if self.compute_dtype in (torch.bfloat16, torch.float16) else 32
+
+    @crop_tap_bits.setter
+    def crop_tap_bits(self, bits: Optional[int]) -> None:
+        assert bits in (None, 16, 32)
+        self._crop_tap_bits = bits
 
     def _ids(self, labels: List[str], im_ids, bsz: int, device):
         obj_ids = self.mesh_db.label_ids(labels, device)
@@ -219,7 +234,7 @@ class PosePredictor(nn.Module):
         obj_ids, _, im_ids_t = self._ids(labels, im_ids, bsz, TCO.device)
         crops, K_crop, boxes_rend, boxes_crop = ops.crop(
             self._ctx(), images, im_ids_t, self.mesh_db.points_subset(2000), obj_ids, K, TCO, tCR,
-            self.render_size, lamb=1.4, out=out)
+            self.render_size, lamb=1.4, out=out, tap_bits=self.crop_tap_bits)
         return crops, K_crop, boxes_rend, boxes_crop
 
     def compute_crops_multiview(self, images, K, TCV_O, tCR, labels) -> torch.Tensor:
@@ -402,7 +417,7 @@ class PosePredictor(nn.Module):
 
             x = self._alloc_input(bsz, device)
             images_crop, K_crop, boxes_rend, boxes_crop = ops.crop(
-                ctx, images, im_ids, pts2000, obj_ids, K, TCO_input, tCR, self.render_size, out=x)
+                ctx, images, im_ids, pts2000, obj_ids, K, TCO_input, tCR, self.render_size, out=x, tap_bits=self.crop_tap_bits)
             if n_views > 1 or self.remove_TCO_rendering:
                 Kmv = K.unsqueeze(1).expand(bsz, n_views, 3, 3).reshape(-1, 3, 3)
                 KV_crop, _, _ = ops.crop_boxes(
@@ -495,7 +510,8 @@ class PosePredictor(nn.Module):
             # fused hand-off: the rasteriser's resolve writes the stem's bf16 space-to-depth input itself (crop channels
             # read from the crop kernel's planes): no float32 [b,9,h,w] network input, no packing pass
             crops, K_crop, _, _ = ops.crop(
-                ctx, images, im_ids, self.mesh_db.points_subset(2000), obj_ids, K, TCO_input, tCR, self.render_size)
+                ctx, images, im_ids, self.mesh_db.points_subset(2000), obj_ids, K, TCO_input, tCR, self.render_size,
+                tap_bits=self.crop_tap_bits)
             render_start = time.time()
             z = ops.render_s2d_bf16(ctx, mesh_ids, TCO_input, K_crop, crops, self._folded.s2d_channels)
             render_time = time.time() - render_start
@@ -508,7 +524,8 @@ class PosePredictor(nn.Module):
             return out
         x = self._alloc_input(bsz, device)
         images_crop, K_crop, boxes_rend, boxes_crop = ops.crop(
-            ctx, images, im_ids, self.mesh_db.points_subset(2000), obj_ids, K, TCO_input, tCR, self.render_size, out=x)
+            ctx, images, im_ids, self.mesh_db.points_subset(2000), obj_ids, K, TCO_input, tCR, self.render_size, out=x,
+            tap_bits=self.crop_tap_bits)
 
         render_timer = CudaTimer(enabled=cuda_timer) if torch.cuda.is_available() else SimpleTimer()
         render_start = time.time()

@@ -225,8 +225,12 @@ def crop(
     render_size: Tuple[int, int],
     lamb: float = 1.4,
     out: Optional[torch.Tensor] = None,
+    tap_bits: int = 32,
 ):
     """crop_inputs: returns (images_cropped [b,C,h,w], K_crop [b,3,3], boxes_rend [b,4], boxes_crop [b,4]).
+
+    tap_bits = 16 lets the kernel sample an fp16 copy of an RGB frame (hpb_set_crop_tap_precision: the result is the
+    float32 crop of fp16(frame), |error| <= 2.5e-4 on [0,1] pixel values); used for the bf16 network hand-off.
 
     images [n_im,C,H,W] float32 (not expanded per hypothesis), im_ids [b]; points [n_obj,n_pts,3], obj_ids [b].
     With `out` ([b,C_total,h,w]) the crop is written into channels [0,C) of it.
@@ -253,6 +257,7 @@ def crop(
     K_crop = torch.empty((b, 3, 3), dtype=torch.float32, device=dev)
     boxes_rend = torch.empty((b, 4), dtype=torch.float32, device=dev)
     boxes_crop = torch.empty((b, 4), dtype=torch.float32, device=dev)
+    ctx.check(ctx.lib.hpb_set_crop_tap_precision(ctx.handle, 16 if (tap_bits == 16 and C == 3) else 32), "hpb_set_crop_tap_precision")
     ev = None
     if _kernel_timer is not None:
         ev = _kernel_timer.bracket("hpb_crop", b * C * h * w * 4)

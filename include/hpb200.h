@@ -151,6 +151,16 @@ int hpb_crop(hpb_ctx *ctx, const float *images_dev, int n_im, int C, int H, int 
              int64_t crops_bstride, float *K_crop_dev, float *boxes_rend_dev, float *boxes_crop_dev,
              void *stream);
 
+/*
+ * Precision of the frame samples ("taps") hpb_crop reads when it resamples from its pixel-interleaved copy of an RGB
+ * frame (many hypotheses per frame).  32 (default): float32, the reference's arithmetic (cropping.py:155-197, torchvision
+ * roi_align on float32 images).  16: the copy holds IEEE fp16 -- 8-byte instead of 16-byte taps, which halves the L1
+ * sector look-ups that bound the kernel; the crop of a frame f then equals the 32-bit crop of fp16(f) bit for bit, i.e.
+ * an absolute error <= 2.5e-4 for pixel values in [0,1] (BASELINE bar for crops: 1e-3).  Meant for the bf16 network
+ * path, whose input is rounded to 8 mantissa bits anyway.  RGB-D frames always use 32.  Host-side switch, no sync.
+ */
+int hpb_set_crop_tap_precision(hpb_ctx *ctx, int bits);
+
 /* Boxes and K_crop only (compute_crops_multiview: return_crops=False, 200 points). H,W = source frame size. */
 int hpb_crop_boxes(hpb_ctx *ctx, int H, int W, const float *points_dev, int n_obj, int n_pts,
                    const int32_t *obj_ids_dev, const float *K_dev, const float *TCO_dev, const float *tCR_dev,

@@ -54,6 +54,8 @@ def main():
         ms = timeit(lambda: ops.crop(ctx, img, zero, pts, zero, K, TCO, tCR, (240, 320), out=x))
         gb = b * 3 * 240 * 320 * 4 / 1e9
         print(json.dumps({"kernel": "crop (boxes+pixels)", "b": b, "ms": round(ms, 4), "hyps_per_s": round(b / ms * 1e3), "GBps": round(gb / ms * 1e3, 1), "frac": round(gb / ms * 1e3 / peak, 4)}))
+        ms = timeit(lambda: ops.crop(ctx, img, zero, pts, zero, K, TCO, tCR, (240, 320), out=x, tap_bits=16))
+        print(json.dumps({"kernel": "crop (boxes+pixels), fp16 taps", "b": b, "ms": round(ms, 4), "hyps_per_s": round(b / ms * 1e3), "GBps": round(gb / ms * 1e3, 1), "frac": round(gb / ms * 1e3 / peak, 4)}))
 
 if __name__ == "__main__":
     main()

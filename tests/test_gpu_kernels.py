@@ -349,6 +349,34 @@ def test_crop_wide_output_uses_column_tiles(ctx, can_mesh_arrays):
         np.testing.assert_allclose(crops.cpu().numpy(), ref, atol=2e-5)
 
 
+def test_crop_fp16_taps_equal_float_crop_of_the_fp16_frame(ctx, golden, can_mesh_arrays):
+    """hpb_set_crop_tap_precision(16): the kernel samples an fp16 copy of the RGB frame.  Exactness statement: the result
+    is the 32-bit-tap crop of fp16(frame), bit for bit (same boxes, same weights, same summation order); against the
+    reference's float32 golden crops (real torchvision roi_align) it stays inside the BASELINE bar of 1e-3 absolute."""
+    from happypose_b200 import ops
+
+    pts = _mesh_points(can_mesh_arrays)[O.sample_point_ids(9951, 2000)]
+    g = golden("ref_crop_full.npz")
+    rep = 3  # 12 rows of one frame: enough rows per frame for the interleaved-copy path the option applies to
+    K, TCO, tCR = (np.tile(g[k], (rep,) + (1,) * (g[k].ndim - 1)) for k in ("K", "TCO", "tCR"))
+    b = len(TCO)
+    image = torch.as_tensor(np.random.RandomState(int(g["image_seed"])).rand(1, 3, 480, 640).astype(np.float32)).cuda()
+    zero = torch.zeros(b, dtype=torch.int32)
+    args = (zero, torch.as_tensor(pts[None]), zero, K, TCO, tCR, (240, 320))
+    c16, K16, _, bc16 = ops.crop(ctx, image, *args, tap_bits=16)
+    c32_of_half, K32, _, bc32 = ops.crop(ctx, image.half().float(), *args, tap_bits=32)
+    assert torch.equal(c16, c32_of_half) and torch.equal(K16, K32) and torch.equal(bc16, bc32)
+    c32, _, _, _ = ops.crop(ctx, image, *args, tap_bits=32)
+    assert 0 < float((c16 - c32).abs().max()) <= 2.5e-4  # fp16 spacing on [0.5, 1) is 4.9e-4; convex combinations keep the bound
+    np.testing.assert_allclose(c16.cpu().numpy()[:4, :, ::5, ::5], g["crops_sub"], atol=1e-3)
+    np.testing.assert_allclose(c32.cpu().numpy()[:4, :, ::5, ::5], g["crops_sub"], atol=1e-3)
+    # RGB-D frames keep float32 taps whatever the option says
+    imaged = torch.cat([image, torch.rand(1, 1, 480, 640, device="cuda") + 0.2], 1)
+    d16, _, _, _ = ops.crop(ctx, imaged, *args, tap_bits=16)
+    d32, _, _, _ = ops.crop(ctx, imaged, *args, tap_bits=32)
+    assert torch.equal(d16, d32)
+
+
 def test_crop_boxes_multiview_200_points(ctx, can_mesh_arrays):
     from happypose_b200 import ops
 
