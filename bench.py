@@ -459,7 +459,8 @@ def run_ours(args):
     crops_buf = torch.empty((b, 3, H_R, W_R), device=dev)
 
     def render_crop_fused():  # what the pipeline's coarse stage does: crop planes, then the rasteriser writes the stem input
-        _, K_crop, _, _ = ops.crop(ctx, obs_dev.images, obj0, pts, obj0, K_rows, TCO, TCO[:, :3, 3].contiguous(), (H_R, W_R), out=crops_buf)
+        _, K_crop, _, _ = ops.crop(ctx, obs_dev.images, obj0, pts, obj0, K_rows, TCO, TCO[:, :3, 3].contiguous(), (H_R, W_R), out=crops_buf,
+                                   tap_bits=coarse.crop_tap_bits)
         ops.render_s2d_bf16(ctx, mesh_ids, TCO, K_crop, crops_buf, 64)
 
     for _ in range(3):
@@ -505,7 +506,7 @@ def run_ours(args):
                         "largest_launch_gbps": v["largest"]["gbps"], "largest_launch_frac": v["largest"]["gbps"] / peak,
                         "largest_launch_ms": v["largest"]["ms_avg"]} for k, v in ksum.items()},
         "hyps": {"metric": "rendered_hyps_per_sec", "value": hyps_per_s, "unit": "hyps/s", "b": b, "ms_per_launch_pair": ms_hyp / hyp_iters,
-                 "path": "hpb_crop -> hpb_render_s2d_bf16 (the pipeline's coarse hand-off: bf16 space-to-depth stem input)",
+                 "path": "hpb_crop (fp16 frame taps) -> hpb_render_s2d_bf16 (the pipeline's coarse hand-off: bf16 space-to-depth stem input)",
                  # bytes moved per hypothesis: crop planes written + read back, stem-input cells written
                  "gbps": b * (2 * 3 * H_R * W_R * 4 + (H_R // 2 + 3) * (W_R // 2 + 3) * 64 * 2) / 1e9 / (ms_hyp / hyp_iters / 1e3),
                  "frac": b * (2 * 3 * H_R * W_R * 4 + (H_R // 2 + 3) * (W_R // 2 + 3) * 64 * 2) / 1e9 / (ms_hyp / hyp_iters / 1e3) / peak,
