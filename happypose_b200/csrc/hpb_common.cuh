@@ -58,7 +58,7 @@ struct hpb_ctx {
     size_t vis_elems = 0;
     unsigned char *vert_scratch = nullptr;  // [resident CTAs][max_nv * 12 B] when a mesh does not fit in shared memory
     size_t vert_scratch_bytes = 0;
-    int max_clusters[4] = {0, 0, 0, 0};  // co-resident clusters of size 1,2,4,8 (queried once per shared-memory size)
+    int max_clusters[5] = {0, 0, 0, 0, 0};  // co-resident clusters of size 1,2,4,8,16 (queried once per shared-memory size)
     size_t max_clusters_smem = (size_t)-1;
     // crop workspace: pixel-interleaved copy of the observed frames
     void *frame_pack = nullptr;

@@ -817,10 +817,14 @@ int hpb_launch_raster(hpb_ctx *ctx, const int32_t *mesh_ids, const float *TCO, c
     // both instantiations get the attribute: the cluster-occupancy query below is made on <false> whichever runs first
     HPB_CUDA_OK(cudaFuncSetAttribute(hpb_raster_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     HPB_CUDA_OK(cudaFuncSetAttribute(hpb_raster_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // clusters of 16 CTAs (non-portable size) for the smallest batches: a 4-view refiner launch then spreads over 64 SMs
+    static bool np_ok = cudaFuncSetAttribute(hpb_raster_kernel<false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
+                        cudaFuncSetAttribute(hpb_raster_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
+    if (!np_ok) cudaGetLastError();
 
     // how many clusters of 1/2/4/8 CTAs can be co-resident (one CTA per SM); queried once per shared-memory size
     if (ctx->max_clusters_smem != smem) {
-        for (int k = 0; k < 4; ++k) {
+        for (int k = 0; k < 5; ++k) {
             const int G = 1 << k;
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3(G * 8, 1, 1);
@@ -833,6 +837,7 @@ int hpb_launch_raster(hpb_ctx *ctx, const int32_t *mesh_ids, const float *TCO, c
             cfg.numAttrs = 1;
             int n = 0;
             if (G == 1) n = ctx->sm_count;
+            else if (G == 16 && !np_ok) n = 0;
             else if (cudaOccupancyMaxActiveClusters(&n, hpb_raster_kernel<false>, &cfg) != cudaSuccess) { n = 0; cudaGetLastError(); }
             ctx->max_clusters[k] = n;
         }
@@ -840,7 +845,7 @@ int hpb_launch_raster(hpb_ctx *ctx, const int32_t *mesh_ids, const float *TCO, c
     }
     // persistent grid: the largest cluster size that still gives every scene its own cluster
     int k = 0;
-    while (k < 3 && ctx->max_clusters[k + 1] >= b) ++k;
+    while (k < 4 && ctx->max_clusters[k + 1] >= b) ++k;
     const int G = 1 << k;
     const int n_groups = b < ctx->max_clusters[k] ? b : ctx->max_clusters[k];
     const int n_ctas = n_groups * G;
