@@ -287,9 +287,11 @@ class PosePredictor(nn.Module):
         return {k: head(x).float() for k, head in self.heads.items()}
 
     # ---- rendering -----------------------------------------------------------------------------
-    def render_images_multiview(self, labels, TCV_O, KV, random_ambient_light: bool = False, out=None, mesh_ids=None):
+    def render_images_multiview(self, labels, TCV_O, KV, random_ambient_light: bool = False, out=None, mesh_ids=None,
+                                mesh_ids_per_view: bool = False):
         """pose_rigid.py:376-453 -> renders [bsz, n_views*n_channels, H, W].
-        With `out` (the network input) the renders are written into its channels after the crop."""
+        With `out` (the network input) the renders are written into its channels after the crop.  `mesh_ids` are the
+        renderer's ids per row, or (mesh_ids_per_view) already repeated per view."""
         bsz = TCV_O.shape[0]
         n_views = TCV_O.shape[1]
         assert isinstance(self.renderer, Panda3dBatchRenderer)
@@ -304,7 +306,8 @@ class PosePredictor(nn.Module):
                 "point lights are not evaluated by the CUDA rasteriser")
         if mesh_ids is None:
             mesh_ids = self.renderer.mesh_ids(labels)
-        mesh_ids = mesh_ids.repeat_interleave(n_views) if n_views > 1 else mesh_ids
+        if not mesh_ids_per_view:
+            mesh_ids = mesh_ids.repeat_interleave(n_views) if n_views > 1 else mesh_ids
         C_in = self.n_input_channels
         if out is None:
             out = torch.empty((bsz, C_in + n_views * self._n_single_render_channels) + tuple(self.render_size), dtype=torch.float32, device=device)
@@ -407,6 +410,13 @@ class PosePredictor(nn.Module):
         n_views = self.n_rendered_views
         pts2000 = self.mesh_db.points_subset(2000)
 
+        # loop invariants of the iterations (each of these is one or more tiny kernels): per-view copies of the ids / K
+        multi = n_views > 1 or self.remove_TCO_rendering
+        if multi:
+            Kmv = K.unsqueeze(1).expand(bsz, n_views, 3, 3).reshape(-1, 3, 3)
+            obj_ids_v = obj_ids.repeat_interleave(n_views)
+        mesh_ids_v = mesh_ids.repeat_interleave(n_views) if (mesh_ids is not None and n_views > 1) else mesh_ids
+
         outputs = {}
         TCO_input = TCO
         for n in range(n_iterations):
@@ -418,10 +428,9 @@ class PosePredictor(nn.Module):
             x = self._alloc_input(bsz, device)
             images_crop, K_crop, boxes_rend, boxes_crop = ops.crop(
                 ctx, images, im_ids, pts2000, obj_ids, K, TCO_input, tCR, self.render_size, out=x, tap_bits=self.crop_tap_bits)
-            if n_views > 1 or self.remove_TCO_rendering:
-                Kmv = K.unsqueeze(1).expand(bsz, n_views, 3, 3).reshape(-1, 3, 3)
+            if multi:
                 KV_crop, _, _ = ops.crop_boxes(
-                    ctx, images.shape[-2:], self.mesh_db.points_subset(200), obj_ids.repeat_interleave(n_views), Kmv,
+                    ctx, images.shape[-2:], self.mesh_db.points_subset(200), obj_ids_v, Kmv,
                     TCV_O_input.flatten(0, 1), tCV_R.flatten(0, 1), self.render_size, lamb=1.4)
                 KV_crop = KV_crop.view(bsz, n_views, 3, 3)
                 if not self.remove_TCO_rendering:
@@ -430,7 +439,8 @@ class PosePredictor(nn.Module):
                 KV_crop = K_crop.unsqueeze(1)
 
             t = time.time()
-            renders = self.render_images_multiview(labels, TCV_O_input, KV_crop, random_ambient_light, out=x, mesh_ids=mesh_ids)
+            renders = self.render_images_multiview(labels, TCV_O_input, KV_crop, random_ambient_light, out=x, mesh_ids=mesh_ids_v,
+                                                   mesh_ids_per_view=mesh_ids_v is not None)
             timing_dict["render"] = time.time() - t
 
             self._normalize_input_(x, tCR)
