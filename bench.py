@@ -349,7 +349,8 @@ def run_ours(args):
     with torch.no_grad():  # identity-biased pose head: random weights must not throw the object out of the frame
         refiner.pose_fc.weight.mul_(1e-2)
         refiner.pose_fc.bias.copy_(torch.tensor([1.0, 0, 0, 0, 1, 0, 0, 0, 1]))
-    est = PoseEstimator(refiner_model=refiner, coarse_model=coarse, bsz_objects=16, bsz_images=576, SO3_grid_size=M_GRID)
+    est = PoseEstimator(refiner_model=refiner, coarse_model=coarse, bsz_objects=16, bsz_images=576, SO3_grid_size=M_GRID,
+                        shard_across_ranks=True)  # every rank passes the same frame + detections; rows are split
     est.use_cuda_graphs = not args.no_graphs
     ctx = coarse._ctx()
 

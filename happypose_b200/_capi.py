@@ -30,6 +30,8 @@ SIGNATURES = {
     "hpb_create": (c_int, [c_int, ctypes.POINTER(c_void_p)]),
     "hpb_destroy": (c_int, [c_void_p]),
     "hpb_launch_count": (c_int64, [c_void_p]),
+    "hpb_workspace_epoch": (c_int64, [c_void_p]),
+    "hpb_reserve": (c_int, [c_void_p, c_int, c_int, c_int64, c_int64, c_int64]),
     "hpb_mesh_upload": (c_int, [c_void_p] * 5 + [c_int64, c_void_p, c_int64, c_void_p, c_int, c_int, c_int, ctypes.POINTER(c_int32)]),
     "hpb_mesh_count": (c_int, [c_void_p]),
     "hpb_mesh_get_mip": (c_int, [c_void_p, c_int32, c_int, c_void_p, ctypes.POINTER(c_int), ctypes.POINTER(c_int), ctypes.POINTER(c_int)]),
@@ -39,7 +41,7 @@ SIGNATURES = {
                            c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int64, c_void_p]),
     "hpb_crop": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p,
                          c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_int64, c_void_p,
-                         c_void_p, c_void_p, c_void_p]),
+                         c_void_p, c_void_p, c_int, c_void_p]),
     "hpb_set_crop_tap_precision": (c_int, [c_void_p, c_int]),
     "hpb_crop_boxes": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
@@ -135,6 +137,15 @@ class Context:
 
     def launch_count(self) -> int:
         return int(self.lib.hpb_launch_count(self.handle))
+
+    def workspace_epoch(self) -> int:
+        """Bumped whenever a workspace buffer was replaced by a larger one (captured graphs may want re-capturing)."""
+        return int(self.lib.hpb_workspace_epoch(self.handle))
+
+    def reserve(self, render_size=(0, 0), frame_pixels: int = 0, topk_rows: int = 0, topk_groups: int = 0) -> None:
+        """Sizes the workspaces up front (hpb_reserve) so that no launch has to allocate, e.g. under graph capture."""
+        _check(self.lib.hpb_reserve(self.handle, int(render_size[0]), int(render_size[1]), int(frame_pixels), int(topk_rows),
+                                    int(topk_groups)), "hpb_reserve")
 
     def check(self, rc: int, what: str) -> None:
         _check(rc, what)

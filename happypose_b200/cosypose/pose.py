@@ -62,16 +62,15 @@ class PosePredictor(nn.Module):
         return ops.pose_update(self._ctx(), TCO, K_crop, pose_outputs, None, variant)
 
     def net_forward(self, x):
-        if not self._net_ready:
-            if x.is_cuda and self.compute_dtype != torch.float32:
-                self.backbone.to(dtype=self.compute_dtype, memory_format=torch.channels_last)
-                self.pose_fc.to(dtype=self.compute_dtype)
-            self._net_ready = True
+        """pose.py:108-114.  Reduced-precision compute runs the unchanged module under autocast (never cast in place);
+        the pooled features and the pose head stay float32."""
         if x.is_cuda and self.compute_dtype != torch.float32:
-            x = x.to(dtype=self.compute_dtype, memory_format=torch.channels_last)
-        f = self.backbone(x)
-        f = f.flatten(2).mean(dim=-1)
-        return {k: head(f).float() for k, head in self.heads.items()}
+            with torch.autocast("cuda", dtype=self.compute_dtype):
+                f = self.backbone(x.contiguous(memory_format=torch.channels_last))
+        else:
+            f = self.backbone(x)
+        f = f.float().flatten(2).mean(dim=-1)
+        return {k: head(f) for k, head in self.heads.items()}
 
     def forward(self, images, K, labels, TCO, n_iterations=1, im_ids=None) -> Dict[str, PosePredictorOutputCosypose]:
         bsz = TCO.shape[0]

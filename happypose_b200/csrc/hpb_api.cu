@@ -13,7 +13,7 @@ int hpb_launch_crop_boxes(hpb_ctx *ctx, int H, int W, const float *points, int n
                           const float *K, const float *TCO, const float *tCR, int b, int h, int w, float lamb,
                           float *K_crop, float *boxes_rend, float *boxes_crop, cudaStream_t stream);
 int hpb_launch_crop_pixels(hpb_ctx *ctx, const float *images, int n_im, int C, int H, int W, const int32_t *im_ids,
-                           const float *boxes, int b, int h, int w, float *crops, int64_t crops_bs,
+                           const float *boxes, int b, int h, int w, float *crops, int64_t crops_bs, int tap_bits,
                            cudaStream_t stream);
 int hpb_launch_normalize_T(hpb_ctx *ctx, const float *T, int b, float *out, cudaStream_t stream);
 int hpb_launch_pose_update(hpb_ctx *ctx, const float *TCO, const float *K_crop, const float *outv, const float *tCR,
@@ -34,6 +34,50 @@ int hpb_launch_topk(hpb_ctx *ctx, const float *scores, const int32_t *groups, in
                     int64_t *out_idx, int32_t *out_count, cudaStream_t stream);
 
 static thread_local char g_err[512] = "";
+
+int hpb_ws_grow(hpb_ctx *ctx, void **ptr, size_t *cur_bytes, size_t need, cudaStream_t stream, const char *what) {
+    if (*cur_bytes >= need && *ptr) return HPB_OK;
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(stream, &st) != cudaSuccess) cudaGetLastError();
+    if (st != cudaStreamCaptureStatusNone) {
+        hpb_set_error("%s workspace must grow to %zu bytes while the stream is being captured into a CUDA graph; "
+                      "run the call once eagerly or call hpb_reserve() before capturing", what, need);
+        return HPB_EINVAL;
+    }
+    void *fresh = nullptr;
+    HPB_CUDA_OK(cudaMalloc(&fresh, need));
+    if (*ptr) ctx->retired.push_back(*ptr);  // captured graphs may still reference it
+    *ptr = fresh;
+    *cur_bytes = need;
+    ctx->workspace_epoch++;
+    return HPB_OK;
+}
+
+int hpb_stream_enter(hpb_ctx *ctx, cudaStream_t stream) {
+    if (ctx->done_ev_valid && ctx->last_stream != stream) {
+        cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(stream, &st) != cudaSuccess) cudaGetLastError();
+        if (st == cudaStreamCaptureStatusNone) HPB_CUDA_OK(cudaStreamWaitEvent(stream, ctx->done_ev, 0));
+    }
+    return HPB_OK;
+}
+
+void hpb_stream_leave(hpb_ctx *ctx, cudaStream_t stream) {
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(stream, &st) != cudaSuccess) cudaGetLastError();
+    if (st != cudaStreamCaptureStatusNone) return;  // inside a graph: ordering is the graph's own
+    if (!ctx->done_ev && cudaEventCreateWithFlags(&ctx->done_ev, cudaEventDisableTiming) != cudaSuccess) {
+        cudaGetLastError();
+        ctx->done_ev = nullptr;
+        return;
+    }
+    if (cudaEventRecord(ctx->done_ev, stream) == cudaSuccess) {
+        ctx->done_ev_valid = true;
+        ctx->last_stream = stream;
+    } else {
+        cudaGetLastError();
+    }
+}
 
 void hpb_set_error(const char *fmt, ...) {
     va_list ap;
@@ -168,6 +212,8 @@ int hpb_destroy(hpb_ctx *ctx) {
     for (auto &m : ctx->meshes) {
         cudaFree(m.pos); cudaFree(m.nrm); cudaFree(m.uv); cudaFree(m.vcol); cudaFree(m.faces); cudaFree(m.tex); cudaFree(m.nu); cudaFree(m.tv);
     }
+    for (void *p : ctx->retired) cudaFree(p);
+    if (ctx->done_ev) cudaEventDestroy(ctx->done_ev);
     cudaFree(ctx->meshes_dev);
     cudaFree(ctx->vis);
     cudaFree(ctx->vert_scratch);
@@ -178,6 +224,19 @@ int hpb_destroy(hpb_ctx *ctx) {
 }
 
 int64_t hpb_launch_count(const hpb_ctx *ctx) { return ctx ? ctx->launches : 0; }
+int64_t hpb_workspace_epoch(const hpb_ctx *ctx) { return ctx ? ctx->workspace_epoch : 0; }
+
+int hpb_reserve(hpb_ctx *ctx, int render_h, int render_w, int64_t frame_pixels, int64_t topk_rows, int64_t topk_groups) {
+    HPB_REQUIRE(ctx, "NULL ctx");
+    HPB_REQUIRE(render_h >= 0 && render_w >= 0 && frame_pixels >= 0 && topk_rows >= 0 && topk_groups >= 0, "negative size");
+    HpbDeviceGuard guard(ctx->device);
+    int rc = HPB_OK;
+    if (render_h > 0 && render_w > 0) rc = hpb_raster_reserve(ctx, render_h, render_w, nullptr);
+    if (rc == HPB_OK && frame_pixels > 0) rc = hpb_crop_reserve(ctx, frame_pixels, nullptr);
+    if (rc == HPB_OK && topk_rows > 0) rc = hpb_topk_reserve(ctx, topk_rows, topk_groups, nullptr);
+    if (rc == HPB_OK) HPB_CUDA_OK(cudaStreamSynchronize(nullptr));
+    return rc;
+}
 int hpb_mesh_count(const hpb_ctx *ctx) { return ctx ? (int)ctx->meshes.size() : 0; }
 
 int hpb_mesh_upload(hpb_ctx *ctx, const float *verts_xyz, const float *normals, const float *uv,
@@ -296,7 +355,11 @@ int hpb_mesh_upload(hpb_ctx *ctx, const float *verts_xyz, const float *normals, 
         HpbMeshDev *nd = nullptr;
         HPB_CUDA_OK(cudaMalloc(&nd, sizeof(HpbMeshDev) * cap));
         HPB_CUDA_OK(cudaDeviceSynchronize());
-        if (ctx->meshes_dev) cudaFree(ctx->meshes_dev);
+        if (ctx->meshes_dev) {
+            // the old table stays valid for the mesh ids it holds (captured graphs reference it): retire, do not free
+            ctx->retired.push_back(ctx->meshes_dev);
+            ctx->workspace_epoch++;
+        }
         ctx->meshes_dev = nd;
         ctx->meshes_dev_cap = cap;
         std::vector<HpbMeshDev> all(n);
@@ -411,9 +474,12 @@ int hpb_crop_boxes(hpb_ctx *ctx, int H, int W, const float *points_dev, int n_ob
 int hpb_crop(hpb_ctx *ctx, const float *images_dev, int n_im, int C, int H, int W, const int32_t *im_ids_dev,
              const float *points_dev, int n_obj, int n_pts, const int32_t *obj_ids_dev, const float *K_dev,
              const float *TCO_dev, const float *tCR_dev, int b, int h, int w, float lamb, float *crops_dev,
-             int64_t crops_bstride, float *K_crop_dev, float *boxes_rend_dev, float *boxes_crop_dev, void *stream) {
+             int64_t crops_bstride, float *K_crop_dev, float *boxes_rend_dev, float *boxes_crop_dev, int tap_bits,
+             void *stream) {
     HPB_REQUIRE(ctx, "NULL ctx");
     HPB_REQUIRE(C == 3 || C == 4, "images must have 3 or 4 channels");  // cropping.py:161
+    HPB_REQUIRE(tap_bits == 0 || tap_bits == 16 || tap_bits == 32, "tap_bits must be 0 (context default), 16 or 32");
+    if (tap_bits == 0) tap_bits = ctx->crop_tap_bits;
     HPB_REQUIRE(n_im > 0 && images_dev && im_ids_dev && crops_dev, "NULL image input/output");
     int rc = hpb_crop_boxes(ctx, H, W, points_dev, n_obj, n_pts, obj_ids_dev, K_dev, TCO_dev, tCR_dev, b, h, w, lamb,
                             K_crop_dev, boxes_rend_dev, boxes_crop_dev, stream);
@@ -422,7 +488,7 @@ int hpb_crop(hpb_ctx *ctx, const float *images_dev, int n_im, int C, int H, int 
     for (int s = 0; s < b; s += 32768) {  // grid.y limit
         const int nb = b - s < 32768 ? b - s : 32768;
         rc = hpb_launch_crop_pixels(ctx, images_dev, n_im, C, H, W, im_ids_dev + s, boxes_crop_dev + (size_t)s * 4, nb,
-                                    h, w, crops_dev + (size_t)s * crops_bstride, crops_bstride, (cudaStream_t)stream);
+                                    h, w, crops_dev + (size_t)s * crops_bstride, crops_bstride, tap_bits, (cudaStream_t)stream);
         if (rc != HPB_OK) return rc;
     }
     return HPB_OK;

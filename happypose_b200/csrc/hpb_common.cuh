@@ -68,7 +68,26 @@ struct hpb_ctx {
     void *topk_ws = nullptr;
     size_t topk_ws_bytes = 0;
     int64_t launches = 0;
+    // Workspaces only ever GROW, and a buffer that is replaced is retired (kept allocated until hpb_destroy), never freed:
+    // kernel parameters baked into captured CUDA graphs keep pointing at valid, correctly initialised memory.
+    // workspace_epoch counts replacements so that a caller can re-capture its graphs onto the new buffers.
+    std::vector<void *> retired;
+    int64_t workspace_epoch = 0;
+    // single-stream use of the shared scratch is enforced by an event hand-over when the launching stream changes
+    cudaStream_t last_stream = nullptr;
+    cudaEvent_t done_ev = nullptr;
+    bool done_ev_valid = false;
 };
+
+// Grow *ptr to at least `need` bytes (no-op when large enough).  Never frees: the old buffer is retired.  Fails with a clear
+// message when the stream is being captured into a CUDA graph (allocation is illegal there): call hpb_reserve() first.
+int hpb_ws_grow(hpb_ctx *ctx, void **ptr, size_t *cur_bytes, size_t need, cudaStream_t stream, const char *what);
+// Orders work on `stream` behind the last launch that used the context's shared scratch on another stream.
+int hpb_stream_enter(hpb_ctx *ctx, cudaStream_t stream);
+void hpb_stream_leave(hpb_ctx *ctx, cudaStream_t stream);
+int hpb_raster_reserve(hpb_ctx *ctx, int h, int w, cudaStream_t stream);
+int hpb_topk_reserve(hpb_ctx *ctx, int64_t n, int64_t n_groups, cudaStream_t stream);
+int hpb_crop_reserve(hpb_ctx *ctx, int64_t frame_pixels, cudaStream_t stream);
 
 void hpb_set_error(const char *fmt, ...);
 

@@ -446,7 +446,7 @@ int hpb_launch_crop_boxes(hpb_ctx *ctx, int H, int W, const float *points, int n
 }
 
 int hpb_launch_crop_pixels(hpb_ctx *ctx, const float *images, int n_im, int C, int H, int W, const int32_t *im_ids,
-                           const float *boxes, int b, int h, int w, float *crops, int64_t crops_bs,
+                           const float *boxes, int b, int h, int w, float *crops, int64_t crops_bs, int tap_bits,
                            cudaStream_t stream) {
     if (b == 0) return HPB_OK;
     if (C != 3 && C != 4) {
@@ -461,15 +461,17 @@ int hpb_launch_crop_pixels(hpb_ctx *ctx, const float *images, int n_im, int C, i
     p.packed_h = nullptr;
     // few distinct frames, many hypotheses: interleave the frames once so a tap is one 16-byte (fp16 copy: 8-byte) load
     const long long n_px = (long long)H * W, total = n_px * n_im;
-    const bool half_taps = ctx->crop_tap_bits == 16 && C == 3;
-    if ((long long)n_im * 8 <= b && total * 16 <= (1ll << 28)) {
-        if (ctx->frame_pack_bytes < (size_t)total * 16) {
-            if (ctx->frame_pack) HPB_CUDA_OK(cudaFree(ctx->frame_pack));
-            ctx->frame_pack = nullptr;
-            ctx->frame_pack_bytes = 0;
-            HPB_CUDA_OK(cudaMalloc(&ctx->frame_pack, (size_t)total * 16));
-            ctx->frame_pack_bytes = (size_t)total * 16;
-        }
+    const bool half_taps = tap_bits == 16 && C == 3;  // per launch, not context state: concurrent callers cannot race on it
+    const bool use_pack = (long long)n_im * 8 <= b && total * 16 <= (1ll << 28);
+    if (use_pack) {
+        const int rc = hpb_crop_reserve(ctx, total, stream);
+        if (rc != HPB_OK) return rc;
+    }
+    {
+        const int rc = hpb_stream_enter(ctx, stream);
+        if (rc != HPB_OK) return rc;
+    }
+    if (use_pack) {
         const int blocks = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
         if (half_taps) hpb_pack_frames_half_kernel<<<blocks, 256, 0, stream>>>(images, n_px, total, (uint2 *)ctx->frame_pack);
         else if (C == 3) hpb_pack_frames_kernel<3><<<blocks, 256, 0, stream>>>(images, n_px, total, (float4 *)ctx->frame_pack);
@@ -496,5 +498,10 @@ int hpb_launch_crop_pixels(hpb_ctx *ctx, const float *images, int n_im, int C, i
     }
     HPB_CUDA_OK(cudaGetLastError());
     ctx->launches++;
+    hpb_stream_leave(ctx, stream);
     return HPB_OK;
+}
+
+int hpb_crop_reserve(hpb_ctx *ctx, int64_t frame_pixels, cudaStream_t stream) {
+    return hpb_ws_grow(ctx, &ctx->frame_pack, &ctx->frame_pack_bytes, (size_t)frame_pixels * 16, stream, "crop frame-pack");
 }

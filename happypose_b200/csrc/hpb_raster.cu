@@ -850,27 +850,21 @@ int hpb_launch_raster(hpb_ctx *ctx, const int32_t *mesh_ids, const float *TCO, c
     const int n_groups = b < ctx->max_clusters[k] ? b : ctx->max_clusters[k];
     const int n_ctas = n_groups * G;
 
-    // workspace (grown on demand; the visibility buffer is armed once and re-armed by the kernel itself)
-    const size_t vis_need = (size_t)ctx->sm_count * npix;
-    if (ctx->vis_elems < vis_need) {
-        if (ctx->vis) HPB_CUDA_OK(cudaFree(ctx->vis));
-        ctx->vis = nullptr;
-        ctx->vis_elems = 0;
-        HPB_CUDA_OK(cudaMalloc(&ctx->vis, vis_need * sizeof(unsigned long long)));
-        ctx->vis_elems = vis_need;
-        hpb_fill_u64_kernel<<<ctx->sm_count * 4, 256, 0, stream>>>(ctx->vis, vis_need, HPB_VIS_EMPTY);
-        HPB_CUDA_OK(cudaGetLastError());
-        ctx->launches++;
+    // workspace (grown on demand, never freed; the visibility buffer is armed once and re-armed by the kernel itself)
+    {
+        const int rc = hpb_raster_reserve(ctx, h, w, stream);
+        if (rc != HPB_OK) return rc;
     }
     if (!verts_in_smem) {
         const size_t need = (size_t)ctx->sm_count * nv_pad * 12;
-        if (ctx->vert_scratch_bytes < need) {
-            if (ctx->vert_scratch) HPB_CUDA_OK(cudaFree(ctx->vert_scratch));
-            ctx->vert_scratch = nullptr;
-            ctx->vert_scratch_bytes = 0;
-            HPB_CUDA_OK(cudaMalloc(&ctx->vert_scratch, need));
-            ctx->vert_scratch_bytes = need;
-        }
+        void *vs = ctx->vert_scratch;
+        const int rc = hpb_ws_grow(ctx, &vs, &ctx->vert_scratch_bytes, need, stream, "rasteriser vertex-scratch");
+        if (rc != HPB_OK) return rc;
+        ctx->vert_scratch = (unsigned char *)vs;
+    }
+    {
+        const int rc = hpb_stream_enter(ctx, stream);
+        if (rc != HPB_OK) return rc;
     }
 
     RasterParams p;
@@ -917,6 +911,23 @@ int hpb_launch_raster(hpb_ctx *ctx, const int32_t *mesh_ids, const float *TCO, c
     cfg.attrs = at;
     cfg.numAttrs = G > 1 ? 1 : 0;
     HPB_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, p));
+    ctx->launches++;
+    hpb_stream_leave(ctx, stream);
+    return HPB_OK;
+}
+
+// Visibility buffer for (h x w) renders: one slice per SM, armed (all-empty) once; the kernel re-arms what it reads.
+int hpb_raster_reserve(hpb_ctx *ctx, int h, int w, cudaStream_t stream) {
+    const size_t vis_need = (size_t)ctx->sm_count * h * w;
+    if (ctx->vis_elems >= vis_need && ctx->vis) return HPB_OK;
+    void *v = ctx->vis;
+    size_t bytes = ctx->vis_elems * sizeof(unsigned long long);
+    const int rc = hpb_ws_grow(ctx, &v, &bytes, vis_need * sizeof(unsigned long long), stream, "rasteriser visibility");
+    if (rc != HPB_OK) return rc;
+    ctx->vis = (unsigned long long *)v;
+    ctx->vis_elems = vis_need;
+    hpb_fill_u64_kernel<<<ctx->sm_count * 4, 256, 0, stream>>>(ctx->vis, vis_need, HPB_VIS_EMPTY);
+    HPB_CUDA_OK(cudaGetLastError());
     ctx->launches++;
     return HPB_OK;
 }

@@ -120,13 +120,11 @@ int hpb_launch_topk(hpb_ctx *ctx, const float *scores, const int32_t *groups, in
         return HPB_OK;
     }
     // workspace layout: keys[n] | bucketed[n] | kept[n] | counts[G] | offsets[G+1] | kept_offsets[G+1] | cursors[G]
-    const size_t need = sizeof(unsigned long long) * 3 * (size_t)n + sizeof(int) * (4 * (size_t)n_groups + 2);
-    if (ctx->topk_ws_bytes < need) {
-        if (ctx->topk_ws) HPB_CUDA_OK(cudaFree(ctx->topk_ws));
-        ctx->topk_ws = nullptr;
-        ctx->topk_ws_bytes = 0;
-        HPB_CUDA_OK(cudaMalloc(&ctx->topk_ws, need));
-        ctx->topk_ws_bytes = need;
+    {
+        const int rc = hpb_topk_reserve(ctx, n, n_groups, stream);
+        if (rc != HPB_OK) return rc;
+        const int rc2 = hpb_stream_enter(ctx, stream);
+        if (rc2 != HPB_OK) return rc2;
     }
     unsigned long long *keys = (unsigned long long *)ctx->topk_ws;
     unsigned long long *bucketed = keys + n;
@@ -145,5 +143,11 @@ int hpb_launch_topk(hpb_ctx *ctx, const float *scores, const int32_t *groups, in
     topk_place_kernel<<<(int)((max_kept + tb - 1) / tb), tb, 0, stream>>>(kept, kept_offsets, n_groups, out_idx);
     HPB_CUDA_OK(cudaGetLastError());
     ctx->launches += 5;
+    hpb_stream_leave(ctx, stream);
     return HPB_OK;
+}
+
+int hpb_topk_reserve(hpb_ctx *ctx, int64_t n, int64_t n_groups, cudaStream_t stream) {
+    const size_t need = sizeof(unsigned long long) * 3 * (size_t)n + sizeof(int) * (4 * (size_t)n_groups + 2);
+    return hpb_ws_grow(ctx, &ctx->topk_ws, &ctx->topk_ws_bytes, need, stream, "top-K");
 }

@@ -117,6 +117,18 @@ def all_gather_collections(coll):
     return out.to(device) if len(out.tensors) else out
 
 
+def all_ranks_equal(values, device=None) -> bool:
+    """True when the list of floats `values` is identical on every rank (one MIN and one MAX all-reduce, one host read)."""
+    if not is_distributed():
+        return True
+    backend = dist.get_backend()
+    dev = torch.device(device) if (backend == "nccl" and device is not None) else torch.device("cpu")
+    v = torch.tensor([float(x) for x in values], dtype=torch.float64, device=dev)
+    both = torch.stack([v, -v])
+    dist.all_reduce(both, op=dist.ReduceOp.MAX)  # max(v) and -min(v)
+    return bool(torch.equal(both[0], -both[1]))
+
+
 def barrier() -> None:
     if is_distributed():
         dist.barrier()

@@ -132,8 +132,21 @@ class FoldedResNet:
                     c2.bias = (b2 + bd).to(dtype).contiguous()
                     down.bias = None
                 self.blocks.append((_Conv(blk.conv1, blk.bn1, dtype), c2, down))
-        self.fc_w = net.fc.weight.detach().to(dtype)
-        self.fc_b = net.fc.bias.detach().to(dtype)
+        # the 512-d feature (average pool + fc) is computed in float32: it feeds the pose / logit heads directly
+        self.fc_w = net.fc.weight.detach().float()
+        self.fc_b = net.fc.bias.detach().float()
+        # snapshot signature: a later load_state_dict / fine-tuning step / .train() invalidates the fold (PosePredictor
+        # checks `stale()` on every eager forward and re-folds)
+        self._tracked = list(net.parameters()) + list(net.buffers())
+        self._net = net
+        self._signature = self._current_signature()
+
+    def _current_signature(self):
+        return (self._net.training, self._tracked[0].device, sum(t._version for t in self._tracked))
+
+    def stale(self) -> bool:
+        """True when the wrapped module changed since the fold (in-place weight updates, .train(), device move)."""
+        return self._current_signature() != self._signature
 
     @property
     def in_channels(self) -> int:
@@ -169,10 +182,15 @@ class FoldedResNet:
         stem = (lambda t, f: self.stem_s2d.relu(t, f)) if packed_s2d else self._stem
         try:
             y = stem(x, fused)
-        except RuntimeError:
-            if not fused:
+        except torch.cuda.OutOfMemoryError:
+            raise
+        except RuntimeError as exc:
+            # only "this cuDNN build has no fused conv+bias+relu kernel for the dtype / shape" selects the plain
+            # conv + relu_ recipe; anything else (launch failures, bad shapes) is a genuine error
+            msg = str(exc).lower()
+            if not fused or not any(t in msg for t in ("cudnn", "unsupported", "not supported", "no kernel", "unable to find")):
                 raise
-            self.fused = fused = False  # this cuDNN build has no fused kernel for the dtype: plain conv + relu_
+            self.fused = fused = False
             y = stem(x, fused)
         x = y
         if self.fast_pool and x.is_contiguous(memory_format=torch.channels_last) and x.shape[1] % 8 == 0:
@@ -184,7 +202,7 @@ class FoldedResNet:
         for c1, c2, down in self.blocks:
             identity = x if down is None else down.plain(x)
             x = c2.add_relu(c1.relu(x, fused), identity, fused)
-        x = x.mean(dim=(2, 3))
+        x = x.mean(dim=(2, 3), dtype=torch.float32)  # float32 accumulate and result: no bf16 rounding of the feature
         return F.linear(x, self.fc_w, self.fc_b)
 
 

@@ -46,7 +46,7 @@ class PoseEstimator(torch.nn.Module):
         bsz_objects: int = 8,
         bsz_images: int = 256,
         SO3_grid_size: int = 576,
-        shard_across_ranks: bool = True,
+        shard_across_ranks: bool = False,
         use_cuda_graphs: bool = False,
     ) -> None:
         super().__init__()
@@ -56,7 +56,12 @@ class PoseEstimator(torch.nn.Module):
         self.depth_refiner = depth_refiner
         self.bsz_objects = bsz_objects
         self.bsz_images = bsz_images
+        # Opt-in (the reference's distributed use is the opposite: every rank gets DIFFERENT scenes and the results are
+        # gathered afterwards, evaluation/prediction_runner.py:65-67).  With shard_across_ranks=True every rank must call
+        # the pipeline with the SAME observation and detections; the rows of the hypothesis table are then split across
+        # the ranks.  The first call for every input shape verifies that the ranks agree (see _check_sharded_inputs).
         self.shard_across_ranks = shard_across_ranks
+        self._sharding_checked: set = set()
         if SO3_grid_size is not None:
             self.load_SO3_grid(SO3_grid_size)
         if self.refiner_model is not None:
@@ -115,6 +120,27 @@ class PoseEstimator(torch.nn.Module):
     def _my_rows(n: int, shard: bool) -> Tuple[int, int]:
         return hdist.shard_range(n) if (shard and hdist.is_distributed()) else (0, n)
 
+    def _check_sharded_inputs(self, observation: ObservationTensor, detections) -> None:
+        """Row sharding assumes identical inputs on every rank; mismatched inputs would otherwise hang or silently mix
+        scenes.  Checked (one all-reduce + host read) the first time a given input shape is seen."""
+        if not (self.shard_across_ranks and hdist.is_distributed()):
+            return
+        key = (len(detections), tuple(observation.images.shape))
+        if key in self._sharding_checked:
+            return
+        import zlib
+
+        labels = "|".join(str(x) for x in detections.infos["label"].tolist())
+        ims = ",".join(str(int(x)) for x in detections.infos["batch_im_id"].tolist())
+        sig = [float(len(detections)), float(zlib.crc32((labels + "#" + ims).encode()) % (1 << 24)),
+               float(detections.bboxes.double().sum().item()), float(observation.K.double().sum().item()),
+               float(observation.images[..., ::16, ::16].double().sum().item())]
+        if not hdist.all_ranks_equal(sig, observation.images.device):
+            raise ValueError("PoseEstimator(shard_across_ranks=True) needs the same observation and detections on every rank "
+                             "(rows of one hypothesis table are split across the ranks); for one-scene-per-rank evaluation "
+                             "construct the estimator with shard_across_ranks=False")
+        self._sharding_checked.add(key)
+
     # ------------------------------------------------------------------------------------------
     @torch.no_grad()
     def forward_refiner(
@@ -143,12 +169,17 @@ class PoseEstimator(torch.nn.Module):
         chunks = {n: {k: [] for k in keys} for n in range(1, n_iterations + 1)}
         all_outputs = []
         model_time = 0.0
+        # refiner_batch_idx / refiner_instance_idx of ALL rows (every rank's shard), so `infos` is the same on every rank
         batch_idx_col = np.zeros(B, np.int64)
         inst_idx_col = np.zeros(B, np.int64)
+        sharded = self.shard_across_ranks and hdist.is_distributed()
+        for r in range(hdist.get_world_size() if sharded else 1):
+            lo_r, hi_r = hdist.shard_range(B, r, hdist.get_world_size()) if sharded else (0, B)
+            rel = np.arange(hi_r - lo_r)
+            batch_idx_col[lo_r:hi_r] = rel // self.bsz_objects
+            inst_idx_col[lo_r:hi_r] = rel % self.bsz_objects
         for batch_idx, s in enumerate(range(lo, hi, self.bsz_objects)):
             e = min(s + self.bsz_objects, hi)
-            batch_idx_col[s:e] = batch_idx
-            inst_idx_col[s:e] = np.arange(e - s)
             timer_ = CudaTimer(enabled=cuda_timer) if torch.cuda.is_available() else SimpleTimer()
             timer_.start()
             outputs_ = model.forward_ids(
@@ -385,6 +416,7 @@ class PoseEstimator(torch.nn.Module):
             if labels_to_keep is not None:
                 detections = filter_detections(detections, labels_to_keep)
             assert len(detections) > 0, "TOFIX: currently, dealing with absence of detections is not supported"
+            self._check_sharded_inputs(observation, detections)
             # detections = add_instance_id(detections) (pose_estimator.py:578) happens inside, behind the coarse enqueue
             data_TCO_coarse, coarse_extra_data = self.forward_coarse_model(
                 observation=observation, detections=detections, cuda_timer=cuda_timer, _instance_ids_after_enqueue=True)

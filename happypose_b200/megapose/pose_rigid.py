@@ -150,7 +150,7 @@ class PosePredictor(nn.Module):
         # replay launch-bound batches as CUDA graphs (utils/cuda_graphs.py); off by default, PoseEstimator turns it on
         self.use_cuda_graphs = False
         self.graph_max_batch = 64
-        self._graphs = GraphCache()
+        self._graphs = GraphCache(lambda: self.renderer._ctx.workspace_epoch())
 
     # ---- properties of the reference -----------------------------------------------------------
     @property
@@ -203,6 +203,11 @@ class PosePredictor(nn.Module):
         if K.shape[0] == bsz and im_ids is None:
             return K
         return K[torch.as_tensor(im_ids).to(K.device).long()]
+
+    def _graph_flags(self) -> Tuple:
+        """Model switches that change what a captured graph contains (part of the graph key)."""
+        return (self.crop_tap_bits, str(self.compute_dtype), bool(self.use_direct_s2d), self.multiview_type,
+                bool(self.views_inplane_rotations), bool(self.remove_TCO_rendering))
 
     def _direct_s2d_ok(self, images: torch.Tensor, return_debug_data: bool, cuda_timer: bool) -> bool:
         """The coarse / scoring forward may skip the float32 network input when nobody asks for it (debug data) and the
@@ -259,32 +264,44 @@ class PosePredictor(nn.Module):
     def _prepare_net(self, x: torch.Tensor) -> None:
         """Once, on first use: choose how the (unchanged) torch network is executed.  On CUDA with a reduced-precision
         compute dtype a torchvision-style ResNet is run through fast_resnet.FoldedResNet (batch-norm folded, fused
-        cuDNN conv+bias+ReLU epilogues, channels_last); anything else runs the module as is."""
+        cuDNN conv+bias+ReLU epilogues, channels_last); anything else runs the module as is (under autocast for a
+        reduced-precision compute dtype -- the user's module is never cast in place).  The Linear heads always stay
+        float32: the pose update multiplies depth by vz ~ 1.0, where bf16 spacing is 2^-8, and coarse logits near 13
+        would tie at 0.0625 steps."""
         if self._net_ready:
-            return
+            if self._folded is None or not self._folded.stale():
+                return
+            self._graphs.clear()  # graphs captured with the old weight snapshot
         self._folded = None
         if x.is_cuda and self.compute_dtype != torch.float32:
             self._folded = fast_resnet.try_fold(self.backbone, self.compute_dtype, self._ctx())
-            if self._folded is None:
-                self.backbone.to(dtype=self.compute_dtype, memory_format=torch.channels_last)
-            for head in self.heads.values():
-                head.to(dtype=self.compute_dtype)
         self._net_ready = True
 
+    def refold(self) -> None:
+        """Re-snapshot the backbone (after load_state_dict / fine-tuning); also drops captured CUDA graphs."""
+        self._net_ready = False
+        self._folded = None
+        self._graphs.clear()
+
+    def _heads_forward(self, feat: torch.Tensor) -> Dict[str, torch.Tensor]:
+        feat = feat.float()
+        return {k: head(feat) for k, head in self.heads.items()}
+
     def net_forward(self, x: torch.Tensor) -> Dict[str, torch.Tensor]:
-        """pose_rigid.py:352-374.  The torch backbone runs in bf16/channels_last; head outputs come back float32."""
+        """pose_rigid.py:352-374.  The torch backbone runs in bf16/channels_last; features and heads are float32."""
         self._prepare_net(x)
         if self._folded is not None:
             x = self._folded(x)  # packs the fp32 planar input to bf16 NHWC itself (space-to-depth for the 7x7 stem)
+        elif x.is_cuda and self.compute_dtype != torch.float32:
+            with torch.autocast("cuda", dtype=self.compute_dtype):
+                x = self.backbone(x.contiguous(memory_format=torch.channels_last))
         else:
-            if x.is_cuda and self.compute_dtype != torch.float32:
-                x = x.to(dtype=self.compute_dtype, memory_format=torch.channels_last)
             x = self.backbone(x)
         if x.dim() == 4:
-            x = x.flatten(2).mean(dim=-1)
+            x = x.float().flatten(2).mean(dim=-1)
         elif x.dim() != 2:
             raise ValueError
-        return {k: head(x).float() for k, head in self.heads.items()}
+        return self._heads_forward(x)
 
     # ---- rendering -----------------------------------------------------------------------------
     def render_images_multiview(self, labels, TCV_O, KV, random_ambient_light: bool = False, out=None, mesh_ids=None,
@@ -385,7 +402,7 @@ class PosePredictor(nn.Module):
             def fn(images_, K_, obj_ids_, mesh_ids_, im_ids_, TCO_):
                 return self._forward_ids_impl(images_, K_, obj_ids_, mesh_ids_, im_ids_, TCO_, n_iterations, False, None)
 
-            outputs, replayed = self._graphs.run(("refiner", n_iterations), fn, tensors)
+            outputs, replayed = self._graphs.run(("refiner", n_iterations) + self._graph_flags(), fn, tensors)
             if replayed:  # static graph buffers: hand out copies of the small tensors, views of the big ones
                 outputs = {k: self._detach_output(o, labels) for k, o in outputs.items()}
             return outputs
@@ -501,7 +518,7 @@ class PosePredictor(nn.Module):
                 o = self._forward_coarse_ids_impl(images_, K_, obj_ids_, mesh_ids_, im_ids_, TCO_, False, False)
                 return o["logits"], o["scores"]
 
-            (logits, scores), replayed = self._graphs.run("coarse", fn, tensors)
+            (logits, scores), replayed = self._graphs.run(("coarse",) + self._graph_flags(), fn, tensors)
             if replayed:
                 logits, scores = logits.clone(), scores.clone()
             return {"logits": logits, "scores": scores, "time": 0.0, "render_time": 0.0, "model_time": 0.0}
@@ -527,7 +544,7 @@ class PosePredictor(nn.Module):
             render_time = time.time() - render_start
             start = time.time()
             feat = self._folded(z, packed_s2d=True)
-            logits = self.heads["renderings_logits"](feat).float()
+            logits = self._heads_forward(feat)["renderings_logits"]
             out = {"logits": logits, "scores": torch.sigmoid(logits), "time": time.time() - start}
             out["render_time"] = render_time
             out["model_time"] = out["time"]

@@ -7,7 +7,6 @@ caller (the reference returns fresh tensors too, panda3d_batch_renderer.py:245-2
 from __future__ import annotations
 
 import ctypes
-import threading
 from typing import Optional, Sequence, Tuple
 
 import numpy as np
@@ -55,7 +54,6 @@ class KernelTimer:
 
 
 _kernel_timer: Optional[KernelTimer] = None
-_crop_lock = threading.Lock()
 
 
 def set_kernel_timer(timer: Optional[KernelTimer]) -> None:
@@ -263,12 +261,10 @@ def crop(
     if _kernel_timer is not None:
         ev = _kernel_timer.bracket("hpb_crop", b * C * h * w * 4)
         ev[0].record()
-    with _crop_lock:  # the tap precision is a context-level switch: keep "set, then launch" atomic across host threads
-        ctx.check(ctx.lib.hpb_set_crop_tap_precision(ctx.handle, 16 if (tap_bits == 16 and C == 3) else 32), "hpb_set_crop_tap_precision")
-        rc = ctx.lib.hpb_crop(
-            ctx.handle, ptr(images), n_im, C, H, W, ptr(im_ids), ptr(points), points.shape[0], points.shape[1], ptr(obj_ids),
-            ptr(K), ptr(TCO), ptr(tCR), b, h, w, lamb, ptr(crops), bs, ptr(K_crop), ptr(boxes_rend), ptr(boxes_crop),
-            stream_ptr(dev))
+    rc = ctx.lib.hpb_crop(
+        ctx.handle, ptr(images), n_im, C, H, W, ptr(im_ids), ptr(points), points.shape[0], points.shape[1], ptr(obj_ids),
+        ptr(K), ptr(TCO), ptr(tCR), b, h, w, lamb, ptr(crops), bs, ptr(K_crop), ptr(boxes_rend), ptr(boxes_crop),
+        16 if (tap_bits == 16 and C == 3) else 32, stream_ptr(dev))  # tap precision travels with the launch
     if ev is not None:
         ev[1].record()
     ctx.check(rc, "hpb_crop")

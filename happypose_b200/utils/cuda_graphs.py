@@ -17,7 +17,12 @@ import torch
 
 
 class GraphCache:
-    def __init__(self) -> None:
+    def __init__(self, epoch_fn: Callable[[], int] = None) -> None:
+        # epoch_fn: the library context's workspace epoch.  libhpb200 never frees or moves a workspace (replaced buffers
+        # are retired), so graphs captured before a growth stay valid; they are dropped anyway when the epoch moves so
+        # that replays use the current buffers and the retired ones stop being touched.
+        self._epoch_fn = epoch_fn
+        self._epoch = None
         self._entries: Dict[Hashable, Tuple[torch.cuda.CUDAGraph, Tuple[torch.Tensor, ...], Any]] = {}
         self._failed: set = set()
         self.replays = 0
@@ -32,6 +37,11 @@ class GraphCache:
         """-> (outputs, replayed).  `fn(*tensors)` must be a pure function of its tensor arguments that launches only on
         the current stream and never synchronises the host.  When capture is impossible the function runs eagerly."""
         full_key = (key, self.signature(tensors))
+        if self._epoch_fn is not None:
+            epoch = self._epoch_fn()
+            if self._epoch is not None and epoch != self._epoch:
+                self._entries.clear()
+            self._epoch = epoch
         if full_key in self._failed:
             return fn(*tensors), False
         entry = self._entries.get(full_key)
@@ -60,6 +70,8 @@ class GraphCache:
             entry = (graph, static, out)
             self._entries[full_key] = entry
             self.captures += 1
+            if self._epoch_fn is not None:
+                self._epoch = self._epoch_fn()  # the warm-up itself may have grown a workspace
         graph, static, out = entry
         for s, t in zip(static, tensors):
             if s.data_ptr() != t.data_ptr():

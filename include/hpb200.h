@@ -88,6 +88,22 @@ int hpb_destroy(hpb_ctx *ctx);
 int64_t hpb_launch_count(const hpb_ctx *ctx);
 
 /*
+ * Workspaces (rasteriser visibility buffer / vertex scratch, the crop's interleaved frame copy, top-K scratch, the
+ * device mesh table) are grown on demand by the launch calls and are NEVER freed or moved while the context lives: a
+ * buffer that has to grow is replaced and the old one retired until hpb_destroy, so kernel parameters baked into a
+ * captured CUDA graph stay valid.  hpb_workspace_epoch() counts such replacements (a caller may re-capture its graphs
+ * when it changes).  Growth cannot happen while `stream` is being captured (allocation is illegal there; the launch
+ * returns HPB_EINVAL): either run the call once eagerly first, or size everything up front with hpb_reserve():
+ *   render_h, render_w  largest render resolution               (0 = skip)
+ *   frame_pixels        n_im * H * W of the largest crop source (0 = skip)
+ *   topk_rows/groups    largest hpb_topk_segmented input        (0 = skip)
+ * The shared scratch is used by one stream at a time: when consecutive launches come from different (non-capturing)
+ * streams the library orders them with an event, so two streams never race on it.
+ */
+int64_t hpb_workspace_epoch(const hpb_ctx *ctx);
+int hpb_reserve(hpb_ctx *ctx, int render_h, int render_w, int64_t frame_pixels, int64_t topk_rows, int64_t topk_groups);
+
+/*
  * Upload one mesh (HOST pointers; synchronous, not on the hot path).
  *   verts_xyz  [n_verts,3] vertex positions already in METRES and with any ypr offset applied
  *   normals    [n_verts,3] unit normals, or NULL (area-weighted smooth normals are generated)
@@ -144,12 +160,14 @@ int hpb_render(hpb_ctx *ctx, const int32_t *mesh_ids_dev, const float *TCO_dev, 
  *   K_dev [b,9], TCO_dev [b,16], tCR_dev [b,3]
  *   outputs: crops_dev [b,C,h,w] (batch stride crops_bstride elements), K_crop_dev [b,9],
  *            boxes_rend_dev [b,4], boxes_crop_dev [b,4]  (x1,y1,x2,y2)
+ *   tap_bits  32 / 16 = precision of the frame samples for THIS launch (see hpb_set_crop_tap_precision), 0 = the
+ *             context default.  A launch argument, so concurrent callers with different precisions cannot race.
  */
 int hpb_crop(hpb_ctx *ctx, const float *images_dev, int n_im, int C, int H, int W, const int32_t *im_ids_dev,
              const float *points_dev, int n_obj, int n_pts, const int32_t *obj_ids_dev, const float *K_dev,
              const float *TCO_dev, const float *tCR_dev, int b, int h, int w, float lamb, float *crops_dev,
              int64_t crops_bstride, float *K_crop_dev, float *boxes_rend_dev, float *boxes_crop_dev,
-             void *stream);
+             int tap_bits, void *stream);
 
 /*
  * Precision of the frame samples ("taps") hpb_crop reads when it resamples from its pixel-interleaved copy of an RGB
@@ -157,7 +175,8 @@ int hpb_crop(hpb_ctx *ctx, const float *images_dev, int n_im, int C, int H, int 
  * roi_align on float32 images).  16: the copy holds IEEE fp16 -- 8-byte instead of 16-byte taps, which halves the L1
  * sector look-ups that bound the kernel; the crop of a frame f then equals the 32-bit crop of fp16(f) bit for bit, i.e.
  * an absolute error <= 2.5e-4 for pixel values in [0,1] (BASELINE bar for crops: 1e-3).  Meant for the bf16 network
- * path, whose input is rounded to 8 mantissa bits anyway.  RGB-D frames always use 32.  Host-side switch, no sync.
+ * path, whose input is rounded to 8 mantissa bits anyway.  RGB-D frames always use 32.  This sets the context DEFAULT
+ * used by launches that pass tap_bits = 0.  Host-side switch, no sync.
  */
 int hpb_set_crop_tap_precision(hpb_ctx *ctx, int bits);
 

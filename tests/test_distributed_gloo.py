@@ -53,6 +53,9 @@ def _worker(rank, world, port, out_dir):
     assert list(got.keys()) == list(full.keys())
     for k in full:
         assert got[k].shape == full[k].shape and torch.equal(got[k], full[k]), k
+    # input agreement check used by PoseEstimator(shard_across_ranks=True)
+    assert hdist.all_ranks_equal([3.0, 1.5, -2.0])
+    assert not hdist.all_ranks_equal([3.0, float(rank)])
     # collections: file-free gather_distributed
     coll = PandasTensorCollection(pd.DataFrame({"rank": [rank] * (rank + 1)}), poses=torch.full((rank + 1, 4, 4), float(rank)))
     allc = coll.gather_distributed()

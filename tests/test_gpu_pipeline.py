@@ -18,6 +18,7 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 MESH = os.path.join(GOLDEN, "obj_000001.npz")
 K_BBQ = np.array([[605.95, 0, 319.03], [0, 605.01, 249.68], [0, 0, 1]], np.float32)  # docs/book/megapose/inference.md:33
 BBOX_BBQ = np.array([384, 234, 522, 455], np.float32)                               # docs/book/megapose/inference.md:37
+PIPELINE_FRAME_SEED = 46  # scripts/find_pipeline_seed.py 2 2 3 8 ...: margins m_topk .042, m_order .047, m_final .22
 
 
 @pytest.fixture(autouse=True)
@@ -175,6 +176,25 @@ def test_refiner_forward_matches_oracle(models, scene):
     assert o.timing_dict is not None and o.tCR.shape == (n, 3) and o.renderings_logits.shape == (n, 4)
 
 
+def pipeline_margins(ref, n_pose_hypotheses):
+    """Decision margins of an oracle pipeline run (scripts/find_pipeline_seed.py): m_topk = gap between the K-th and
+    (K+1)-th coarse logit of every group, m_order = smallest gap between consecutive kept logits, m_final = gap between
+    the two best pose logits of a group."""
+    logits = ref["coarse_logits"]
+    K = n_pose_hypotheses
+    srt = -np.sort(-logits, axis=1)
+    m_topk = float((srt[:, K - 1] - srt[:, K]).min()) if logits.shape[1] > K else np.inf
+    kept = np.sort(logits.reshape(-1)[ref["keep"]])[::-1]
+    m_order = float(np.min(-np.diff(kept))) if len(kept) > 1 else np.inf
+    m_final = np.inf
+    groups = np.repeat(np.arange(logits.shape[0]), logits.shape[1])[ref["keep"]]
+    for g in np.unique(groups):
+        pl = np.sort(ref["pose_logits"][groups == g])[::-1]
+        if len(pl) > 1:
+            m_final = min(m_final, float(pl[0] - pl[1]))
+    return {"m_topk": m_topk, "m_order": m_order, "m_final": m_final}
+
+
 def _detections(n_det, device="cuda"):
     from happypose_b200.utils.tensor_collection import PandasTensorCollection
 
@@ -196,7 +216,7 @@ def test_run_inference_pipeline_matches_oracle(models, scene):
     est = PoseEstimator(refiner_model=refiner, coarse_model=coarse, bsz_objects=8, bsz_images=32, SO3_grid_size=576)
     est._SO3_grid = est._SO3_grid[::8]
     assert est._SO3_grid.shape == (72, 3, 3)
-    rs = np.random.RandomState(23)
+    rs = np.random.RandomState(PIPELINE_FRAME_SEED)
     image = rs.rand(1, 3, 480, 640).astype(np.float32)
     det, boxes, det_obj = _detections(2)
     obs = ObservationTensor(torch.as_tensor(image), torch.as_tensor(K_BBQ[None])).cuda()
@@ -215,22 +235,24 @@ def test_run_inference_pipeline_matches_oracle(models, scene):
     assert list(coarse_df["hypothesis_id"][:3]) == [0, 1, 2] and len(coarse_df) == 144 and "coarse_logit" in coarse_df and "instance_id" in coarse_df
     np.testing.assert_allclose(cd["logits"].cpu().numpy(), ref["coarse_logits"], rtol=1e-3, atol=5e-3)
     np.testing.assert_allclose(extra["coarse"]["preds"].poses.cpu().numpy(), ref["TCO_init"], atol=1e-5)
-    # top-K: same rows in the same (global descending) order, provided the oracle's own margins are not razor thin
+    # top-K: same rows in the same (global descending) order, same final pose.  UNCONDITIONAL: the frame was chosen
+    # (scripts/find_pipeline_seed.py) so that every decision of the oracle run -- K-th vs (K+1)-th coarse logit of a group,
+    # order of the kept rows, best vs second-best pose logit -- has a margin far above the GPU-vs-CPU fp32 logit noise
+    # (5e-3, asserted above); the margins are re-computed from the oracle here and asserted.
+    margins = pipeline_margins(ref, 2)
+    assert min(margins.values()) > 3e-2, f"frame seed {PIPELINE_FRAME_SEED} lost its decision margins: {margins}"
     kept = extra["coarse_filter"]["preds"].infos
-    ref_logits = ref["coarse_logits"].reshape(-1)
-    order = np.sort(ref_logits)[::-1]
-    if np.min(np.abs(np.diff(order[:6]))) > 2e-2:
-        assert (kept["hypothesis_id"].to_numpy() + 72 * kept["bbox_id"].to_numpy() == ref["keep"]).all()
-        pts = scene.points[0]
-        refined = extra["refiner_all_hypotheses"]["preds"]["iteration=3"].poses.cpu().numpy()
-        for k in range(len(refined)):
-            assert P.add_error(pts, refined[k], ref["refined"][k]) < 1e-3
-        assert len(final) == 2
-        fin = final.infos
-        for row in range(2):
-            g = int(fin["bbox_id"].iloc[row])
-            j = int(np.where(ref["final_groups"] == g)[0][0])
-            assert P.add_error(pts, final.poses[row].cpu().numpy(), ref["final_poses"][j]) < 1e-3
+    assert (kept["hypothesis_id"].to_numpy() + 72 * kept["bbox_id"].to_numpy() == ref["keep"]).all()
+    pts = scene.points[0]
+    refined = extra["refiner_all_hypotheses"]["preds"]["iteration=3"].poses.cpu().numpy()
+    for k in range(len(refined)):
+        assert P.add_error(pts, refined[k], ref["refined"][k]) < 1e-3
+    assert len(final) == 2
+    fin = final.infos
+    for row in range(2):
+        g = int(fin["bbox_id"].iloc[row])
+        j = int(np.where(ref["final_groups"] == g)[0][0])
+        assert P.add_error(pts, final.poses[row].cpu().numpy(), ref["final_poses"][j]) < 1e-3
     assert set(["pose_logit", "pose_score", "refiner_batch_idx", "refiner_instance_idx"]).issubset(final.infos.columns)
     assert final.poses.shape == (2, 4, 4) and final.poses.is_cuda
 
