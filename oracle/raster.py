@@ -3,7 +3,8 @@
 Never imported by happypose_b200/.  Callers: tests/, __graft_entry__.smoke(), bench.py
 (cpu_baseline / --impl reference).  See raster_oracle.c for the restated reference semantics
 (toolbox/renderer/panda3d_scene_renderer.py:55-102,320-390, renderer/types.py:91-137,254-299,
-renderer/utils.py:46-79) and the "parity unpinned" statement.
+renderer/utils.py:46-79) and for what is / is not pinned against real Panda3D pixels (oracle/figure_pin.py,
+tests/test_oracle_figure_pin.py).
 """
 from __future__ import annotations
 

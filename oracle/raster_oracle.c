@@ -4,9 +4,17 @@
  * file; only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg
  * use it, as the checker / host-core baseline.
  *
- * PARITY UNPINNED: Panda3D 1.10.13 + OpenGL cannot be installed here, and the reference's own
- * tests (tests/test_batch_renderer_panda3d.py:71-242) assert only shapes, dtypes and a few pixel
- * signs, which tests/test_oracle_raster.py re-asserts on this oracle.  The semantics restated:
+ * PARITY: Panda3D 1.10.13 + OpenGL cannot be installed here, so the renderer itself never runs next to this
+ * oracle.  It is pinned to the only real Panda3D pixels the reference ships, the golden figures
+ * tests/data/panda3d_obj_{batch,scene}_render.png (written by tests/test_batch_renderer_panda3d.py:148-163):
+ * tests/test_oracle_figure_pin.py renders the same scene with this oracle, resamples it the way matplotlib
+ * built the figure (oracle/figure_pin.py) and compares: silhouette IoU 0.9995 / centroid within 0.01 px /
+ * identical extents, depth panel within 1 grey level (corr 0.98), normal channels R,G corr 0.96 and B corr
+ * +0.77 (the opposite B sign convention gives -0.77), rgb channel means within 1 level (corr 0.9).  That
+ * pins projection, flip, depth read-back, normal colour convention and texture orientation at FIGURE
+ * resolution (one figure pixel ~ 8 image pixels); per-pixel texture filtering, MSAA and near-plane clipping
+ * remain unpinned (below).  The reference's structural test assertions (:71-242) are re-asserted on this
+ * oracle in tests/test_oracle_raster.py.  The semantics restated:
  *
  *   projection / pixel centres  toolbox/renderer/types.py:111-137 (set_lens_parameters) and
  *                               :254-293 (flipud read-back): pixel (i,j) samples the ray through
