@@ -58,6 +58,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graphs", action="store_true")
     ap.add_argument("--no-clocks", action="store_true", help="do not poll nvidia-smi during the timed regions (debugging)")
+    ap.add_argument("--clock-sampler", default="smi", choices=["nvml", "smi"],
+                    help="nvml: in-process NVML polling thread; smi: the recipe's `nvidia-smi -lms` child started before the warm-up")
     ap.add_argument("--profile-range", action="store_true",
                     help="bracket the kernel-timed region with cudaProfilerStart/Stop (ncu --profile-from-start off)")
     return ap.parse_args()
@@ -87,21 +89,31 @@ def detections_arrays(n_det):
 # clocks (B200_PROFILING.md): sampled during the timed region
 # ----------------------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """SM clock / throttle-reason samples taken DURING the timed regions.  In-process NVML thread (nvidia_ml_py): a
-    poll is a few microseconds of driver query, unlike spawning `nvidia-smi -lms`, whose start-up inside a timed
-    region stalls kernel launches for milliseconds (measured: e2e 22.9 ms/step with it vs 15.4 ms without).
-    Falls back to the nvidia-smi poller (the recipe's clocks line) when NVML cannot be loaded."""
+    """SM clock / throttle-reason samples taken DURING the timed regions.
 
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+    mode "smi" (default): the profiling recipe's `nvidia-smi --query-gpu=... -lms` child process, started BEFORE the
+    warm-up (its start-up stalls kernel launches for milliseconds, so it must not begin inside a timed region) and left
+    running; its time-stamped lines are filtered to the timed regions afterwards.  The sampling happens in another
+    process, so it does not touch this process's host thread.
+    mode "nvml": an in-process NVML polling thread (nvidia_ml_py).  Round 1 used it; at N >= 2 it cost the end-to-end
+    region 3.4 ms per step (15.6 vs 12.2 ms/step, profiles/r2_e2e_n2_clock_sampler.txt): rank 0's host thread competes
+    with the poller while every step ends in a host synchronisation and every collective waits for the slowest rank.
+    That, not the pipeline, was the N >= 2 e2e efficiency of 0.77 in SCALE_r01.json.  Kept for debugging only."""
+
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index, period_s=0.02):
+    def __init__(self, index, period_s=0.02, mode="nvml"):
         self.samples = []  # (sm MHz, power W, reasons bitmask)
         self.sm_max = None
         self.proc = None
         self.thread = None
         self._stop = threading.Event()
         self._armed = threading.Event()
+        self.windows = []  # [t0, t1] wall-clock intervals of the timed regions (smi mode keeps samples inside them)
+        if mode == "smi":
+            self._start_smi(index)
+            return
         try:
             import pynvml as N
 
@@ -142,7 +154,7 @@ class ClockSampler:
         self.path = f"/tmp/hpb_clocks_{os.getpid()}.csv"
         try:
             self.f = open(self.path, "w")
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(index)],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50", "-i", str(index)],
                                          stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -150,6 +162,10 @@ class ClockSampler:
     def arm(self, on=True):
         """Samples are kept only while armed (= while a timed region is running)."""
         (self._armed.set if on else self._armed.clear)()
+        if on:
+            self.windows.append([time.time(), None])
+        elif self.windows and self.windows[-1][1] is None:
+            self.windows[-1][1] = time.time()
 
     def stop(self):
         if self.thread is not None:
@@ -176,15 +192,20 @@ class ClockSampler:
         self.f.close()
         sm, mx, reasons, power = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        import datetime
+
         for line in open(self.path):
             p = [x.strip() for x in line.split(",")]
-            if len(p) < 7:
+            if len(p) < 8:
                 continue
             try:
-                sm.append(float(p[0])); mx.append(float(p[1])); power.append(float(p[2]))
+                ts = datetime.datetime.strptime(p[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                if self.windows and not any(w0 - 0.05 <= ts <= (w1 or ts) + 0.05 for w0, w1 in self.windows):
+                    continue  # outside the timed regions
+                sm.append(float(p[1])); mx.append(float(p[2])); power.append(float(p[3]))
             except ValueError:
                 continue
-            for nme, v in zip(names, p[3:7]):
+            for nme, v in zip(names, p[4:8]):
                 if v.lower().startswith("active"):
                     reasons.add(nme)
         try:
@@ -403,7 +424,7 @@ def run_ours(args):
 
     # the clock sampler starts BEFORE the warm-up (its start-up cost stays outside every timed region) and keeps samples
     # only while a timed region is running
-    sampler = ClockSampler(local_rank) if (rank == 0 and not args.no_clocks) else None
+    sampler = ClockSampler(local_rank, mode=args.clock_sampler) if (rank == 0 and not args.no_clocks) else None
     for _ in range(max(args.warmup, 3)):
         step_resident()
 
@@ -457,12 +478,12 @@ def run_ours(args):
         _, K_crop, _, _ = ops.crop(ctx, obs_dev.images, obj0, pts, obj0, K_rows, TCO, TCO[:, :3, 3].contiguous(), (H_R, W_R), out=x)
         ops.render(ctx, mesh_ids, TCO, K_crop, (H_R, W_R), render_normals=True, out=x, out_channel_offset=3)
 
-    crops_buf = torch.empty((b, 3, H_R, W_R), device=dev)
+    z_buf = torch.zeros((b, 64, H_R // 2 + 3, W_R // 2 + 3), dtype=torch.bfloat16, device=dev, memory_format=torch.channels_last)
 
-    def render_crop_fused():  # what the pipeline's coarse stage does: crop planes, then the rasteriser writes the stem input
-        _, K_crop, _, _ = ops.crop(ctx, obs_dev.images, obj0, pts, obj0, K_rows, TCO, TCO[:, :3, 3].contiguous(), (H_R, W_R), out=crops_buf,
-                                   tap_bits=coarse.crop_tap_bits)
-        ops.render_s2d_bf16(ctx, mesh_ids, TCO, K_crop, crops_buf, 64)
+    def render_crop_fused():  # what the pipeline's coarse stage does: bf16 crop pixels, then the rasteriser writes the stem input
+        crops_h, K_crop, _, _ = ops.crop_bf16x4(ctx, obs_dev.images, obj0, pts, obj0, K_rows, TCO, TCO[:, :3, 3].contiguous(), (H_R, W_R),
+                                                tap_bits=coarse.crop_tap_bits)
+        ops.render_s2d_bf16(ctx, mesh_ids, TCO, K_crop, crops_h, 64, out=z_buf, pad_prezeroed=True)
 
     for _ in range(3):
         render_crop()
@@ -487,30 +508,34 @@ def run_ours(args):
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "hpb_raster_kernel", "achieved": rk["gbps"], "peak": peak, "unit": "GB/s",
-                     "frac": rk["gbps"] / peak, "peak_source": peak_src, "traffic": None,
-                     "launches_timed": rk["launches"], "avg_launch_ms": rk["ms_avg"], "algorithmic_bytes_per_launch": rk["bytes_avg"],
+        # roofline of the dominant kernel of this library, on SURVEY 8(d)'s ALGORITHMIC bytes: 1 843 200 B per rendered view
+        # (6 float32 planes of 240x320: the reference's layout of the result), whatever layout the launch actually wrote.
+        # The bytes the launches really move (bf16 stem-input cells + the crop read for the fused 576-scene launch) are the
+        # secondary `moved_*` keys.
+        "roofline": {"bound": "hbm", "kernel": "hpb_raster_kernel", "achieved": rk.get("fp32_equivalent_gbps", 0.0), "peak": peak, "unit": "GB/s",
+                     "frac": rk.get("fp32_equivalent_gbps", 0.0) / peak, "peak_source": peak_src, "traffic": None,
+                     "algorithmic_bytes_per_view": 6 * H_R * W_R * 4,
+                     "launches_timed": rk["launches"], "avg_launch_ms": rk["ms_avg"],
+                     "moved_bytes_per_launch": rk["bytes_avg"], "moved_achieved": rk["gbps"], "moved_frac": rk["gbps"] / peak,
                      "share_of_step": rk["ms_total"] / ms_bracketed if ms_bracketed > 0 else None,
                      "bracketed_ms_per_step": ms_bracketed / args.steps,
-                     # the same figure for the largest launch class alone (the 576-scene coarse launch; the average above
+                     # the same figures for the largest launch class alone (the 576-scene coarse launch; the average above
                      # also contains the 4..16-scene refiner / scoring launches, which cannot fill 148 SMs)
-                     "largest_launch": ({"scenes_bytes": rk["largest"]["bytes"], "launches": rk["largest"]["launches"],
-                                         "avg_launch_ms": rk["largest"]["ms_avg"], "achieved": rk["largest"]["gbps"],
-                                         "frac": rk["largest"]["gbps"] / peak,
-                                         "fp32_equivalent_achieved": rk["largest"]["fp32_equivalent_gbps"]} if "largest" in rk else None),
-                     # the 576-scene coarse launch is the fused hand-off (hpb_render_s2d_bf16): its algorithmic bytes are
-                     # the bf16 stem-input cells it writes + the crop planes it reads (3 487 872 B / scene); the figure
-                     # in the reference's float32 layout (1 843 200 B / scene) is given alongside
-                     "fp32_equivalent_achieved": rk.get("fp32_equivalent_gbps")},
+                     "largest_launch": ({"launches": rk["largest"]["launches"], "avg_launch_ms": rk["largest"]["ms_avg"],
+                                         "achieved": rk["largest"]["fp32_equivalent_gbps"], "frac": rk["largest"]["fp32_equivalent_gbps"] / peak,
+                                         "moved_bytes": rk["largest"]["bytes"], "moved_achieved": rk["largest"]["gbps"],
+                                         "moved_frac": rk["largest"]["gbps"] / peak} if "largest" in rk else None)},
         "kernels": {k: {"gbps": v["gbps"], "frac": v["gbps"] / peak, "avg_launch_ms": v["ms_avg"], "launches": v["launches"],
                         "share_of_step": v["ms_total"] / ms_bracketed,
                         "largest_launch_gbps": v["largest"]["gbps"], "largest_launch_frac": v["largest"]["gbps"] / peak,
                         "largest_launch_ms": v["largest"]["ms_avg"]} for k, v in ksum.items()},
         "hyps": {"metric": "rendered_hyps_per_sec", "value": hyps_per_s, "unit": "hyps/s", "b": b, "ms_per_launch_pair": ms_hyp / hyp_iters,
-                 "path": "hpb_crop (fp16 frame taps) -> hpb_render_s2d_bf16 (the pipeline's coarse hand-off: bf16 space-to-depth stem input)",
-                 # bytes moved per hypothesis: crop planes written + read back, stem-input cells written
-                 "gbps": b * (2 * 3 * H_R * W_R * 4 + (H_R // 2 + 3) * (W_R // 2 + 3) * 64 * 2) / 1e9 / (ms_hyp / hyp_iters / 1e3),
-                 "frac": b * (2 * 3 * H_R * W_R * 4 + (H_R // 2 + 3) * (W_R // 2 + 3) * 64 * 2) / 1e9 / (ms_hyp / hyp_iters / 1e3) / peak,
+                 "path": "hpb_crop_bf16x4 (fp16 frame taps) -> hpb_render_s2d_bf16 (the pipeline's coarse hand-off: bf16 space-to-depth stem input, 96 B per cell)",
+                 # 2 764 800 algorithmic bytes per coarse hypothesis (the 9-channel float32 network input)
+                 "gbps": b * 9 * H_R * W_R * 4 / 1e9 / (ms_hyp / hyp_iters / 1e3),
+                 "frac": b * 9 * H_R * W_R * 4 / 1e9 / (ms_hyp / hyp_iters / 1e3) / peak,
+                 # bytes really moved per hypothesis: bf16 crop pixels written + read back, stem-input cells written
+                 "moved_gbps": b * (2 * H_R * W_R * 8 + (H_R // 2 + 3) * (W_R // 2 + 3) * 96) / 1e9 / (ms_hyp / hyp_iters / 1e3),
                  "planar_fp32": {"value": world * b * hyp_iters / (ms_hyp_planar / 1e3), "ms_per_launch_pair": ms_hyp_planar / hyp_iters,
                                  "gbps": b * 9 * H_R * W_R * 4 / 1e9 / (ms_hyp_planar / hyp_iters / 1e3),
                                  "frac": b * 9 * H_R * W_R * 4 / 1e9 / (ms_hyp_planar / hyp_iters / 1e3) / peak}},
@@ -521,7 +546,7 @@ def run_ours(args):
             tr = json.load(open(traffic_file))
             # dram bytes of ONE ncu --set full capture of the 576-scene launch, scaled to this run's average launch by
             # the measured traffic / algorithmic ratio (1.07: mesh + texture reads on top of the image writes)
-            line["roofline"]["traffic"] = tr["traffic_over_algorithmic"] * rk["bytes_avg"]
+            line["roofline"]["traffic"] = tr["traffic_over_algorithmic"] * rk["bytes_avg"]  # ratio measured against MOVED bytes
             line["roofline"]["traffic_capture"] = {"launch": tr.get("launch", "576 scenes"), "dram_bytes": tr["traffic_bytes_per_launch"],
                                                    "algorithmic_bytes": tr["algorithmic_bytes_of_that_launch"]}
         except Exception:

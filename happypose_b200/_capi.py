@@ -20,6 +20,7 @@ c_void_p, c_int, c_int32, c_int64, c_float, c_uint32 = (
 RENDER_RGB, RENDER_NORMALS, RENDER_DEPTH, RENDER_MASK = 1, 2, 4, 8
 POSE_MEGAPOSE, POSE_COSYPOSE_6D, POSE_COSYPOSE_QUAT = 0, 1, 2
 TCO_INIT_AUTODEPTH_WITH_R, TCO_INIT_ZUP_AUTODEPTH, TCO_INIT_FROM_BOXES = 0, 1, 2
+CROPS_F32_PLANAR, CROPS_BF16X4 = 0, 1
 DEPTH_NORM = {"none": 0, "tCR_scale": 1, "tCR_scale_clamp_center": 2, "tCR_center_clamp": 3}
 MV_TYPES = {"TCO+front_1view": 0, "TCO+front_3views": 1, "sphere_26views": 2}
 
@@ -53,7 +54,11 @@ SIGNATURES = {
     "hpb_normalize_depth": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "hpb_pack_input_bf16": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
     "hpb_pack_input_s2d_bf16": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
-    "hpb_render_s2d_bf16": (c_int, [c_void_p] * 5 + [c_int, c_int, c_int, c_float, c_float, c_void_p, c_int64, c_void_p, c_int, c_void_p]),
+    "hpb_render_s2d_bf16": (c_int, [c_void_p] * 5 + [c_int, c_int, c_int, c_float, c_float, c_void_p, c_int64, c_int, c_void_p, c_int,
+                                    c_int, c_void_p]),
+    "hpb_crop_bf16x4": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p,
+                                c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_int64, c_void_p,
+                                c_void_p, c_void_p, c_int, c_void_p]),
     "hpb_maxpool3x3s2_bf16_nhwc": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "hpb_topk_segmented": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
 }

@@ -14,7 +14,7 @@ int hpb_launch_crop_boxes(hpb_ctx *ctx, int H, int W, const float *points, int n
                           float *K_crop, float *boxes_rend, float *boxes_crop, cudaStream_t stream);
 int hpb_launch_crop_pixels(hpb_ctx *ctx, const float *images, int n_im, int C, int H, int W, const int32_t *im_ids,
                            const float *boxes, int b, int h, int w, float *crops, int64_t crops_bs, int tap_bits,
-                           cudaStream_t stream);
+                           cudaStream_t stream, void *crops_bf16x4 = nullptr);
 int hpb_launch_normalize_T(hpb_ctx *ctx, const float *T, int b, float *out, cudaStream_t stream);
 int hpb_launch_pose_update(hpb_ctx *ctx, const float *TCO, const float *K_crop, const float *outv, const float *tCR,
                            int b, int variant, float *TCO_out, cudaStream_t stream);
@@ -439,8 +439,8 @@ int hpb_render(hpb_ctx *ctx, const int32_t *mesh_ids_dev, const float *TCO_dev, 
 }
 
 int hpb_render_s2d_bf16(hpb_ctx *ctx, const int32_t *mesh_ids_dev, const float *TCO_dev, const float *K_dev,
-                        const float *ambient_dev, int b, int h, int w, float z_near, float z_far, const float *crops_dev,
-                        int64_t crops_bstride, void *out_dev, int C_padded, void *stream) {
+                        const float *ambient_dev, int b, int h, int w, float z_near, float z_far, const void *crops_dev,
+                        int64_t crops_bstride, int crops_format, void *out_dev, int C_padded, int pad_prezeroed, void *stream) {
     HPB_REQUIRE(ctx, "NULL ctx");
     HPB_REQUIRE(b >= 0 && h > 0 && w > 0 && (long long)h * w < (1ll << 30), "bad batch / resolution");
     HPB_REQUIRE(h % 2 == 0 && w % 2 == 0, "space-to-depth output needs even height and width");
@@ -448,13 +448,16 @@ int hpb_render_s2d_bf16(hpb_ctx *ctx, const int32_t *mesh_ids_dev, const float *
     if (b == 0) return HPB_OK;
     HPB_REQUIRE(mesh_ids_dev && TCO_dev && K_dev && crops_dev && out_dev, "NULL input");
     HPB_REQUIRE((reinterpret_cast<uintptr_t>(out_dev) & 15u) == 0, "out_dev must be 16-byte aligned");
-    HPB_REQUIRE(crops_bstride >= 3ll * h * w, "crops_bstride smaller than 3 planes");
+    HPB_REQUIRE(crops_format == HPB_CROPS_F32_PLANAR || crops_format == HPB_CROPS_BF16X4, "unknown crops_format");
+    HPB_REQUIRE(crops_bstride >= (crops_format == HPB_CROPS_F32_PLANAR ? 3ll : 1ll) * h * w, "crops_bstride smaller than one crop");
+    HPB_REQUIRE((reinterpret_cast<uintptr_t>(crops_dev) & (crops_format == HPB_CROPS_BF16X4 ? 7u : 3u)) == 0, "crops_dev misaligned");
+    HPB_REQUIRE(!pad_prezeroed || C_padded >= 48, "pad_prezeroed needs at least 48 padded channels");
     HPB_REQUIRE(z_near > 0.f && z_far > z_near, "bad near/far");
     HPB_REQUIRE(!ctx->meshes.empty(), "no mesh uploaded");
     HpbDeviceGuard guard(ctx->device);
     return hpb_launch_raster(ctx, mesh_ids_dev, TCO_dev, K_dev, ambient_dev, b, h, w, z_near, z_far,
                              HPB_RENDER_RGB | HPB_RENDER_NORMALS, nullptr, 0, nullptr, 0, nullptr, 0, nullptr, 0, 1, 0,
-                             (cudaStream_t)stream, crops_dev, crops_bstride, out_dev, C_padded);
+                             (cudaStream_t)stream, crops_dev, crops_bstride, out_dev, C_padded, crops_format, pad_prezeroed ? 1 : 0);
 }
 
 int hpb_crop_boxes(hpb_ctx *ctx, int H, int W, const float *points_dev, int n_obj, int n_pts,
@@ -489,6 +492,31 @@ int hpb_crop(hpb_ctx *ctx, const float *images_dev, int n_im, int C, int H, int 
         const int nb = b - s < 32768 ? b - s : 32768;
         rc = hpb_launch_crop_pixels(ctx, images_dev, n_im, C, H, W, im_ids_dev + s, boxes_crop_dev + (size_t)s * 4, nb,
                                     h, w, crops_dev + (size_t)s * crops_bstride, crops_bstride, tap_bits, (cudaStream_t)stream);
+        if (rc != HPB_OK) return rc;
+    }
+    return HPB_OK;
+}
+
+int hpb_crop_bf16x4(hpb_ctx *ctx, const float *images_dev, int n_im, int H, int W, const int32_t *im_ids_dev,
+                    const float *points_dev, int n_obj, int n_pts, const int32_t *obj_ids_dev, const float *K_dev,
+                    const float *TCO_dev, const float *tCR_dev, int b, int h, int w, float lamb, void *crops_dev,
+                    int64_t crops_bstride, float *K_crop_dev, float *boxes_rend_dev, float *boxes_crop_dev, int tap_bits,
+                    void *stream) {
+    HPB_REQUIRE(ctx, "NULL ctx");
+    HPB_REQUIRE(n_im > 0 && images_dev && im_ids_dev && crops_dev, "NULL image input/output");
+    HPB_REQUIRE((reinterpret_cast<uintptr_t>(crops_dev) & 7u) == 0, "crops_dev must be 8-byte aligned");
+    HPB_REQUIRE(crops_bstride >= (int64_t)h * w, "crops_bstride smaller than one crop");
+    HPB_REQUIRE(tap_bits == 0 || tap_bits == 16 || tap_bits == 32, "tap_bits must be 0 (context default), 16 or 32");
+    if (tap_bits == 0) tap_bits = ctx->crop_tap_bits;
+    int rc = hpb_crop_boxes(ctx, H, W, points_dev, n_obj, n_pts, obj_ids_dev, K_dev, TCO_dev, tCR_dev, b, h, w, lamb,
+                            K_crop_dev, boxes_rend_dev, boxes_crop_dev, stream);
+    if (rc != HPB_OK || b == 0) return rc;
+    HpbDeviceGuard guard(ctx->device);
+    for (int s = 0; s < b; s += 32768) {  // grid.y limit
+        const int nb = b - s < 32768 ? b - s : 32768;
+        rc = hpb_launch_crop_pixels(ctx, images_dev, n_im, 3, H, W, im_ids_dev + s, boxes_crop_dev + (size_t)s * 4, nb, h, w,
+                                    nullptr, crops_bstride, tap_bits, (cudaStream_t)stream,
+                                    reinterpret_cast<unsigned char *>(crops_dev) + (size_t)s * crops_bstride * 8);
         if (rc != HPB_OK) return rc;
     }
     return HPB_OK;

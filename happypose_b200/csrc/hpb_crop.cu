@@ -18,6 +18,7 @@
 //                           im_id: no per-hypothesis copy of the frame (the reference materialises images[batch_im_ids],
 //                           pose_estimator.py:390).  Stores are coalesced along x.  RGB-D frames also resample the
 //                           depth-validity map and zero depth where validity < 0.99 (cropping.py:181-195).
+#include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
 #include "hpb_common.cuh"
@@ -123,7 +124,16 @@ struct CropPixParams {
     int band;  // output rows per CTA
     const float4 *packed;  // [n_im,H,W] pixel-interleaved copy of `images` (r,g,b,depth|0) or nullptr
     const uint2 *packed_h;  // same in fp16 (r,g,b,0): 8-byte taps (hpb_set_crop_tap_precision(ctx, 16), RGB frames)
+    uint2 *crops_h;         // OUTFMT 1: [b][h][w] (r,g,b,0) bfloat16 pixels, batch stride crops_bs pixels (hpb_crop_bf16x4)
 };
+
+__device__ __forceinline__ uint2 pack_bf16x4(float r, float g, float b) {
+    const __nv_bfloat162 rg = __floats2bfloat162_rn(r, g);
+    uint2 v;
+    v.x = *reinterpret_cast<const unsigned *>(&rg);
+    v.y = (unsigned)__bfloat16_as_ushort(__float2bfloat16_rn(b));
+    return v;
+}
 
 // Planar [n_im,C,H,W] -> pixel-interleaved float4 [n_im,H,W]: the crop then fetches all channels of a tap with ONE
 // 16-byte load.  Done per hpb_crop call when few distinct frames serve many hypotheses (the usual case: 1 frame).
@@ -230,7 +240,8 @@ __device__ __forceinline__ bool axis_weights(float start, float bin, int i, int 
 // for every row.  The raw taps of the NEXT source row are prefetched one step ahead.  ncu (profiles/): the kernel is
 // bound by L1 bandwidth (4 overlapping 16-byte taps per thread per source row), not by issue slots or DRAM.
 // MODE 0: taps from the planar float32 frame; 1: from the pixel-interleaved float4 copy; 2: from the fp16 copy (C == 3)
-template <int C, int MODE>
+// OUTFMT 0: planar float32 crops; 1 (C == 3): pixel-interleaved bfloat16 (r,g,b,0), one 8-byte store per pixel
+template <int C, int MODE, int OUTFMT>
 __global__ void __launch_bounds__(CROP_MAX_THREADS, 3) hpb_crop_pixels_kernel(const CropPixParams p) {
     constexpr bool PACKED = MODE != 0;
     constexpr int NCH = C == 4 ? 5 : C;  // RGB-D: the depth-validity map is resampled as a 5th channel
@@ -349,6 +360,7 @@ __global__ void __launch_bounds__(CROP_MAX_THREADS, 3) hpb_crop_pixels_kernel(co
         float *optr[C];  // one output pointer per plane, bumped by one row per iteration
 #pragma unroll
         for (int c = 0; c < C; ++c) optr[c] = out + c * plane_out + (size_t)row0 * p.w + j0;
+        uint2 *optr_h = OUTFMT == 1 ? p.crops_h + (size_t)n * p.crops_bs + (size_t)row0 * p.w + j0 : nullptr;
         const int wout = p.w;
         for (int i = 0; i < rows; ++i) {
             const int by = sBY[i];  // uniform over the CTA
@@ -385,10 +397,15 @@ __global__ void __launch_bounds__(CROP_MAX_THREADS, 3) hpb_crop_pixels_kernel(co
                     acc[c] = fmaf(wq.w, hw[3][c], fmaf(wq.z, hw[2][c], fmaf(wq.y, hw[1][c], wq.x * hw[0][c])));
             }
             if (C == 4 && acc[NCH - 1] < 0.99f) acc[3] = 0.0f;  // cropping.py:191-195
+            if (OUTFMT == 1) {
+                __stcs(optr_h, pack_bf16x4(acc[0], acc[1], acc[2]));
+                optr_h += wout;
+            } else {
 #pragma unroll
-            for (int c = 0; c < C; ++c) {
-                __stcs(optr[c], acc[c]);
-                optr[c] += wout;
+                for (int c = 0; c < C; ++c) {
+                    __stcs(optr[c], acc[c]);
+                    optr[c] += wout;
+                }
             }
         }
         return;
@@ -423,9 +440,13 @@ __global__ void __launch_bounds__(CROP_MAX_THREADS, 3) hpb_crop_pixels_kernel(co
             }
         }
         if (C == 4 && accv < 0.99f) acc[C - 1] = 0.0f;  // cropping.py:191-195
-        float *o = out + (size_t)oy * p.w + j;
+        if (OUTFMT == 1) {
+            __stcs(p.crops_h + (size_t)n * p.crops_bs + (size_t)oy * p.w + j, pack_bf16x4(acc[0], acc[1], acc[2]));
+        } else {
+            float *o = out + (size_t)oy * p.w + j;
 #pragma unroll
-        for (int c = 0; c < C; ++c) __stcs(o + c * plane_out, acc[c]);
+            for (int c = 0; c < C; ++c) __stcs(o + c * plane_out, acc[c]);
+        }
     }
 }
 
@@ -447,7 +468,7 @@ int hpb_launch_crop_boxes(hpb_ctx *ctx, int H, int W, const float *points, int n
 
 int hpb_launch_crop_pixels(hpb_ctx *ctx, const float *images, int n_im, int C, int H, int W, const int32_t *im_ids,
                            const float *boxes, int b, int h, int w, float *crops, int64_t crops_bs, int tap_bits,
-                           cudaStream_t stream) {
+                           cudaStream_t stream, void *crops_bf16x4) {
     if (b == 0) return HPB_OK;
     if (C != 3 && C != 4) {
         hpb_set_error("hpb_crop: C must be 3 or 4 (got %d)", C);
@@ -457,6 +478,7 @@ int hpb_launch_crop_pixels(hpb_ctx *ctx, const float *images, int n_im, int C, i
     p.images = images; p.im_ids = im_ids; p.boxes = boxes;
     p.n_im = n_im; p.C = C; p.H = H; p.W = W; p.b = b; p.h = h; p.w = w;
     p.crops = crops; p.crops_bs = crops_bs;
+    p.crops_h = reinterpret_cast<uint2 *>(crops_bf16x4);
     p.packed = nullptr;
     p.packed_h = nullptr;
     // few distinct frames, many hypotheses: interleave the frames once so a tap is one 16-byte (fp16 copy: 8-byte) load
@@ -488,13 +510,17 @@ int hpb_launch_crop_pixels(hpb_ctx *ctx, const float *images, int n_im, int C, i
     const int threads = w >= CROP_MAX_THREADS ? CROP_MAX_THREADS : ((w + 31) / 32) * 32;  // one thread per output column
     const size_t smem = (size_t)band * CROP_SPAN * sizeof(float) + (size_t)band * sizeof(int);
     dim3 grid((h + band - 1) / band, b, (w + threads - 1) / threads);
-    if (C == 3) {
-        if (p.packed_h) hpb_crop_pixels_kernel<3, 2><<<grid, threads, smem, stream>>>(p);
-        else if (p.packed) hpb_crop_pixels_kernel<3, 1><<<grid, threads, smem, stream>>>(p);
-        else hpb_crop_pixels_kernel<3, 0><<<grid, threads, smem, stream>>>(p);
+    if (C == 3 && p.crops_h) {
+        if (p.packed_h) hpb_crop_pixels_kernel<3, 2, 1><<<grid, threads, smem, stream>>>(p);
+        else if (p.packed) hpb_crop_pixels_kernel<3, 1, 1><<<grid, threads, smem, stream>>>(p);
+        else hpb_crop_pixels_kernel<3, 0, 1><<<grid, threads, smem, stream>>>(p);
+    } else if (C == 3) {
+        if (p.packed_h) hpb_crop_pixels_kernel<3, 2, 0><<<grid, threads, smem, stream>>>(p);
+        else if (p.packed) hpb_crop_pixels_kernel<3, 1, 0><<<grid, threads, smem, stream>>>(p);
+        else hpb_crop_pixels_kernel<3, 0, 0><<<grid, threads, smem, stream>>>(p);
     } else {
-        if (p.packed) hpb_crop_pixels_kernel<4, 1><<<grid, threads, smem, stream>>>(p);
-        else hpb_crop_pixels_kernel<4, 0><<<grid, threads, smem, stream>>>(p);
+        if (p.packed) hpb_crop_pixels_kernel<4, 1, 0><<<grid, threads, smem, stream>>>(p);
+        else hpb_crop_pixels_kernel<4, 0, 0><<<grid, threads, smem, stream>>>(p);
     }
     HPB_CUDA_OK(cudaGetLastError());
     ctx->launches++;

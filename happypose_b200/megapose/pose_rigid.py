@@ -223,6 +223,19 @@ class PosePredictor(nn.Module):
         self._prepare_net(images)
         return self._folded is not None and self._folded.accepts_s2d and self._folded.s2d_channels >= 40
 
+    def _s2d_buffer(self, bsz: int, device) -> torch.Tensor:
+        """Persistent, zero-initialised stem-input buffer of the fused hand-off: only the rasteriser writes it (the first 48
+        channels of every cell), so the zero padding channels never have to be rewritten.  One buffer per model, grown to
+        the largest batch seen; smaller batches use its leading rows.  (Inside a captured CUDA graph the buffer was created
+        by the eager warm-up, so the graph only holds its address.)"""
+        h, w = self.render_size
+        buf = getattr(self, "_s2d_buf", None)
+        if buf is None or buf.shape[0] < bsz or buf.device != torch.device(device):
+            buf = torch.zeros((bsz, self._folded.s2d_channels, h // 2 + 3, w // 2 + 3), dtype=torch.bfloat16, device=device,
+                              memory_format=torch.channels_last)
+            self._s2d_buf = buf
+        return buf[:bsz]
+
     def _alloc_input(self, bsz: int, device) -> torch.Tensor:
         C = self.n_input_channels + self._n_single_render_channels * self.n_rendered_views
         h, w = self.render_size
@@ -536,11 +549,13 @@ class PosePredictor(nn.Module):
         if self._direct_s2d_ok(images, return_debug_data, cuda_timer):
             # fused hand-off: the rasteriser's resolve writes the stem's bf16 space-to-depth input itself (crop channels
             # read from the crop kernel's planes): no float32 [b,9,h,w] network input, no packing pass
-            crops, K_crop, _, _ = ops.crop(
+            # ... and the crop travels as bf16 pixels (8 B instead of 12 B per pixel, one load in the resolve)
+            crops, K_crop, _, _ = ops.crop_bf16x4(
                 ctx, images, im_ids, self.mesh_db.points_subset(2000), obj_ids, K, TCO_input, tCR, self.render_size,
                 tap_bits=self.crop_tap_bits)
             render_start = time.time()
-            z = ops.render_s2d_bf16(ctx, mesh_ids, TCO_input, K_crop, crops, self._folded.s2d_channels)
+            z = ops.render_s2d_bf16(ctx, mesh_ids, TCO_input, K_crop, crops, self._folded.s2d_channels,
+                                    out=self._s2d_buffer(bsz, device), pad_prezeroed=self._folded.s2d_channels >= 48)
             render_time = time.time() - render_start
             start = time.time()
             feat = self._folded(z, packed_s2d=True)

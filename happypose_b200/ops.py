@@ -271,6 +271,41 @@ def crop(
     return crops, K_crop, boxes_rend, boxes_crop
 
 
+def crop_bf16x4(ctx: Context, images, im_ids, points, obj_ids, K, TCO, tCR, render_size, lamb: float = 1.4, tap_bits: int = 32):
+    """crop_inputs for RGB frames with the crop delivered as [b,h,w,4] bfloat16 pixels (r,g,b,0) -- the float32 crop of
+    `crop` rounded to nearest even, 8 bytes per pixel (hpb_crop_bf16x4).  Feeds render_s2d_bf16.
+    Returns (crops [b,h,w,4] bf16, K_crop, boxes_rend, boxes_crop)."""
+    dev = ctx.device
+    images = _f32(images, dev)
+    n_im, C, H, W = images.shape
+    assert C == 3, "the bf16x4 crop format is for RGB frames"
+    h, w = int(render_size[0]), int(render_size[1])
+    K = _f32(K, dev).reshape(-1, 9)
+    TCO = _f32(TCO, dev).reshape(-1, 16)
+    tCR = _f32(tCR, dev).reshape(-1, 3)
+    b = TCO.shape[0]
+    assert K.shape[0] == b and tCR.shape[0] == b
+    im_ids = _i32(im_ids, dev)
+    obj_ids = _i32(obj_ids, dev)
+    points = _f32(points, dev)
+    crops = torch.empty((b, h, w, 4), dtype=torch.bfloat16, device=dev)
+    K_crop = torch.empty((b, 3, 3), dtype=torch.float32, device=dev)
+    boxes_rend = torch.empty((b, 4), dtype=torch.float32, device=dev)
+    boxes_crop = torch.empty((b, 4), dtype=torch.float32, device=dev)
+    ev = None
+    if _kernel_timer is not None:
+        ev = _kernel_timer.bracket("hpb_crop", b * h * w * 8, fp32_equivalent_bytes=b * 3 * h * w * 4)
+        ev[0].record()
+    rc = ctx.lib.hpb_crop_bf16x4(
+        ctx.handle, ptr(images), n_im, H, W, ptr(im_ids), ptr(points), points.shape[0], points.shape[1], ptr(obj_ids),
+        ptr(K), ptr(TCO), ptr(tCR), b, h, w, lamb, ptr(crops), h * w, ptr(K_crop), ptr(boxes_rend), ptr(boxes_crop),
+        16 if tap_bits == 16 else 32, stream_ptr(dev))
+    if ev is not None:
+        ev[1].record()
+    ctx.check(rc, "hpb_crop_bf16x4")
+    return crops, K_crop, boxes_rend, boxes_crop
+
+
 def crop_boxes(ctx: Context, image_size, points, obj_ids, K, TCO, tCR, render_size, lamb: float = 1.4):
     """compute_crops_multiview maths: (K_crop, boxes_rend, boxes_crop) without resampling any pixels."""
     dev = ctx.device
@@ -388,10 +423,13 @@ def pack_input_s2d_bf16(ctx: Context, x: torch.Tensor, c_padded: int) -> torch.T
 
 
 def render_s2d_bf16(ctx: Context, mesh_ids: torch.Tensor, TCO: torch.Tensor, K: torch.Tensor, crops: torch.Tensor, c_padded: int,
-                    ambient: Optional[torch.Tensor] = None, z_near: float = 0.1, z_far: float = 10.0) -> torch.Tensor:
+                    ambient: Optional[torch.Tensor] = None, z_near: float = 0.1, z_far: float = 10.0,
+                    out: Optional[torch.Tensor] = None, pad_prezeroed: bool = False) -> torch.Tensor:
     """Renders rgb + normals of b scenes and writes the stem's input directly: z [b,c_padded,h/2+3,w/2+3] bfloat16
     channels_last = pack_input_s2d_bf16(cat(crops, rgb, normals)) without the float32 network input or the packing pass
-    (hpb_render_s2d_bf16).  crops: [b,3,h,w] float32 (a contiguous tensor or the first 3 channels of a wider one)."""
+    (hpb_render_s2d_bf16).  crops: [b,3,h,w] float32 (a contiguous tensor or the first 3 channels of a wider one), or
+    [b,h,w,4] bfloat16 (crop_bf16x4).  `out`: a caller-owned result buffer; with pad_prezeroed its channels >= 48 must
+    already be zero and stay untouched by anyone else (the kernel then writes 96 B instead of 2*c_padded B per cell)."""
     dev = ctx.device
     TCO = _f32(TCO, dev).reshape(-1, 16)
     K = _f32(K, dev).reshape(-1, 9)
@@ -399,20 +437,32 @@ def render_s2d_bf16(ctx: Context, mesh_ids: torch.Tensor, TCO: torch.Tensor, K: 
     assert K.shape[0] == b, "K and TCO batch sizes differ"
     mesh_ids = _i32(mesh_ids, dev)
     assert mesh_ids.numel() == b
-    assert crops.dtype == torch.float32 and crops.dim() == 4 and crops.shape[0] == b and crops.shape[1] == 3
-    h, w = int(crops.shape[2]), int(crops.shape[3])
-    assert crops.stride(3) == 1 and crops.stride(2) == w and crops.stride(1) == h * w, "crop planes must be dense"
+    if crops.dtype == torch.bfloat16:
+        assert crops.dim() == 4 and crops.shape[0] == b and crops.shape[3] == 4 and crops.is_contiguous()
+        h, w = int(crops.shape[1]), int(crops.shape[2])
+        fmt, crops_bs, crop_bytes = _capi.CROPS_BF16X4, h * w, h * w * 8
+    else:
+        assert crops.dtype == torch.float32 and crops.dim() == 4 and crops.shape[0] == b and crops.shape[1] == 3
+        h, w = int(crops.shape[2]), int(crops.shape[3])
+        assert crops.stride(3) == 1 and crops.stride(2) == w and crops.stride(1) == h * w, "crop planes must be dense"
+        fmt, crops_bs, crop_bytes = _capi.CROPS_F32_PLANAR, crops.stride(0), 3 * h * w * 4
     amb = None if ambient is None else _f32(ambient, dev).reshape(b, 3)
-    out = torch.empty((b, c_padded, h // 2 + 3, w // 2 + 3), dtype=torch.bfloat16, device=dev, memory_format=torch.channels_last)
+    shape = (b, c_padded, h // 2 + 3, w // 2 + 3)
+    if out is None:
+        assert not pad_prezeroed, "pad_prezeroed needs a caller-owned, pre-zeroed `out`"
+        out = torch.empty(shape, dtype=torch.bfloat16, device=dev, memory_format=torch.channels_last)
+    else:
+        assert tuple(out.shape) == shape and out.dtype == torch.bfloat16 and out.is_contiguous(memory_format=torch.channels_last)
     ev = None
     if _kernel_timer is not None:
-        # bytes this launch has to move: the bf16 cells of the stem input it writes (the layout the consumer needs, zero
-        # padding included) + the crop planes it reads; fp32-equivalent = the 6 float32 planes per view of hpb_render
-        ev = _kernel_timer.bracket("hpb_raster_kernel", b * ((h // 2 + 3) * (w // 2 + 3) * c_padded * 2 + 3 * h * w * 4),
+        # bytes this launch moves: the bf16 cells of the stem input it writes (96 B per cell into a pre-zeroed buffer, else
+        # the whole padded cell) + the crop it reads; fp32-equivalent = the 6 float32 planes per view of hpb_render
+        cell_bytes = 96 if pad_prezeroed else c_padded * 2
+        ev = _kernel_timer.bracket("hpb_raster_kernel", b * ((h // 2 + 3) * (w // 2 + 3) * cell_bytes + crop_bytes),
                                    fp32_equivalent_bytes=b * 6 * h * w * 4)
         ev[0].record()
     rc = ctx.lib.hpb_render_s2d_bf16(ctx.handle, ptr(mesh_ids), ptr(TCO), ptr(K), ptr(amb), b, h, w, z_near, z_far,
-                                     ptr(crops), crops.stride(0), ptr(out), c_padded, stream_ptr(dev))
+                                     ptr(crops), crops_bs, fmt, ptr(out), c_padded, 1 if pad_prezeroed else 0, stream_ptr(dev))
     if ev is not None:
         ev[1].record()
     ctx.check(rc, "hpb_render_s2d_bf16")

@@ -170,6 +170,17 @@ int hpb_crop(hpb_ctx *ctx, const float *images_dev, int n_im, int C, int H, int 
              int tap_bits, void *stream);
 
 /*
+ * hpb_crop for RGB frames (C = 3) with the crop written as crops_dev [b, h, w] pixels of 4 bfloat16 (r, g, b, 0)
+ * (8 bytes per pixel, batch stride crops_bstride pixels): each value is the float32 crop of hpb_crop rounded to nearest
+ * even, i.e. exactly what the network input packing would make of it.  Consumer: hpb_render_s2d_bf16(HPB_CROPS_BF16X4).
+ */
+int hpb_crop_bf16x4(hpb_ctx *ctx, const float *images_dev, int n_im, int H, int W, const int32_t *im_ids_dev,
+                    const float *points_dev, int n_obj, int n_pts, const int32_t *obj_ids_dev, const float *K_dev,
+                    const float *TCO_dev, const float *tCR_dev, int b, int h, int w, float lamb, void *crops_dev,
+                    int64_t crops_bstride, float *K_crop_dev, float *boxes_rend_dev, float *boxes_crop_dev,
+                    int tap_bits, void *stream);
+
+/*
  * Precision of the frame samples ("taps") hpb_crop reads when it resamples from its pixel-interleaved copy of an RGB
  * frame (many hypotheses per frame).  32 (default): float32, the reference's arithmetic (cropping.py:155-197, torchvision
  * roi_align on float32 images).  16: the copy holds IEEE fp16 -- 8-byte instead of 16-byte taps, which halves the L1
@@ -243,13 +254,22 @@ int hpb_pack_input_s2d_bf16(hpb_ctx *ctx, const float *x_dev, int64_t x_bstride,
  * network input of PosePredictor.forward_coarse (pose_rigid.py:708-788: x = cat(images_crop, renders), then the stem
  * of net_forward :352-374): renders the b scenes and writes out_dev [b, h/2+3, w/2+3, C_padded] bfloat16 with
  *   out[n, I, J, (r*2+s)*9 + c] = xpad[n, c, 2I+r, 2J+s],   xpad = zero-padded-by-3 9-channel input whose channels 0..2
- * are crops_dev [b, 3, h, w] float32 (row stride crops_bstride floats; the output of hpb_crop) and channels 3..8 the
- * rendered rgb + normals; channels 36.. are zero.  Bit-identical to hpb_crop -> hpb_render into x -> hpb_pack_input_s2d_bf16,
- * without ever materialising the float32 network input.  h and w even, C_padded >= 40 and a multiple of 8.
+ * are the crop (the output of hpb_crop / hpb_crop_bf16x4) and channels 3..8 the rendered rgb + normals; channels 36.. are
+ * zero.  Bit-identical to hpb_crop -> hpb_render into x -> hpb_pack_input_s2d_bf16, without ever materialising the float32
+ * network input.  h and w even, C_padded >= 40 and a multiple of 8.
+ *   crops_format   HPB_CROPS_F32_PLANAR: crops_dev [b, 3, h, w] float32, batch stride crops_bstride floats;
+ *                  HPB_CROPS_BF16X4:     crops_dev [b, h, w] pixels of 4 bfloat16 (r, g, b, 0), batch stride crops_bstride
+ *                                        pixels -- hpb_crop_bf16x4's output: half the bytes, one 8-byte load per pixel
+ *   pad_prezeroed  non-zero: the caller guarantees that channels >= 48 of out_dev are already zero (a persistent buffer that
+ *                  only this call writes, e.g. from cudaMemset at allocation); the kernel then writes 96 bytes per cell
+ *                  instead of 2 * C_padded.  Needs C_padded >= 48.
  */
+#define HPB_CROPS_F32_PLANAR 0
+#define HPB_CROPS_BF16X4 1
 int hpb_render_s2d_bf16(hpb_ctx *ctx, const int32_t *mesh_ids_dev, const float *TCO_dev, const float *K_dev,
-                        const float *ambient_dev, int b, int h, int w, float z_near, float z_far, const float *crops_dev,
-                        int64_t crops_bstride, void *out_dev, int C_padded, void *stream);
+                        const float *ambient_dev, int b, int h, int w, float z_near, float z_far, const void *crops_dev,
+                        int64_t crops_bstride, int crops_format, void *out_dev, int C_padded, int pad_prezeroed,
+                        void *stream);
 
 /*
  * nn.MaxPool2d(kernel_size=3, stride=2, padding=1) of the ResNet stem (torchvision_resnet.py:215) on bfloat16

@@ -557,6 +557,45 @@ def test_render_s2d_bf16_equals_render_then_pack(ctx, can):
         # a second call: the visibility buffer must have been re-armed by the first
         again = ops.render_s2d_bf16(ctx, ids, torch.as_tensor(T), torch.as_tensor(K), crops, 64)
         assert torch.equal(again.view(torch.int16), want.view(torch.int16))
+        # the shipped form: crop handed over as bf16 pixels (r,g,b,0), persistent pre-zeroed output (96 B per cell written);
+        # written twice into the same buffer with different crops to show that nothing stale survives
+        crops_h = torch.zeros((b, *res, 4), dtype=torch.bfloat16, device="cuda")
+        crops_h[..., :3] = crops.permute(0, 2, 3, 1).to(torch.bfloat16)
+        buf = torch.zeros((b + 2, 64, res[0] // 2 + 3, res[1] // 2 + 3), dtype=torch.bfloat16, device="cuda", memory_format=torch.channels_last)
+        ops.render_s2d_bf16(ctx, ids, torch.as_tensor(T), torch.as_tensor(K), torch.flip(crops_h, (1,)).contiguous(), 64, out=buf[:b], pad_prezeroed=True)
+        got_h = ops.render_s2d_bf16(ctx, ids, torch.as_tensor(T), torch.as_tensor(K), crops_h, 64, out=buf[:b], pad_prezeroed=True)
+        assert got_h.data_ptr() == buf.data_ptr()
+        assert torch.equal(got_h.view(torch.int16), want.view(torch.int16)), f"bf16x4 / pre-zeroed, b={b} res={res}"
+        assert not buf[b:].any()
+
+
+def test_crop_bf16x4_is_the_rounded_float32_crop(ctx, can):
+    """hpb_crop_bf16x4 = hpb_crop rounded to bfloat16 (nearest even), pixel-interleaved, for float32 and fp16 taps, the
+    fast (few frames, many rows) and the generic (wide box) paths; K_crop / boxes identical."""
+    from happypose_b200 import ops
+
+    om, _ = can
+    rs = np.random.RandomState(32)
+    dev = torch.device("cuda")
+    for b, n_im, tap in ((40, 1, 32), (40, 1, 16), (3, 3, 32)):
+        T, _ = random_crop_scene(rs, b, z_range=(0.35, 0.9))
+        T[:, :2, 3] += rs.uniform(-0.05, 0.05, (b, 2)).astype(np.float32)
+        if b == 3:
+            T[0, 2, 3] = 0.12  # very close: a crop box several times wider than the output -> generic path
+        K = np.tile(np.array([[605.95, 0, 319.03], [0, 605.01, 249.68], [0, 0, 1]], np.float32), (b, 1, 1))
+        img = torch.as_tensor(rs.rand(n_im, 3, 480, 640).astype(np.float32)).to(dev)
+        im_ids = torch.as_tensor(rs.randint(0, n_im, b).astype(np.int32)).to(dev)
+        pts = torch.as_tensor(om.pos[rs.choice(len(om.pos), 2000, replace=False)][None]).to(dev)
+        zero = torch.zeros(b, dtype=torch.int32, device=dev)
+        Tt, Kt = torch.as_tensor(T).to(dev), torch.as_tensor(K).to(dev)
+        tCR = Tt[:, :3, 3].contiguous()
+        c32, K32, br32, bc32 = ops.crop(ctx, img, im_ids, pts, zero, Kt, Tt, tCR, (240, 320), tap_bits=tap)
+        ch, Kh, brh, bch = ops.crop_bf16x4(ctx, img, im_ids, pts, zero, Kt, Tt, tCR, (240, 320), tap_bits=tap)
+        assert ch.shape == (b, 240, 320, 4) and ch.dtype == torch.bfloat16
+        assert torch.equal(K32, Kh) and torch.equal(br32, brh) and torch.equal(bc32, bch)
+        want = c32.permute(0, 2, 3, 1).to(torch.bfloat16)
+        assert torch.equal(ch[..., :3].contiguous().view(torch.int16), want.contiguous().view(torch.int16)), f"b={b} tap={tap}"
+        assert not ch[..., 3].any()
 
 
 def test_maxpool_bf16_nhwc_is_bit_exact(ctx):
