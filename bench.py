@@ -51,7 +51,7 @@ METRIC, UNIT = "megapose_poses_per_sec", "poses/s"
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--dets", type=int, default=1, help="detections (poses) per GPU per step")
@@ -62,7 +62,17 @@ def parse_args():
                     help="nvml: in-process NVML polling thread; smi: the recipe's `nvidia-smi -lms` child started before the warm-up")
     ap.add_argument("--profile-range", action="store_true",
                     help="bracket the kernel-timed region with cudaProfilerStart/Stop (ncu --profile-from-start off)")
-    return ap.parse_args()
+    ap.add_argument("--config", default="megapose1", choices=["megapose1", "cosypose21", "sweep", "tless240", "gso1000"],
+                    help="megapose1 = BASELINE configs[0] (the headline metric); the others are configs[1..4] (bench_configs.py)")
+    ap.add_argument("--meshes", type=int, default=0, help="gso1000: number of meshes (default 1000)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="megapose1 at N > 1: weak = --dets detections PER GPU (default); strong = --dets detections in total, their "
+                         "576 rows each split across the ranks (the latency case: 72 rows per GPU at N = 8)")
+    args = ap.parse_args()
+    args.steps_given = args.steps is not None
+    if args.steps is None:
+        args.steps = 10
+    return args
 
 
 def config_dict(args, world):
@@ -70,9 +80,9 @@ def config_dict(args, world):
         "workload": "BASELINE configs[0]: MegaPose barbecue-sauce-style example, 1 object per GPU, 640x480 synthetic RGB frame, "
                     "576 coarse hypotheses + top-1 + 5 refiner iterations x 4 views + 1 scoring pass, random-init ResNet-34 (bf16)",
         "mesh": "tests/golden/obj_000001.npz (reference tests/data/obj_000001.ply: 9951 verts, 15728 faces, 512^2 texture)",
-        "detections_per_gpu": args.dets, "coarse_hypotheses": M_GRID, "refiner_iterations": N_REFINER_ITERS, "refiner_views": N_VIEWS,
+        "detections_per_gpu": args.dets if getattr(args, "scaling", "weak") == "weak" else args.dets / world, "coarse_hypotheses": M_GRID, "refiner_iterations": N_REFINER_ITERS, "refiner_views": N_VIEWS,
         "render_size": [H_R, W_R], "frame": [H_IM, W_IM], "bsz_images": 576, "bsz_objects": 16,
-        "parallelism": f"hypothesis-sharded x{world}",
+        "parallelism": f"hypothesis-sharded x{world}" + (" (strong: the detections' rows are split across the ranks)" if getattr(args, "scaling", "weak") == "strong" else ""),
         "l2": "no explicit flush: every step writes/reads 1.6 GB of network input per pose (> 126 MB L2)",
     }
 
@@ -375,7 +385,7 @@ def run_ours(args):
     est.use_cuda_graphs = not args.no_graphs
     ctx = coarse._ctx()
 
-    n_det = args.dets * world
+    n_det = args.dets * (world if args.scaling == "weak" else 1)
     boxes_np = detections_arrays(n_det)
     rs = np.random.RandomState(0)
     image_host = torch.as_tensor(rs.rand(1, 3, H_IM, W_IM).astype(np.float32)).pin_memory()
@@ -478,7 +488,7 @@ def run_ours(args):
         _, K_crop, _, _ = ops.crop(ctx, obs_dev.images, obj0, pts, obj0, K_rows, TCO, TCO[:, :3, 3].contiguous(), (H_R, W_R), out=x)
         ops.render(ctx, mesh_ids, TCO, K_crop, (H_R, W_R), render_normals=True, out=x, out_channel_offset=3)
 
-    z_buf = torch.zeros((b, 64, H_R // 2 + 3, W_R // 2 + 3), dtype=torch.bfloat16, device=dev, memory_format=torch.channels_last)
+    z_buf = torch.empty((b, 64, H_R // 2 + 3, W_R // 2 + 3), dtype=torch.bfloat16, device=dev, memory_format=torch.channels_last).zero_()
 
     def render_crop_fused():  # what the pipeline's coarse stage does: bf16 crop pixels, then the rasteriser writes the stem input
         crops_h, K_crop, _, _ = ops.crop_bf16x4(ctx, obs_dev.images, obj0, pts, obj0, K_rows, TCO, TCO[:, :3, 3].contiguous(), (H_R, W_R),
@@ -502,7 +512,7 @@ def run_ours(args):
     rk = ksum.get("hpb_raster_kernel", {"gbps": 0.0, "ms_avg": 0.0, "launches": 0, "bytes_avg": 0, "ms_total": 0.0})
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "bf16 (networks) / f32 (rasteriser, crop, pose kernels)", "data": "synthetic", "config": config_dict(args, world),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(poses.numel() * 4 + scores.size * 8),
                 "ms_per_step": ms_e2e / args.steps},
@@ -530,12 +540,12 @@ def run_ours(args):
                         "largest_launch_gbps": v["largest"]["gbps"], "largest_launch_frac": v["largest"]["gbps"] / peak,
                         "largest_launch_ms": v["largest"]["ms_avg"]} for k, v in ksum.items()},
         "hyps": {"metric": "rendered_hyps_per_sec", "value": hyps_per_s, "unit": "hyps/s", "b": b, "ms_per_launch_pair": ms_hyp / hyp_iters,
-                 "path": "hpb_crop_bf16x4 (fp16 frame taps) -> hpb_render_s2d_bf16 (the pipeline's coarse hand-off: bf16 space-to-depth stem input, 96 B per cell)",
+                 "path": "hpb_crop_bf16x4 (fp16 frame taps) -> hpb_render_s2d_bf16 (the pipeline's coarse hand-off: bf16 space-to-depth stem input, 128 B per cell)",
                  # 2 764 800 algorithmic bytes per coarse hypothesis (the 9-channel float32 network input)
                  "gbps": b * 9 * H_R * W_R * 4 / 1e9 / (ms_hyp / hyp_iters / 1e3),
                  "frac": b * 9 * H_R * W_R * 4 / 1e9 / (ms_hyp / hyp_iters / 1e3) / peak,
                  # bytes really moved per hypothesis: bf16 crop pixels written + read back, stem-input cells written
-                 "moved_gbps": b * (2 * H_R * W_R * 8 + (H_R // 2 + 3) * (W_R // 2 + 3) * 96) / 1e9 / (ms_hyp / hyp_iters / 1e3),
+                 "moved_gbps": b * (2 * H_R * W_R * 8 + (H_R // 2 + 3) * (W_R // 2 + 3) * 128) / 1e9 / (ms_hyp / hyp_iters / 1e3),
                  "planar_fp32": {"value": world * b * hyp_iters / (ms_hyp_planar / 1e3), "ms_per_launch_pair": ms_hyp_planar / hyp_iters,
                                  "gbps": b * 9 * H_R * W_R * 4 / 1e9 / (ms_hyp_planar / hyp_iters / 1e3),
                                  "frac": b * 9 * H_R * W_R * 4 / 1e9 / (ms_hyp_planar / hyp_iters / 1e3) / peak}},
@@ -586,7 +596,14 @@ def main():
     if args.impl == "reference":
         run_reference(args)
     else:
-        run_ours(args)
+        if args.config != "megapose1":
+            import bench_configs
+
+            if not torch.cuda.is_available():
+                raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+            bench_configs.CONFIGS[args.config](args, sys.modules[__name__])
+        else:
+            run_ours(args)
         import torch.distributed as dist
 
         if dist.is_available() and dist.is_initialized():

@@ -444,14 +444,13 @@ int hpb_render_s2d_bf16(hpb_ctx *ctx, const int32_t *mesh_ids_dev, const float *
     HPB_REQUIRE(ctx, "NULL ctx");
     HPB_REQUIRE(b >= 0 && h > 0 && w > 0 && (long long)h * w < (1ll << 30), "bad batch / resolution");
     HPB_REQUIRE(h % 2 == 0 && w % 2 == 0, "space-to-depth output needs even height and width");
-    HPB_REQUIRE(C_padded >= 40 && C_padded % 8 == 0, "C_padded must be a multiple of 8 and hold 4 * 9 channels");
+    HPB_REQUIRE(C_padded >= 64 && C_padded % 32 == 0, "C_padded must be a multiple of 32 with C_padded / 4 >= 9 channels per sub-pixel");
     if (b == 0) return HPB_OK;
     HPB_REQUIRE(mesh_ids_dev && TCO_dev && K_dev && crops_dev && out_dev, "NULL input");
     HPB_REQUIRE((reinterpret_cast<uintptr_t>(out_dev) & 15u) == 0, "out_dev must be 16-byte aligned");
     HPB_REQUIRE(crops_format == HPB_CROPS_F32_PLANAR || crops_format == HPB_CROPS_BF16X4, "unknown crops_format");
     HPB_REQUIRE(crops_bstride >= (crops_format == HPB_CROPS_F32_PLANAR ? 3ll : 1ll) * h * w, "crops_bstride smaller than one crop");
     HPB_REQUIRE((reinterpret_cast<uintptr_t>(crops_dev) & (crops_format == HPB_CROPS_BF16X4 ? 7u : 3u)) == 0, "crops_dev misaligned");
-    HPB_REQUIRE(!pad_prezeroed || C_padded >= 48, "pad_prezeroed needs at least 48 padded channels");
     HPB_REQUIRE(z_near > 0.f && z_far > z_near, "bad near/far");
     HPB_REQUIRE(!ctx->meshes.empty(), "no mesh uploaded");
     HpbDeviceGuard guard(ctx->device);
@@ -646,7 +645,7 @@ int hpb_pack_input_s2d_bf16(hpb_ctx *ctx, const float *x_dev, int64_t x_bstride,
                             int C_padded, void *stream) {
     HPB_REQUIRE(ctx && b >= 0 && C > 0 && H > 0 && W > 0, "bad argument");
     HPB_REQUIRE(H % 2 == 0 && W % 2 == 0, "space-to-depth needs even H and W");
-    HPB_REQUIRE(C_padded >= 4 * C && C_padded % 8 == 0 && C <= 64, "C_padded must be a multiple of 8 and >= 4*C (C <= 64)");
+    HPB_REQUIRE(C_padded >= 4 * C && C_padded % 32 == 0 && C <= 64, "C_padded must be a multiple of 32 and >= 4*C (C <= 64)");
     if (b == 0) return HPB_OK;
     HPB_REQUIRE(x_dev && out_dev, "NULL pointer");
     HPB_REQUIRE(((uintptr_t)out_dev & 15) == 0, "output must be 16-byte aligned");

@@ -470,7 +470,8 @@ int hpb_launch_maxpool(hpb_ctx *ctx, const void *in, int b, int H, int W, int C,
 
 // ------------------------------------------------------------------------------------------------------------------
 // Space-to-depth network-input packing for the ResNet stem.  A 7x7 / stride 2 / pad 3 convolution over C channels equals
-// a 4x4 / stride 1 / no-pad convolution over 4C channels of z, where z[n, I, J, (r*2+s)*C + c] = xpad[n, c, 2I+r, 2J+s]
+// a 4x4 / stride 1 / no-pad convolution over the channels of z, where z[n, I, J, (r*2+s)*Cs + c] = xpad[n, c, 2I+r, 2J+s]
+// (Cs = Cz / 4 channels reserved per sub-pixel, c < C used, the rest zero: every sub-pixel block starts 16-byte aligned)
 // and xpad is x zero-padded by 3 pixels (w'[o,(r,s,c),a,b] = w[o,c,2a+r,2b+s], zero for tap index 7).  The stride-1 form
 // has a 4x deeper reduction per tap and runs several times faster on the tensor cores than cuDNN's strided 9/27-channel
 // stem.  This kernel builds z (bfloat16, pixel-interleaved, channels padded to Cz with zeros) straight from the float32
@@ -488,7 +489,7 @@ constexpr int S2D_MARGIN = 4;  // zero columns left of x = 0 in the staged rows 
 //   staged row index  (r * C + c), plus one all-zero row for the padded channels k >= 4C
 //   staged column     xx + S2D_MARGIN for xx in [-S2D_MARGIN, W + 4)
 __global__ void __launch_bounds__(S2D_THREADS) hpb_pack_s2d_kernel(const float *x, long long bstride, int C, int H, int W, int Hz, int Wz,
-                                                                   int Cz8, int Wp, unsigned c_magic, uint4 *out) {
+                                                                   int Cz8, int Wp, int Cs, unsigned cs_magic, uint4 *out) {
     extern __shared__ __align__(16) unsigned short s_rows[];  // [(2C + 1)][Wp]
     const int I = blockIdx.x;
     const long long n = blockIdx.y;
@@ -540,9 +541,9 @@ __global__ void __launch_bounds__(S2D_THREADS) hpb_pack_s2d_kernel(const float *
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
         const int k = 8 * q + e;
-        const int rs = (int)(((unsigned)k * c_magic) >> 16);  // k / C for k < 4C + 64 <= 65536 / C
-        const int c = k - rs * C;
-        off[e] = rs < 4 ? ((rs >> 1) * C + c) * Wp + (rs & 1) - 3 + S2D_MARGIN : n_rows * Wp;
+        const int rs = (int)(((unsigned)k * cs_magic) >> 16);  // k / Cs: sub-pixel (r,s) = rs, channel c within its block of Cs
+        const int c = k - rs * Cs;
+        off[e] = (rs < 4 && c < C) ? ((rs >> 1) * C + c) * Wp + (rs & 1) - 3 + S2D_MARGIN : n_rows * Wp;
     }
     uint4 *dst = out + ((n * Hz + I) * Wz) * Cz8 + q;
     for (int J = j0; J < Wz; J += JT) {
@@ -578,9 +579,10 @@ int hpb_launch_pack_s2d(hpb_ctx *ctx, const float *x, int64_t bstride, int b, in
         return HPB_EINVAL;
     }
     HPB_CUDA_OK(cudaFuncSetAttribute(hpb_pack_s2d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const unsigned c_magic = 65535u / (unsigned)C + 1u;
+    const int Cs = Cz / 4;  // channels reserved per sub-pixel (r,s): z channel (r*2+s)*Cs + c
+    const unsigned cs_magic = 65535u / (unsigned)Cs + 1u;
     dim3 grid(Hz, b);
-    hpb_pack_s2d_kernel<<<grid, S2D_THREADS, smem, stream>>>(x, bstride, C, H, W, Hz, Wz, Cz8, Wp, c_magic, reinterpret_cast<uint4 *>(out));
+    hpb_pack_s2d_kernel<<<grid, S2D_THREADS, smem, stream>>>(x, bstride, C, H, W, Hz, Wz, Cz8, Wp, Cs, cs_magic, reinterpret_cast<uint4 *>(out));
     HPB_CUDA_OK(cudaGetLastError());
     ctx->launches++;
     return HPB_OK;

@@ -77,8 +77,7 @@ struct RasterParams {
     const uint2 *crops_h; // [b][h][w] (r,g,b,0) bfloat16, pixel-interleaved: hpb_crop_bf16x4's output (crops_fmt 1)
     long long crops_bs;   // batch stride in elements of the respective format
     int crops_fmt;
-    int pad_prezeroed;    // channels >= 48 of the output are already zero (persistent buffer): only 96 B per cell are written
-    int stage_off;        // byte offset of the per-warp cp.async staging area in dynamic shared memory (-1: none)
+    int pad_prezeroed;    // the padding channels (>= 16 of every sub-pixel block) of the output are already zero (persistent buffer)
     int Hz, Wz, Cz8;      // Hz = h/2 + 3, Wz = w/2 + 3
     unsigned wz_magic;    // floor(2^32 / Wz) + 1
 };
@@ -102,24 +101,6 @@ __device__ __forceinline__ void put_fragment(float d, unsigned lo, unsigned long
         atomicMin(slot, ((unsigned long long)__float_as_uint(d) << 32) | lo);
     }
 }
-
-// cp.async (LDGSTS): global -> shared copies that occupy no registers while in flight.  The resolve uses them to fetch the
-// NEXT work unit's visibility keys (and crop channels) while the current unit is being shaded: ncu showed 44 % of all warp
-// stall samples on long-scoreboard waits, more than half of them at the first use of exactly these two loads.
-__device__ __forceinline__ void cp_async_cg16(void *smem_dst, const void *gsrc) {  // through L2 only: coherent with the atomics
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_ca8(void *smem_dst, const void *gsrc) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_ca4(void *smem_dst, const void *gsrc) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-constexpr int STAGE_BYTES = 1024;  // per warp and stage: 32 x 16 B key pairs | 32 x 16 B crop slots (3 x 4 B planes or one 8 B pixel)
 
 // Depth plane of a triangle oriented so that area2 > 0, anchored at the pixel (jx0, jy0) of its clamped bounding box:
 //   d(col,row) = fmaf(Dx, col, fmaf(Dy, row, Dc)), the GL window depth (1/near - 1/z) / (1/near - 1/far).
@@ -627,12 +608,6 @@ __global__ void __launch_bounds__(RASTER_THREADS, 1) hpb_raster_kernel(const Ras
                 }
             }
         };
-        // Per-warp cp.async staging (two stages): while a warp shades work unit u it already has the loads of unit u + 1 in
-        // flight (visibility keys through L2, crop channels), landing in shared memory without holding registers.  Every
-        // lane copies and later reads only its OWN 16-byte slots, so no warp-level synchronisation is needed; a 16-byte
-        // key copy holds the aligned pixel pair that contains the lane's pixel (needs an even image width).
-        const bool staged = p.stage_off >= 0 && (p.w & 1) == 0;
-        unsigned char *stg = smem_raw + (staged ? p.stage_off : 0) + warp * (2 * STAGE_BYTES);
         if constexpr (!S2D) {
         // Work unit = one 32-pixel span of one row, dealt to the warps of the cluster round-robin (fine-grained, so the
         // shaded and the empty spans spread evenly).  The row / span arithmetic is per warp, not per pixel; spans that
@@ -640,31 +615,10 @@ __global__ void __launch_bounds__(RASTER_THREADS, 1) hpb_raster_kernel(const Ras
         const int nspan = (p.w + 31) >> 5;
         const int n_units = p.h * nspan;
         const int sp0 = bx0 >> 5, sp1 = bx1 >> 5;
-        const int u_stride = G * RASTER_WARPS;
-        auto locate = [&](int u, int &py, int &sp) {
-            py = (int)__umulhi((unsigned)u, p.span_magic);
+        for (int u = rank * RASTER_WARPS + warp; u < n_units; u += G * RASTER_WARPS) {
+            int py = (int)__umulhi((unsigned)u, p.span_magic);
             if (py * nspan > u) --py;
-            sp = u - py * nspan;
-        };
-        auto prefetch = [&](int u, int st) {
-            if (u < n_units) {
-                int py, sp;
-                locate(u, py, sp);
-                const int px = (sp << 5) + lane;
-                if (py >= by0 && py <= by1 && px >= bx0 && px <= bx1)  // bx1 <= w - 1: inside the row
-                    cp_async_cg16(stg + st * STAGE_BYTES + lane * 16, vis + ((py * p.w + px) & ~1));
-            }
-            cp_async_commit();
-        };
-        int u = rank * RASTER_WARPS + warp, st = 0;
-        if (staged) prefetch(u, 0);
-        for (; u < n_units; u += u_stride, st ^= 1) {
-            if (staged) {
-                prefetch(u + u_stride, st ^ 1);
-                cp_async_wait<1>();
-            }
-            int py, sp;
-            locate(u, py, sp);
+            const int sp = u - py * nspan;
             const int px = (sp << 5) + lane;
             const int pix = py * p.w + px;
             const bool in_row = px < p.w;
@@ -689,8 +643,7 @@ __global__ void __launch_bounds__(RASTER_THREADS, 1) hpb_raster_kernel(const Ras
             }
             unsigned long long key = HPB_VIS_EMPTY;
             if (in_row && px >= bx0 && px <= bx1) {
-                key = staged ? *reinterpret_cast<const unsigned long long *>(stg + st * STAGE_BYTES + lane * 16 + ((pix & 1) << 3))
-                             : __ldcg(vis + pix);
+                key = __ldcg(vis + pix);
                 if (key != HPB_VIS_EMPTY) __stcg(vis + pix, HPB_VIS_EMPTY);  // re-arm for the next scene
             }
             float r = 0.f, g = 0.f, bl = 0.f, n0 = 0.f, n1 = 0.f, n2 = 0.f, z = 0.f;
@@ -712,114 +665,65 @@ __global__ void __launch_bounds__(RASTER_THREADS, 1) hpb_raster_kernel(const Ras
         }
         } else {
             // ---- space-to-depth resolve: 4 lanes per CELL of the stem's input, one pixel per lane ----
-            // z[n][I][J][(r*2+s)*9 + c] = xpad[n][c][2I + r][2J + s], xpad = the 9-channel network input (3 crop channels
-            // read from the crop kernel's output, 6 rendered channels shaded here) zero-padded by 3 pixels; channels >= 36
-            // are zero.  Lane l of a warp shades sub-pixel (r,s) = l & 3 of cell l >> 2 of the warp's 8 consecutive cells,
-            // so the shading runs once per iteration exactly as in the planar resolve.  A cell's 36 bf16 values are 72
-            // contiguous bytes whose 16-byte groups straddle the sub-pixels: lane `sub` assembles group `sub` from its own 9
-            // values and the last `sub` values of its left neighbour (two shuffles), so a warp store writes 8 x 64
-            // contiguous bytes -- whole sectors; a second store covers group 4 (4 values + zeros) and the zero groups.
+            // z[n][I][J][(r*2+s)*Cs + c] = xpad[n][c][2I + r][2J + s]  (Cs = Cz / 4 channels reserved per sub-pixel, c < 9 used):
+            // xpad = the 9-channel network input (3 crop channels from the crop kernel, 6 rendered channels shaded here)
+            // zero-padded by 3 pixels.  Lane l of a warp shades sub-pixel (r,s) = l & 3 of cell l >> 2 of the warp's 8
+            // consecutive cells, and a sub-pixel's channel block starts on a 16-byte boundary (Cs is a multiple of 8), so every
+            // lane stores its own 9 bf16 values as two 16-byte vectors: no cross-lane traffic, no unaligned groups.  (Round 1
+            // packed the 36 values densely, (r*2+s)*9 + c: the shuffles / funnel shifts / selects that re-aligned them cost 142
+            // warp instructions per 8 cells -- a third of the whole kernel, more than the shading itself.)
             const int n_cells = p.Hz * p.Wz;
             uint4 *zbase = p.s2d + (size_t)hyp * n_cells * p.Cz8;
             const int sub = lane & 3;
-            const int q_stride = G * RASTER_WARPS * 8;
-            // this lane's pixel of the work unit starting at cell q0; returns its linear index, -1 outside the image
-            auto locate = [&](int q0, int &q, int &px, int &py) -> int {
-                q = q0 + (lane >> 2);
+            const int sub_g = sub * (p.Cz8 >> 2);  // first 16-byte group of this lane's sub-pixel
+            const uint2 *crop_h = p.crops_h ? p.crops_h + (size_t)hyp * p.crops_bs : nullptr;
+            const float *crop_f = p.crops ? p.crops + (size_t)hyp * p.crops_bs : nullptr;
+            for (int q0 = (rank * RASTER_WARPS + warp) * 8; q0 < n_cells; q0 += G * RASTER_WARPS * 8) {
+                const int q = q0 + (lane >> 2);
                 int I = (int)__umulhi((unsigned)q, p.wz_magic);
                 if (I * p.Wz > q) --I;
                 const int J = q - I * p.Wz;
-                py = 2 * I + (sub >> 1) - 3;
-                px = 2 * J + (sub & 1) - 3;
-                return (q < n_cells && py >= 0 && py < p.h && px >= 0 && px < p.w) ? py * p.w + px : -1;
-            };
-            auto prefetch = [&](int q0, int st) {
-                if (q0 < n_cells) {
-                    int q, px, py;
-                    const int pix = locate(q0, q, px, py);
-                    if (pix >= 0) {
-                        unsigned char *slot = stg + st * STAGE_BYTES;
-                        if (p.crops_fmt == 1) {
-                            cp_async_ca8(slot + 512 + lane * 16, p.crops_h + (size_t)hyp * p.crops_bs + pix);
-                        } else {
-                            const float *c = p.crops + (size_t)hyp * p.crops_bs + pix;
-                            cp_async_ca4(slot + 512 + lane * 16, c);
-                            cp_async_ca4(slot + 512 + lane * 16 + 4, c + npix);
-                            cp_async_ca4(slot + 512 + lane * 16 + 8, c + 2 * npix);
-                        }
-                        if (py >= by0 && py <= by1 && px >= bx0 && px <= bx1) cp_async_cg16(slot + lane * 16, vis + (pix & ~1));
-                    }
-                }
-                cp_async_commit();
-            };
-            int q0 = (rank * RASTER_WARPS + warp) * 8, st = 0;
-            prefetch(q0, 0);  // S2D launches always have the staging area (even width is an API requirement)
-            for (; q0 < n_cells; q0 += q_stride, st ^= 1) {
-                prefetch(q0 + q_stride, st ^ 1);
-                cp_async_wait<1>();
-                int q, px, py;
-                const int pix = locate(q0, q, px, py);
-                const bool cell_ok = q < n_cells;
-                const unsigned char *slot = stg + st * STAGE_BYTES;
-                // own values o0..o8 as bf16 pairs, even alignment: e0 = (o0,o1) .. e3 = (o6,o7), e4 = (o8,0)
-                unsigned e[5] = {0u, 0u, 0u, 0u, 0u};
-                if (pix >= 0) {
+                const int py = 2 * I + (sub >> 1) - 3, px = 2 * J + (sub & 1) - 3;
+                // own values o0..o8 as bf16 pairs: e0 = (o0,o1) .. e3 = (o6,o7), e4 = (o8,0)
+                unsigned e0 = 0u, e1 = 0u, e2 = 0u, e3 = 0u, e4 = 0u;
+                if (q < n_cells && (unsigned)py < (unsigned)p.h && (unsigned)px < (unsigned)p.w) {
+                    const int pix = py * p.w + px;
                     float v[6];
 #pragma unroll
                     for (int c = 0; c < 6; ++c) v[c] = 0.f;
+                    unsigned c2;  // crop channel 2 as bf16 bits
+                    if (crop_h) {
+                        const uint2 cw = __ldcs(crop_h + pix);
+                        e0 = cw.x;
+                        c2 = cw.y & 0xffffu;
+                    } else {
+                        const float c0 = __ldcs(crop_f + pix), c1 = __ldcs(crop_f + npix + pix), cb = __ldcs(crop_f + 2 * npix + pix);
+                        const __nv_bfloat162 h01 = __floats2bfloat162_rn(c0, c1);
+                        e0 = *reinterpret_cast<const unsigned *>(&h01);
+                        c2 = (unsigned)__bfloat16_as_ushort(__float2bfloat16_rn(cb));
+                    }
                     if (py >= by0 && py <= by1 && px >= bx0 && px <= bx1) {
-                        const unsigned long long key = *reinterpret_cast<const unsigned long long *>(slot + lane * 16 + ((pix & 1) << 3));
+                        const unsigned long long key = __ldcg(vis + pix);
                         if (key != HPB_VIS_EMPTY) {
                             __stcg(vis + pix, HPB_VIS_EMPTY);  // re-arm for the next scene
                             float zz = 0.f;
                             shade(key, px, py, v[0], v[1], v[2], v[3], v[4], v[5], zz);
                         }
                     }
-                    unsigned c2;  // crop channel 2 as bf16 bits
-                    if (p.crops_fmt == 1) {
-                        const uint2 cw = *reinterpret_cast<const uint2 *>(slot + 512 + lane * 16);
-                        e[0] = cw.x;
-                        c2 = cw.y & 0xffffu;
-                    } else {
-                        const float4 cf = *reinterpret_cast<const float4 *>(slot + 512 + lane * 16);
-                        const __nv_bfloat162 h01 = __floats2bfloat162_rn(cf.x, cf.y);
-                        e[0] = *reinterpret_cast<const unsigned *>(&h01);
-                        c2 = (unsigned)__bfloat16_as_ushort(__float2bfloat16_rn(cf.z));
-                    }
-                    e[1] = c2 | ((unsigned)__bfloat16_as_ushort(__float2bfloat16_rn(v[0])) << 16);
+                    e1 = c2 | ((unsigned)__bfloat16_as_ushort(__float2bfloat16_rn(v[0])) << 16);
                     const __nv_bfloat162 h45 = __floats2bfloat162_rn(v[1], v[2]), h67 = __floats2bfloat162_rn(v[3], v[4]);
-                    e[2] = *reinterpret_cast<const unsigned *>(&h45);
-                    e[3] = *reinterpret_cast<const unsigned *>(&h67);
-                    e[4] = (unsigned)__bfloat16_as_ushort(__float2bfloat16_rn(v[5]));
+                    e2 = *reinterpret_cast<const unsigned *>(&h45);
+                    e3 = *reinterpret_cast<const unsigned *>(&h67);
+                    e4 = (unsigned)__bfloat16_as_ushort(__float2bfloat16_rn(v[5]));
                 }
-                // left neighbour's tail: t0 = (p6,p7), t1 = (p8,0)
-                const unsigned t0 = __shfl_up_sync(0xffffffffu, e[3], 1), t1 = __shfl_up_sync(0xffffffffu, e[4], 1);
-                // halfword string S = p6 p7 p8 o0 .. o8; group `sub` of the cell = S[3 - sub .. 10 - sub]
-                const unsigned A0 = t0;                                   // (p6,p7)
-                const unsigned A1 = (t1 & 0xffffu) | (e[0] << 16);        // (p8,o0)
-                const unsigned A2 = __funnelshift_r(e[0], e[1], 16);      // (o1,o2)
-                const unsigned A3 = __funnelshift_r(e[1], e[2], 16);      // (o3,o4)
-                const unsigned A4 = __funnelshift_r(e[2], e[3], 16);      // (o5,o6)
-                const unsigned A5 = __funnelshift_r(e[3], e[4], 16);      // (o7,o8)
-                const unsigned B0 = __funnelshift_r(t0, t1, 16);          // (p7,p8)
-                uint4 g0;
-                if (sub == 0) g0 = make_uint4(e[0], e[1], e[2], e[3]);
-                else if (sub == 1) g0 = make_uint4(A1, A2, A3, A4);
-                else if (sub == 2) g0 = make_uint4(B0, e[0], e[1], e[2]);
-                else g0 = make_uint4(A0, A1, A2, A3);
-                const uint4 g1 = sub == 3 ? make_uint4(A4, A5, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);  // values 32..35, then zeros
-                if (cell_ok) {
-                    uint4 *cell = zbase + (size_t)q * p.Cz8;
-                    __stcs(cell + sub, g0);
-                    const int e1i = 4 + ((sub + 1) & 3);  // lane 3 -> group 4, lanes 0..2 -> groups 5..7
-                    if (p.pad_prezeroed) {
-                        // persistent, pre-zeroed output: only the sector that carries data (groups 4,5 = bytes 64..95) is
-                        // completed; groups >= 6 keep their zeros -> 96 instead of Cz * 2 bytes written per cell
-                        if (e1i <= 5) __stcs(cell + e1i, g1);
-                    } else {
-                        if (e1i < p.Cz8) __stcs(cell + e1i, g1);
-                        for (int x = 8 + sub; x < p.Cz8; x += 4) __stcs(cell + x, make_uint4(0u, 0u, 0u, 0u));
-                    }
+                if (q < n_cells) {
+                    uint4 *cell = zbase + (size_t)q * p.Cz8 + sub_g;
+                    __stcs(cell, make_uint4(e0, e1, e2, e3));
+                    __stcs(cell + 1, make_uint4(e4, 0u, 0u, 0u));
+                    // channels 16.. of the sub-pixel block are zero padding: written unless the caller keeps a persistent
+                    // pre-zeroed buffer that only this kernel writes
+                    if (!p.pad_prezeroed)
+                        for (int x = 2; x < (p.Cz8 >> 2); ++x) __stcs(cell + x, make_uint4(0u, 0u, 0u, 0u));
                 }
             }
         }
@@ -902,15 +806,10 @@ int hpb_launch_raster(hpb_ctx *ctx, const int32_t *mesh_ids, const float *TCO, c
         HPB_CUDA_OK(cudaFuncGetAttributes(&fa, hpb_raster_kernel<false>));
         static_smem = fa.sharedSizeBytes + 256;
     }
-    // dynamic shared memory = [screen-space vertices | per-warp cp.async staging of the resolve (2 stages x 1 KB per warp)]
-    const size_t stage_bytes = (size_t)RASTER_WARPS * 2 * STAGE_BYTES;
-    const size_t reserved = static_smem + stage_bytes + 16;
-    const size_t smem_cap = (size_t)ctx->max_smem_optin > reserved ? (size_t)ctx->max_smem_optin - reserved : 0;
+    const size_t smem_cap = (size_t)ctx->max_smem_optin > static_smem ? (size_t)ctx->max_smem_optin - static_smem : 0;
     const int verts_in_smem = smem_need <= smem_cap;
     // when some mesh does not fit, the others still use as much shared memory as there is (per-scene choice in the kernel)
-    const size_t vert_bytes = verts_in_smem ? smem_need : (smem_cap / 24) * 24;
-    const size_t stage_off = (vert_bytes + 15) & ~(size_t)15;
-    const size_t smem = stage_off + stage_bytes;
+    const size_t smem = verts_in_smem ? smem_need : (smem_cap / 24) * 24;
     void (*kern)(const RasterParams) = s2d_out ? hpb_raster_kernel<true> : hpb_raster_kernel<false>;
     // both instantiations get the attribute: the cluster-occupancy query below is made on <false> whichever runs first
     HPB_CUDA_OK(cudaFuncSetAttribute(hpb_raster_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -987,8 +886,7 @@ int hpb_launch_raster(hpb_ctx *ctx, const int32_t *mesh_ids, const float *TCO, c
     p.vis = ctx->vis;
     p.vert_scratch = ctx->vert_scratch;
     p.max_nv = nv_pad;
-    p.smem_verts = (int)(vert_bytes / 12);
-    p.stage_off = (int)stage_off;
+    p.smem_verts = (int)(smem / 12);
     p.G = G;
     p.span_magic = (unsigned)((1ull << 32) / (unsigned)((w + 31) / 32)) + 1u;
     p.s2d = reinterpret_cast<uint4 *>(s2d_out);

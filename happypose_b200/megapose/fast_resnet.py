@@ -69,20 +69,26 @@ class _Conv:
 
 def s2d_weight(w: torch.Tensor, c_padded: int) -> torch.Tensor:
     """[O,C,7,7] stem weight -> [O,c_padded,4,4] weight of the equivalent stride-1 convolution over the space-to-depth
-    input: w'[o, (r*2+s)*C + c, a, b] = w[o, c, 2a+r, 2b+s] (tap index 7 = zero)."""
+    input: w'[o, (r*2+s)*Cs + c, a, b] = w[o, c, 2a+r, 2b+s] (tap index 7 = zero), Cs = c_padded / 4 channels reserved per
+    sub-pixel (r,s), channels c >= C of every block zero."""
     O, C = w.shape[:2]
+    assert c_padded % 4 == 0 and c_padded // 4 >= C
+    Cs = c_padded // 4
     w8 = F.pad(w, (0, 1, 0, 1))                                  # [O,C,8,8]
     w8 = w8.reshape(O, C, 4, 2, 4, 2).permute(0, 3, 5, 1, 2, 4)    # [O,r,s,C,a,b]
-    w4 = w8.reshape(O, 4 * C, 4, 4)
-    return F.pad(w4, (0, 0, 0, 0, 0, c_padded - 4 * C))
+    w8 = F.pad(w8, (0, 0, 0, 0, 0, Cs - C))                      # [O,r,s,Cs,a,b]
+    return w8.reshape(O, c_padded, 4, 4)
 
 
 def s2d_reference(x: torch.Tensor, c_padded: int) -> torch.Tensor:
-    """Plain-torch statement of ops.pack_input_s2d_bf16 (used by the tests): z[n,(r*2+s)*C+c,I,J] = xpad[n,c,2I+r,2J+s]."""
+    """Plain-torch statement of ops.pack_input_s2d_bf16 (used by the tests): z[n,(r*2+s)*Cs+c,I,J] = xpad[n,c,2I+r,2J+s]."""
     n, C, H, W = x.shape
+    assert c_padded % 4 == 0 and c_padded // 4 >= C
+    Cs = c_padded // 4
     xp = F.pad(x, (3, 3, 3, 3))
-    z = xp.reshape(n, C, H // 2 + 3, 2, W // 2 + 3, 2).permute(0, 3, 5, 1, 2, 4).reshape(n, 4 * C, H // 2 + 3, W // 2 + 3)
-    return F.pad(z, (0, 0, 0, 0, 0, c_padded - 4 * C))
+    z = xp.reshape(n, C, H // 2 + 3, 2, W // 2 + 3, 2).permute(0, 3, 5, 1, 2, 4)   # [n,r,s,C,I,J]
+    z = F.pad(z, (0, 0, 0, 0, 0, Cs - C))
+    return z.reshape(n, c_padded, H // 2 + 3, W // 2 + 3)
 
 
 class FoldedResNet:

@@ -111,6 +111,9 @@ class PosePredictor(nn.Module):
         self.n_rendered_views = n_rendered_views
         self.input_depth = input_depth
         self.multiview_type = multiview_type
+        # Stored, and -- exactly like the reference -- not used by forward(): pose_rigid.py:578-584 calls make_TCO_multiview
+        # without views_inplane_rotations; the only caller that turns it on is the training loss
+        # (megapose/training/megapose_forward_loss.py:116-123), through lib3d.multiview.make_TCO_multiview, which supports it.
         self.views_inplane_rotations = views_inplane_rotations
         self.render_normals = render_normals
         self.render_depth = render_depth
@@ -221,7 +224,7 @@ class PosePredictor(nn.Module):
         if h % 2 or w % 2:
             return False
         self._prepare_net(images)
-        return self._folded is not None and self._folded.accepts_s2d and self._folded.s2d_channels >= 40
+        return self._folded is not None and self._folded.accepts_s2d and self._folded.s2d_channels >= 64
 
     def _s2d_buffer(self, bsz: int, device) -> torch.Tensor:
         """Persistent, zero-initialised stem-input buffer of the fused hand-off: only the rasteriser writes it (the first 48
@@ -231,8 +234,8 @@ class PosePredictor(nn.Module):
         h, w = self.render_size
         buf = getattr(self, "_s2d_buf", None)
         if buf is None or buf.shape[0] < bsz or buf.device != torch.device(device):
-            buf = torch.zeros((bsz, self._folded.s2d_channels, h // 2 + 3, w // 2 + 3), dtype=torch.bfloat16, device=device,
-                              memory_format=torch.channels_last)
+            buf = torch.empty((bsz, self._folded.s2d_channels, h // 2 + 3, w // 2 + 3), dtype=torch.bfloat16, device=device,
+                              memory_format=torch.channels_last).zero_()
             self._s2d_buf = buf
         return buf[:bsz]
 
@@ -555,7 +558,7 @@ class PosePredictor(nn.Module):
                 tap_bits=self.crop_tap_bits)
             render_start = time.time()
             z = ops.render_s2d_bf16(ctx, mesh_ids, TCO_input, K_crop, crops, self._folded.s2d_channels,
-                                    out=self._s2d_buffer(bsz, device), pad_prezeroed=self._folded.s2d_channels >= 48)
+                                    out=self._s2d_buffer(bsz, device), pad_prezeroed=True)
             render_time = time.time() - render_start
             start = time.time()
             feat = self._folded(z, packed_s2d=True)

@@ -429,7 +429,7 @@ def render_s2d_bf16(ctx: Context, mesh_ids: torch.Tensor, TCO: torch.Tensor, K: 
     channels_last = pack_input_s2d_bf16(cat(crops, rgb, normals)) without the float32 network input or the packing pass
     (hpb_render_s2d_bf16).  crops: [b,3,h,w] float32 (a contiguous tensor or the first 3 channels of a wider one), or
     [b,h,w,4] bfloat16 (crop_bf16x4).  `out`: a caller-owned result buffer; with pad_prezeroed its channels >= 48 must
-    already be zero and stay untouched by anyone else (the kernel then writes 96 B instead of 2*c_padded B per cell)."""
+    already be zero and stay untouched by anyone else (the kernel then writes only the 32 data bytes per sub-pixel)."""
     dev = ctx.device
     TCO = _f32(TCO, dev).reshape(-1, 16)
     K = _f32(K, dev).reshape(-1, 9)
@@ -455,9 +455,9 @@ def render_s2d_bf16(ctx: Context, mesh_ids: torch.Tensor, TCO: torch.Tensor, K: 
         assert tuple(out.shape) == shape and out.dtype == torch.bfloat16 and out.is_contiguous(memory_format=torch.channels_last)
     ev = None
     if _kernel_timer is not None:
-        # bytes this launch moves: the bf16 cells of the stem input it writes (96 B per cell into a pre-zeroed buffer, else
+        # bytes this launch moves: the bf16 cells of the stem input it writes (4 x 32 B per cell into a pre-zeroed buffer, else
         # the whole padded cell) + the crop it reads; fp32-equivalent = the 6 float32 planes per view of hpb_render
-        cell_bytes = 96 if pad_prezeroed else c_padded * 2
+        cell_bytes = 128 if pad_prezeroed else c_padded * 2
         ev = _kernel_timer.bracket("hpb_raster_kernel", b * ((h // 2 + 3) * (w // 2 + 3) * cell_bytes + crop_bytes),
                                    fp32_equivalent_bytes=b * 6 * h * w * 4)
         ev[0].record()

@@ -242,9 +242,10 @@ int hpb_pack_input_bf16(hpb_ctx *ctx, const float *x_dev, int64_t x_bstride, int
 /*
  * Space-to-depth variant of hpb_pack_input_bf16 for a 7x7 / stride 2 / pad 3 stem convolution (ResNet conv1,
  * torchvision_resnet.py:211): out_dev [b, H/2+3, W/2+3, C_padded] bfloat16 with
- *   out[n, I, J, (r*2+s)*C + c] = xpad[n, c, 2I+r, 2J+s],  xpad = x zero-padded by 3 pixels,  channels 4C.. zero,
- * so that conv1 becomes a 4x4 / stride 1 / unpadded convolution over 4C channels (same sums, 4x deeper reduction per
- * tap).  H and W even, C_padded >= 4C and a multiple of 8.
+ *   out[n, I, J, (r*2+s)*Cs + c] = xpad[n, c, 2I+r, 2J+s],  xpad = x zero-padded by 3 pixels,  Cs = C_padded / 4,
+ * channels c >= C of every sub-pixel block zero, so that conv1 becomes a 4x4 / stride 1 / unpadded convolution over
+ * C_padded channels (same sums, 4x deeper reduction per tap; the weight is permuted the same way).  Every sub-pixel's
+ * channel block starts on a 16-byte boundary.  H and W even, C_padded >= 4C and a multiple of 32.
  */
 int hpb_pack_input_s2d_bf16(hpb_ctx *ctx, const float *x_dev, int64_t x_bstride, int b, int C, int H, int W, void *out_dev,
                             int C_padded, void *stream);
@@ -253,16 +254,17 @@ int hpb_pack_input_s2d_bf16(hpb_ctx *ctx, const float *x_dev, int64_t x_bstride,
  * hpb_render (rgb + normals, one view per row) fused with hpb_pack_input_s2d_bf16 for the 9-channel coarse / scoring
  * network input of PosePredictor.forward_coarse (pose_rigid.py:708-788: x = cat(images_crop, renders), then the stem
  * of net_forward :352-374): renders the b scenes and writes out_dev [b, h/2+3, w/2+3, C_padded] bfloat16 with
- *   out[n, I, J, (r*2+s)*9 + c] = xpad[n, c, 2I+r, 2J+s],   xpad = zero-padded-by-3 9-channel input whose channels 0..2
- * are the crop (the output of hpb_crop / hpb_crop_bf16x4) and channels 3..8 the rendered rgb + normals; channels 36.. are
- * zero.  Bit-identical to hpb_crop -> hpb_render into x -> hpb_pack_input_s2d_bf16, without ever materialising the float32
- * network input.  h and w even, C_padded >= 40 and a multiple of 8.
+ *   out[n, I, J, (r*2+s)*Cs + c] = xpad[n, c, 2I+r, 2J+s], Cs = C_padded / 4,  xpad = zero-padded-by-3 9-channel input whose
+ * channels 0..2 are the crop (the output of hpb_crop / hpb_crop_bf16x4) and channels 3..8 the rendered rgb + normals;
+ * channels 9..Cs-1 of every sub-pixel block are zero.  Bit-identical to hpb_crop -> hpb_render into x ->
+ * hpb_pack_input_s2d_bf16, without ever materialising the float32 network input.  h and w even, C_padded a multiple of 32,
+ * >= 64.
  *   crops_format   HPB_CROPS_F32_PLANAR: crops_dev [b, 3, h, w] float32, batch stride crops_bstride floats;
  *                  HPB_CROPS_BF16X4:     crops_dev [b, h, w] pixels of 4 bfloat16 (r, g, b, 0), batch stride crops_bstride
  *                                        pixels -- hpb_crop_bf16x4's output: half the bytes, one 8-byte load per pixel
- *   pad_prezeroed  non-zero: the caller guarantees that channels >= 48 of out_dev are already zero (a persistent buffer that
- *                  only this call writes, e.g. from cudaMemset at allocation); the kernel then writes 96 bytes per cell
- *                  instead of 2 * C_padded.  Needs C_padded >= 48.
+ *   pad_prezeroed  non-zero: the caller guarantees that the padding channels 16..Cs-1 of every sub-pixel block of out_dev
+ *                  are already zero (a persistent buffer that only this call writes); the kernel then writes only the 32
+ *                  bytes per sub-pixel that carry data.  No effect for C_padded = 64 (Cs = 16: nothing to skip).
  */
 #define HPB_CROPS_F32_PLANAR 0
 #define HPB_CROPS_BF16X4 1

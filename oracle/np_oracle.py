@@ -378,8 +378,9 @@ _MV_POSITIONS = {
 }
 
 
-def make_TCO_multiview(TCO, tCR, multiview_type="TCO+front_3views", n_views=4, remove_TCO_rendering=False):
-    """multiview.py:166-251 (without views_inplane_rotations): TCV_O [b,V,4,4] in TCO's dtype."""
+def make_TCO_multiview(TCO, tCR, multiview_type="TCO+front_3views", n_views=4, remove_TCO_rendering=False,
+                       views_inplane_rotations=False):
+    """multiview.py:166-251: TCV_O [b,V,4,4] ([b,4V,4,4] with views_inplane_rotations, :239-250) in TCO's dtype."""
     TCO = np.asarray(TCO)
     tCR = np.asarray(tCR)
     b = len(TCO)
@@ -400,7 +401,19 @@ def make_TCO_multiview(TCO, tCR, multiview_type="TCO+front_3views", n_views=4, r
     Rt = np.swapaxes(TC0_CV[..., :3, :3], -1, -2)
     inv[..., :3, :3] = Rt
     inv[..., :3, 3] = -(Rt @ TC0_CV[..., :3, 3:4])[..., 0]
-    return (inv @ TCO[:, None]).astype(TCO.dtype)
+    TCV_O = (inv @ TCO[:, None]).astype(TCO.dtype)
+    if views_inplane_rotations:
+        # multiview.py:239-250: every view 4x, copies 1..3 with the ROTATION part pre-multiplied by a rotation about the
+        # camera z axis by 90 / 180 / 270 degrees (transforms3d.euler.euler2mat(0, 0, angle), cast to TCO's dtype); the
+        # translation is left as it is
+        assert remove_TCO_rendering
+        TCV_O = np.repeat(TCV_O[:, :, None], 4, axis=2)
+        for idx, angle in enumerate([np.pi / 2, np.pi, 3 * np.pi / 2]):
+            c, s = np.cos(angle), np.sin(angle)
+            dR = np.array([[c, -s, 0.0], [s, c, 0.0], [0.0, 0.0, 1.0]]).astype(TCO.dtype)
+            TCV_O[:, :, idx + 1, :3, :3] = dR @ TCV_O[:, :, idx + 1, :3, :3]
+        TCV_O = TCV_O.reshape(b, -1, 4, 4)
+    return TCV_O
 
 
 # ----------------------------------------------------------------------------------------------

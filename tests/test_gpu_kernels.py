@@ -442,6 +442,15 @@ def test_multiview_matches_oracle(ctx):
         np.testing.assert_allclose(got, ref, atol=1e-5)
     got = ops.multiview(ctx, torch.as_tensor(T), torch.as_tensor(tCR), "TCO+front_3views", 3, remove_TCO_rendering=True).cpu().numpy()
     np.testing.assert_allclose(got, O.make_TCO_multiview(T, tCR, "TCO+front_3views", 3, remove_TCO_rendering=True), atol=1e-5)
+    # the training-time option of lib3d.multiview.make_TCO_multiview (multiview.py:239-250; megapose_forward_loss.py:116-123):
+    # 26 sphere views x 4 in-plane rotations
+    from happypose_b200.lib3d.multiview import make_TCO_multiview
+
+    got = make_TCO_multiview(torch.as_tensor(T).cuda(), torch.as_tensor(tCR).cuda(), "sphere_26views", 26, remove_TCO_rendering=True,
+                             views_inplane_rotations=True).cpu().numpy()
+    ref = O.make_TCO_multiview(T, tCR, "sphere_26views", 26, remove_TCO_rendering=True, views_inplane_rotations=True)
+    assert got.shape == ref.shape == (32, 104, 4, 4)
+    np.testing.assert_allclose(got, ref, atol=1e-5)
     one = ops.multiview(ctx, torch.as_tensor(T), torch.as_tensor(tCR), "TCO+front_3views", 1).cpu().numpy()
     assert (one[:, 0] == T).all()
     bad = T.copy()
@@ -521,7 +530,7 @@ def test_pack_input_s2d_matches_torch_statement(ctx):
     from happypose_b200.megapose.fast_resnet import s2d_reference
 
     torch.manual_seed(1)
-    for C, H, W, cz in ((9, 240, 320, 64), (27, 16, 24, 128), (6, 10, 14, 24)):
+    for C, H, W, cz in ((9, 240, 320, 64), (27, 16, 24, 128), (6, 10, 14, 32), (9, 12, 16, 96)):
         x = torch.randn(2, C, H, W, device="cuda")
         got = ops.pack_input_s2d_bf16(ctx, x, cz)
         ref = s2d_reference(x, cz).to(torch.bfloat16)
@@ -550,23 +559,28 @@ def test_render_s2d_bf16_equals_render_then_pack(ctx, can):
         got = ops.render_s2d_bf16(ctx, ids, torch.as_tensor(T), torch.as_tensor(K), crops, 64)
         assert got.shape == want.shape and got.is_contiguous(memory_format=torch.channels_last)
         assert torch.equal(got.view(torch.int16), want.view(torch.int16)), f"b={b} res={res}"
-        # crops given as the first 3 channels of a wider tensor (row stride 9 planes), 40 padded channels
-        want40 = ops.pack_input_s2d_bf16(ctx, x, 40)
-        got40 = ops.render_s2d_bf16(ctx, ids, torch.as_tensor(T), torch.as_tensor(K), x[:, :3], 40)
-        assert torch.equal(got40.view(torch.int16), want40.view(torch.int16))
+        # crops given as the first 3 channels of a wider tensor (row stride 9 planes), 96 padded channels (24 per sub-pixel)
+        want96 = ops.pack_input_s2d_bf16(ctx, x, 96)
+        got96 = ops.render_s2d_bf16(ctx, ids, torch.as_tensor(T), torch.as_tensor(K), x[:, :3], 96)
+        assert torch.equal(got96.view(torch.int16), want96.view(torch.int16))
         # a second call: the visibility buffer must have been re-armed by the first
         again = ops.render_s2d_bf16(ctx, ids, torch.as_tensor(T), torch.as_tensor(K), crops, 64)
         assert torch.equal(again.view(torch.int16), want.view(torch.int16))
-        # the shipped form: crop handed over as bf16 pixels (r,g,b,0), persistent pre-zeroed output (96 B per cell written);
-        # written twice into the same buffer with different crops to show that nothing stale survives
+        # the shipped form: crop handed over as bf16 pixels (r,g,b,0), persistent pre-zeroed output; written twice into the
+        # same buffer with different crops to show that nothing stale survives (also with 128 padded channels, where the
+        # kernel really skips the padding groups)
         crops_h = torch.zeros((b, *res, 4), dtype=torch.bfloat16, device="cuda")
         crops_h[..., :3] = crops.permute(0, 2, 3, 1).to(torch.bfloat16)
-        buf = torch.zeros((b + 2, 64, res[0] // 2 + 3, res[1] // 2 + 3), dtype=torch.bfloat16, device="cuda", memory_format=torch.channels_last)
+        buf = torch.empty((b + 2, 64, res[0] // 2 + 3, res[1] // 2 + 3), dtype=torch.bfloat16, device="cuda", memory_format=torch.channels_last).zero_()
         ops.render_s2d_bf16(ctx, ids, torch.as_tensor(T), torch.as_tensor(K), torch.flip(crops_h, (1,)).contiguous(), 64, out=buf[:b], pad_prezeroed=True)
         got_h = ops.render_s2d_bf16(ctx, ids, torch.as_tensor(T), torch.as_tensor(K), crops_h, 64, out=buf[:b], pad_prezeroed=True)
         assert got_h.data_ptr() == buf.data_ptr()
         assert torch.equal(got_h.view(torch.int16), want.view(torch.int16)), f"bf16x4 / pre-zeroed, b={b} res={res}"
         assert not buf[b:].any()
+        buf128 = torch.empty((b, 128, res[0] // 2 + 3, res[1] // 2 + 3), dtype=torch.bfloat16, device="cuda", memory_format=torch.channels_last).zero_()
+        ops.render_s2d_bf16(ctx, ids, torch.as_tensor(T), torch.as_tensor(K), torch.flip(crops_h, (1,)).contiguous(), 128, out=buf128, pad_prezeroed=True)
+        got128 = ops.render_s2d_bf16(ctx, ids, torch.as_tensor(T), torch.as_tensor(K), crops_h, 128, out=buf128, pad_prezeroed=True)
+        assert torch.equal(got128.view(torch.int16), ops.pack_input_s2d_bf16(ctx, x, 128).view(torch.int16))
 
 
 def test_crop_bf16x4_is_the_rounded_float32_crop(ctx, can):
