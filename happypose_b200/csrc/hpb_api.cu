@@ -33,6 +33,10 @@ int hpb_launch_normalize_depth(hpb_ctx *ctx, float *depth, int64_t bstride, cons
 int hpb_launch_topk(hpb_ctx *ctx, const float *scores, const int32_t *groups, int n, int n_groups, int K,
                     int64_t *out_idx, int32_t *out_count, cudaStream_t stream);
 
+int hpb_launch_icp_points(hpb_ctx *ctx, const float *depth_measured, int n_im, const float *depth_rendered, const uint8_t *masks,
+                          const int32_t *im_ids, const float *K, int N, int H, int W, float delta, int64_t cap, float *pts_tgt,
+                          float *pts_src, int32_t *counts, uint8_t *mask_out, int32_t *idx_tgt, int32_t *idx_src, cudaStream_t stream);
+
 static thread_local char g_err[512] = "";
 
 int hpb_ws_grow(hpb_ctx *ctx, void **ptr, size_t *cur_bytes, size_t need, cudaStream_t stream, const char *what) {
@@ -619,6 +623,20 @@ int hpb_topk_segmented(hpb_ctx *ctx, const float *scores_dev, const int32_t *gro
     HPB_REQUIRE(n == 0 || (scores_dev && group_ids_dev && out_idx_dev), "NULL pointer");
     HpbDeviceGuard guard(ctx->device);
     return hpb_launch_topk(ctx, scores_dev, group_ids_dev, n, n_groups, K, out_idx_dev, out_count_dev, (cudaStream_t)stream);
+}
+
+int hpb_icp_points(hpb_ctx *ctx, const float *depth_measured_dev, int n_im, const float *depth_rendered_dev,
+                   const uint8_t *masks_dev, const int32_t *im_ids_dev, const float *K_dev, int N, int H, int W,
+                   float depth_delta_thresh, int64_t capacity, float *points_tgt_dev, float *points_src_dev,
+                   int32_t *counts_dev, uint8_t *mask_out_dev, int32_t *index_tgt_dev, int32_t *index_src_dev, void *stream) {
+    HPB_REQUIRE(ctx && N >= 0 && n_im > 0 && H > 0 && W > 0 && capacity > 0, "bad argument");
+    if (N == 0) return HPB_OK;
+    HPB_REQUIRE(depth_measured_dev && depth_rendered_dev && im_ids_dev && K_dev, "NULL input");
+    HPB_REQUIRE(points_tgt_dev && points_src_dev && counts_dev, "NULL output");
+    HpbDeviceGuard guard(ctx->device);
+    return hpb_launch_icp_points(ctx, depth_measured_dev, n_im, depth_rendered_dev, masks_dev, im_ids_dev, K_dev, N, H, W,
+                                 depth_delta_thresh, capacity, points_tgt_dev, points_src_dev, counts_dev, mask_out_dev,
+                                 index_tgt_dev, index_src_dev, (cudaStream_t)stream);
 }
 
 int hpb_pack_input_bf16(hpb_ctx *ctx, const float *x_dev, int64_t x_bstride, int b, int C, int h, int w, void *out_dev,

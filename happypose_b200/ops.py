@@ -480,6 +480,55 @@ def maxpool3x3s2_bf16(ctx: Context, x: torch.Tensor) -> torch.Tensor:
 
 
 # ------------------------------------------------------------------------------------------------
+# ICP depth refiner, input stage
+# ------------------------------------------------------------------------------------------------
+def icp_points(ctx: Context, depth_measured, depth_rendered, im_ids, K, masks=None, depth_delta_thresh: float = 0.1,
+               capacity: Optional[int] = None, return_mask: bool = False, return_index: bool = False):
+    """Masks and point clouds of icp_refinement (icp_refiner.py:138-176) for N pose estimates in one launch.
+    depth_measured [n_im,H,W], depth_rendered [N,H,W] (or [N,1,H,W]), im_ids [N], K [N,3,3], masks [n_im,H,W] bool/uint8 or
+    None (threshold mask).  Returns (points_tgt [N,cap,3], points_src [N,cap,3], counts [N,2] int32[, mask [N,H,W] bool]
+    [, index_tgt [N,cap] int32, index_src [N,cap] int32 = linear pixel index of every point]); rows beyond counts are
+    undefined.  Nothing synchronises: read `counts` when you need the sizes."""
+    dev = ctx.device
+    dm = _f32(depth_measured, dev)
+    if dm.dim() == 4:
+        dm = dm[:, 0]
+    dr = _f32(depth_rendered, dev)
+    if dr.dim() == 4:
+        dr = dr[:, 0]
+    dm, dr = dm.contiguous(), dr.contiguous()
+    n_im, H, W = dm.shape
+    N = dr.shape[0]
+    assert tuple(dr.shape[1:]) == (H, W), "rendered and measured depth maps must have the same resolution"
+    im_ids = _i32(im_ids, dev)
+    K = _f32(K, dev).reshape(-1, 9)
+    assert im_ids.numel() == N and K.shape[0] == N
+    mk = None
+    if masks is not None:
+        mk = torch.as_tensor(masks).to(device=dev)
+        if mk.dim() == 4:
+            mk = mk[:, 0]
+        mk = mk.to(torch.uint8).contiguous()
+        assert tuple(mk.shape) == (n_im, H, W)
+    cap = int(capacity) if capacity is not None else H * W
+    pt = torch.empty((N, cap, 3), dtype=torch.float32, device=dev)
+    ps = torch.empty((N, cap, 3), dtype=torch.float32, device=dev)
+    counts = torch.zeros((N, 2), dtype=torch.int32, device=dev)
+    mo = torch.empty((N, H, W), dtype=torch.uint8, device=dev) if return_mask else None
+    it = torch.empty((N, cap), dtype=torch.int32, device=dev) if return_index else None
+    isrc = torch.empty((N, cap), dtype=torch.int32, device=dev) if return_index else None
+    rc = ctx.lib.hpb_icp_points(ctx.handle, ptr(dm), n_im, ptr(dr), ptr(mk), ptr(im_ids), ptr(K), N, H, W, float(depth_delta_thresh), cap,
+                                ptr(pt), ptr(ps), ptr(counts), ptr(mo), ptr(it), ptr(isrc), stream_ptr(dev))
+    ctx.check(rc, "hpb_icp_points")
+    out = (pt, ps, counts)
+    if return_mask:
+        out += (mo.bool(),)
+    if return_index:
+        out += (it, isrc)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
 # top-K
 # ------------------------------------------------------------------------------------------------
 def topk_segmented(ctx: Context, scores, group_ids, n_groups: int, K: int, expected_count: Optional[int] = None) -> torch.Tensor:

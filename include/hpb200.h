@@ -29,6 +29,7 @@
  *   hpb_multiview         toolbox/lib3d/multiview.py:28-92,166-251
  *   hpb_topk_segmented    toolbox/utils/tensor_collection.py:201-230 (filter_top_pose_estimates)
  *   hpb_normalize_depth   pose_rigid.py:455-544
+ *   hpb_icp_points        megapose/inference/icp_refiner.py:138-176,271-289 + refiner_utils.py (compute_masks)
  */
 #ifndef HPB200_H
 #define HPB200_H
@@ -272,6 +273,26 @@ int hpb_render_s2d_bf16(hpb_ctx *ctx, const int32_t *mesh_ids_dev, const float *
                         const float *ambient_dev, int b, int h, int w, float z_near, float z_far, const void *crops_dev,
                         int64_t crops_bstride, int crops_format, void *out_dev, int C_padded, int pad_prezeroed,
                         void *stream);
+
+/*
+ * Input stage of the ICP depth refiner (megapose/inference/icp_refiner.py:138-176, 271-289; refiner_utils.py compute_masks):
+ * for each of N pose estimates, from the measured depth map of its frame and its rendered depth map (hpb_render with
+ * HPB_RENDER_DEPTH at frame resolution), the mask and the two point clouds the reference extracts on the host:
+ *   mask    masks_dev[im] when given (uint8 [n_im,H,W]), else the "threshold" mask: measured > 0, rendered > 0,
+ *           |measured - rendered| <= depth_delta_thresh
+ *   target  (u * d / fx, v * d / fy, d) of the MEASURED depth where 0.2 < d < 5 inside the mask
+ *   source  the same of the RENDERED depth at those pixels where rendered > 0
+ * with u, v = (x - cx), (y - cy) truncated to int16 (getXYZ keeps them in an int16 table, :107-110).  Points come out in
+ * row-major pixel order.  points_*_dev [N, capacity, 3] float32; counts_dev [N, 2] int32 = (n_target, n_source), the true
+ * counts even when they exceed `capacity` (points beyond it are dropped).  mask_out_dev [N,H,W] uint8 or NULL;
+ * index_tgt_dev / index_src_dev [N, capacity] int32 or NULL: the linear pixel index y * W + x of every emitted point (the
+ * caller gathers its host-side normal maps with them).
+ * depth_measured_dev [n_im,H,W], depth_rendered_dev [N,H,W], im_ids_dev [N], K_dev [N,9].
+ */
+int hpb_icp_points(hpb_ctx *ctx, const float *depth_measured_dev, int n_im, const float *depth_rendered_dev,
+                   const uint8_t *masks_dev, const int32_t *im_ids_dev, const float *K_dev, int N, int H, int W,
+                   float depth_delta_thresh, int64_t capacity, float *points_tgt_dev, float *points_src_dev,
+                   int32_t *counts_dev, uint8_t *mask_out_dev, int32_t *index_tgt_dev, int32_t *index_src_dev, void *stream);
 
 /*
  * nn.MaxPool2d(kernel_size=3, stride=2, padding=1) of the ResNet stem (torchvision_resnet.py:215) on bfloat16

@@ -489,3 +489,41 @@ def normalize_depth(depth, tCR_z, kind):
     if kind == "none":
         return depth
     raise ValueError(kind)
+
+
+# ----------------------------------------------------------------------------------------------
+# megapose/inference/icp_refiner.py (input stage of the ICP depth refiner), refiner_utils.py
+# ----------------------------------------------------------------------------------------------
+def icp_get_xyz(depth, fx, fy, cx, cy):
+    """icp_refiner.py:106-135 (getXYZ, whole image): the pixel offsets live in an int16 table, so (x - cx) and (y - cy)
+    are TRUNCATED towards zero before use; x = u * depth * 1 / fx evaluated left to right in float32."""
+    depth = np.asarray(depth, F32)
+    H, W = depth.shape
+    u = (np.arange(W) - np.float64(cx)).astype(np.int16)
+    v = (np.arange(H) - np.float64(cy)).astype(np.int16)
+    xyz = np.zeros((H, W, 3), np.float64)
+    xyz[:, :, 0] = u[None, :] * depth * 1 / F32(fx)
+    xyz[:, :, 1] = v[:, None] * depth * 1 / F32(fy)
+    xyz[:, :, 2] = depth
+    return xyz.astype(F32)
+
+
+def icp_compute_masks(depth_rendered, depth_measured, depth_delta_thresh=0.1):
+    """refiner_utils.py compute_masks(mask_type="threshold"): measured > 0, rendered > 0, |measured - rendered| <= thresh."""
+    m = np.logical_and(depth_measured > 0, depth_rendered > 0)
+    m[np.abs(depth_measured - depth_rendered) > depth_delta_thresh] = False
+    return m
+
+
+def icp_input_points(depth_measured, depth_rendered, K, mask=None, depth_delta_thresh=0.1):
+    """icp_refinement (icp_refiner.py:138-176) up to the ICP call: (points_tgt [n_t,3], points_src [n_s,3]) in row-major
+    pixel order.  Target = measured points with 0.2 < d < 5 inside the mask; source = rendered points at the same pixels
+    where something was rendered."""
+    dm, dr = np.asarray(depth_measured, F32), np.asarray(depth_rendered, F32)
+    if mask is None:
+        mask = icp_compute_masks(dr, dm, depth_delta_thresh)
+    K = np.asarray(K, F32)
+    valid = np.logical_and(np.logical_and(dm > 0.2, dm < 5), mask)
+    pt = icp_get_xyz(dm, K[0, 0], K[1, 1], K[0, 2], K[1, 2])[valid]
+    ps = icp_get_xyz(dr, K[0, 0], K[1, 1], K[0, 2], K[1, 2])[np.logical_and(valid, dr > 0)]
+    return pt, ps

@@ -157,3 +157,15 @@ def test_multiview_invariants():
     bad[0, 0, 0] = np.nan
     out = O.make_TCO_multiview(bad, tCR, "TCO+front_3views", n_views=4)
     assert np.isfinite(out[1:]).all()
+
+
+def test_icp_input_points_match_reference(golden):
+    """ref_icp.npz: getXYZ / compute_masks / the validity rules of icp_refinement, run from the reference's own source
+    (tests/golden/generate_golden_icp.py)."""
+    g = golden("ref_icp.npz")
+    for case in (0, 1):
+        dm, dr, K = g[f"depth_measured{case}"], g[f"depth_rendered{case}"], g[f"K{case}"]
+        np.testing.assert_array_equal(O.icp_compute_masks(dr, dm, 0.1), g[f"mask{case}"])
+        pt, ps = O.icp_input_points(dm, dr, K)
+        np.testing.assert_array_equal(pt, g[f"points_tgt{case}"])
+        np.testing.assert_array_equal(ps, g[f"points_src{case}"])
