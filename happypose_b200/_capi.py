@@ -39,7 +39,8 @@ SIGNATURES = {
     "hpb_mesh_closed_sign": (c_int, [c_void_p, c_int32, ctypes.POINTER(c_int)]),
     "hpb_mesh_set_cull": (c_int, [c_void_p, c_int32, c_int]),
     "hpb_render": (c_int, [c_void_p] * 5 + [c_int, c_int, c_int, c_float, c_float, c_uint32,
-                           c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int64, c_void_p]),
+                           c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int, c_int64, c_void_p, c_int,
+                           c_void_p]),
     "hpb_crop": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p,
                          c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_int64, c_void_p,
                          c_void_p, c_void_p, c_int, c_void_p]),

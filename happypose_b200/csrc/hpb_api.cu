@@ -423,7 +423,7 @@ int hpb_render(hpb_ctx *ctx, const int32_t *mesh_ids_dev, const float *TCO_dev, 
                const float *ambient_dev, int b, int h, int w, float z_near, float z_far, uint32_t flags,
                float *rgb_dev, int64_t rgb_bstride, float *normals_dev, int64_t normals_bstride, float *depth_dev,
                int64_t depth_bstride, uint8_t *mask_dev, int64_t mask_bstride, int views, int64_t view_stride,
-               void *stream) {
+               const float *lights_dev, int n_lights, void *stream) {
     HPB_REQUIRE(ctx, "NULL ctx");
     HPB_REQUIRE(b >= 0 && h > 0 && w > 0 && (long long)h * w < (1ll << 30), "bad batch / resolution");
     HPB_REQUIRE(views >= 1 && b % views == 0, "b must be a multiple of views");
@@ -436,10 +436,13 @@ int hpb_render(hpb_ctx *ctx, const int32_t *mesh_ids_dev, const float *TCO_dev, 
     HPB_REQUIRE(!(flags & HPB_RENDER_DEPTH) || depth_dev, "depth requested but NULL");
     HPB_REQUIRE(!(flags & HPB_RENDER_MASK) || mask_dev, "mask requested but NULL");
     HPB_REQUIRE(flags != 0, "nothing to render");
+    HPB_REQUIRE(n_lights >= 0 && n_lights <= HPB_MAX_LIGHTS, "at most 8 point / directional lights per scene");
+    HPB_REQUIRE(n_lights == 0 || lights_dev, "lights_dev is NULL");
     HpbDeviceGuard guard(ctx->device);
     return hpb_launch_raster(ctx, mesh_ids_dev, TCO_dev, K_dev, ambient_dev, b, h, w, z_near, z_far, flags, rgb_dev,
                              rgb_bstride, normals_dev, normals_bstride, depth_dev, depth_bstride, mask_dev,
-                             mask_bstride, views, view_stride, (cudaStream_t)stream);
+                             mask_bstride, views, view_stride, (cudaStream_t)stream, nullptr, 0, nullptr, 0, 0, 0, lights_dev,
+                             n_lights);
 }
 
 int hpb_render_s2d_bf16(hpb_ctx *ctx, const int32_t *mesh_ids_dev, const float *TCO_dev, const float *K_dev,

@@ -8,6 +8,7 @@
 #include "../../include/hpb200.h"
 
 #define HPB_MAX_MIPS 16
+#define HPB_MAX_LIGHTS 8
 #define HPB_SUBPIX_BITS 8
 #define HPB_SUBPIX 256
 #define HPB_GUARD 4194304.0f  // 2^22 fixed-point units (16384 px) guard band for snapped vertices
@@ -125,6 +126,7 @@ int hpb_launch_raster(hpb_ctx *ctx, const int32_t *mesh_ids, const float *TCO, c
                       int b, int h, int w, float z_near, float z_far, uint32_t flags, float *rgb, int64_t rgb_bs,
                       float *nrm, int64_t nrm_bs, float *depth, int64_t depth_bs, uint8_t *mask, int64_t mask_bs,
                       int views, int64_t view_stride, cudaStream_t stream, const void *crops = nullptr,
-                      int64_t crops_bs = 0, void *s2d_out = nullptr, int Cz = 0, int crops_fmt = 0, int pad_prezeroed = 0);
+                      int64_t crops_bs = 0, void *s2d_out = nullptr, int Cz = 0, int crops_fmt = 0, int pad_prezeroed = 0,
+                      const float *lights = nullptr, int n_lights = 0);
 int hpb_launch_mip(const uchar4 *src, int sw, int sh, uchar4 *dst, int dw, int dh, cudaStream_t stream);
 int hpb_launch_tex_expand(const uint8_t *src, int n, int c, uchar4 *dst, cudaStream_t stream);

@@ -54,6 +54,8 @@ struct RasterParams {
     const float *TCO;
     const float *K;
     const float *ambient;
+    const float *lights;  // [b][n_lights][8]: (type 0 point / 1 directional, x, y, z in the OBJECT = world frame, r, g, b, -) or nullptr
+    int n_lights;
     int b, h, w;
     float z_near;
     float inv_near, cd, a_f, b_f, eps_hi;
@@ -317,13 +319,16 @@ __device__ unsigned long long g_phase_clk[8];
 
 // S2D = false: planar float32 outputs (hpb_render); true: bf16 space-to-depth network input (hpb_render_s2d_bf16).  Two
 // instantiations so that the packed-output state of the second does not cost the first any registers.
-template <bool S2D>
+// LIT: per-pixel Lambert shading by point / directional lights (the render_normals=False light rig of
+// megapose/models/pose_rigid.py:105-141,421-422); a separate instantiation, so the hot path carries none of its registers.
+template <bool S2D, bool LIT>
 __global__ void __launch_bounds__(RASTER_THREADS, 1) hpb_raster_kernel(const RasterParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ HpbMeshDev sM;
     __shared__ float sT[16];
     __shared__ float sK[4];
     __shared__ float sAmb[3];
+    __shared__ float sLight[HPB_MAX_LIGHTS][8];  // LIT: (type, position or direction in the CAMERA frame, colour)
     __shared__ int sFinite;
     __shared__ int sClipped;
     __shared__ int sBox[4];  // min x, min y, max x, max y of the snapped vertices (fixed point)
@@ -372,11 +377,22 @@ __global__ void __launch_bounds__(RASTER_THREADS, 1) hpb_raster_kernel(const Ras
             else if (tid == 21) sK[3] = v;  // cy
         } else if (tid < 28) {
             float a = p.ambient ? p.ambient[(size_t)hyp * 3 + (tid - 25)] : 1.0f;
-            if (a > 1.0f) a = 1.0f;
+            if (!LIT && a > 1.0f) a = 1.0f;  // with lights the sum of all contributions is clamped per pixel instead
             if (!(a > 0.0f)) a = 0.0f;
             sAmb[tid - 25] = a;
         }
         __syncthreads();
+        if (LIT && tid < p.n_lights) {  // lights are placed in the world (= object) frame: move them into the camera frame
+            const float *L = p.lights + ((size_t)hyp * p.n_lights + tid) * 8;
+            const float x = L[1], y = L[2], z = L[3];
+            const bool dir = L[0] != 0.0f;
+            float cx3 = fmaf(sT[2], z, fmaf(sT[1], y, sT[0] * x)), cy3 = fmaf(sT[6], z, fmaf(sT[5], y, sT[4] * x));
+            float cz3 = fmaf(sT[10], z, fmaf(sT[9], y, sT[8] * x));
+            if (!dir) { cx3 = cx3 + sT[3]; cy3 = cy3 + sT[7]; cz3 = cz3 + sT[11]; }
+            sLight[tid][0] = L[0]; sLight[tid][1] = cx3; sLight[tid][2] = cy3; sLight[tid][3] = cz3;
+            sLight[tid][4] = L[4]; sLight[tid][5] = L[5]; sLight[tid][6] = L[6]; sLight[tid][7] = 0.0f;
+        }
+        if (LIT) __syncthreads();
         HPB_PHASE_MARK(0)  // scene set-up
         const bool finite = sFinite != 0;
         const HpbMeshDev &m = sM;
@@ -556,7 +572,8 @@ __global__ void __launch_bounds__(RASTER_THREADS, 1) hpb_raster_kernel(const Ras
                     if (d > p.eps_hi) z = 0.0f;
                 }
                 const float4 A0 = __ldg(m.nu + f.x), A1 = __ldg(m.nu + f.y), A2 = __ldg(m.nu + f.z);
-                if (do_nrm) {
+                float lit0 = sAmb[0], lit1 = sAmb[1], lit2 = sAmb[2];
+                if (do_nrm || LIT) {
                     // object-space normal interpolated over the triangle, rotated into the eye frame, normalised once
                     const float ox = fmaf(p2, A2.x, fmaf(p1, A1.x, p0 * A0.x));
                     const float oy = fmaf(p2, A2.y, fmaf(p1, A1.y, p0 * A0.y));
@@ -569,9 +586,36 @@ __global__ void __launch_bounds__(RASTER_THREADS, 1) hpb_raster_kernel(const Ras
                         const float rl = __frcp_rn(__fsqrt_rn(len2));
                         nx *= rl; ny *= rl; nz *= rl;
                     }
-                    n0 = encode_normal(nx, sNrmTab, sLut);
-                    n1 = encode_normal(nz, sNrmTab, sLut);
-                    n2 = encode_normal(-ny, sNrmTab, sLut);
+                    if (do_nrm) {
+                        n0 = encode_normal(nx, sNrmTab, sLut);
+                        n1 = encode_normal(nz, sNrmTab, sLut);
+                        n2 = encode_normal(-ny, sNrmTab, sLut);
+                    }
+                    if (LIT) {
+                        // surface point in the camera frame from the pixel centre and the metric depth of the winning fragment
+                        const float dk = __uint_as_float((unsigned)(key >> 32));
+                        const float zc = p.a_f / (dk - p.b_f);
+                        const float X = (((float)px + 0.5f) - sK[2]) / sK[0] * zc, Y = (((float)py + 0.5f) - sK[3]) / sK[1] * zc;
+                        for (int li = 0; li < p.n_lights; ++li) {
+                            float ndl;
+                            if (sLight[li][0] != 0.0f) {  // directional: light travels along (x,y,z)
+                                ndl = -fmaf(nz, sLight[li][3], fmaf(ny, sLight[li][2], nx * sLight[li][1]));
+                            } else {
+                                const float lx = sLight[li][1] - X, ly = sLight[li][2] - Y, lz = sLight[li][3] - zc;
+                                const float l2 = fmaf(lz, lz, fmaf(ly, ly, lx * lx));
+                                ndl = fmaf(nz, lz, fmaf(ny, ly, nx * lx));
+                                if (l2 > 0.0f) ndl = ndl * __frcp_rn(__fsqrt_rn(l2));
+                            }
+                            if (ndl > 0.0f) {
+                                lit0 = fmaf(ndl, sLight[li][4], lit0);
+                                lit1 = fmaf(ndl, sLight[li][5], lit1);
+                                lit2 = fmaf(ndl, sLight[li][6], lit2);
+                            }
+                        }
+                        if (lit0 > 1.0f) lit0 = 1.0f;
+                        if (lit1 > 1.0f) lit1 = 1.0f;
+                        if (lit2 > 1.0f) lit2 = 1.0f;
+                    }
                 }
                 if (do_rgb) {
                     float3 col = make_float3(255.0f, 255.0f, 255.0f);
@@ -602,9 +646,9 @@ __global__ void __launch_bounds__(RASTER_THREADS, 1) hpb_raster_kernel(const Ras
                         col.y = fmaf(p2, (float)c2.y, fmaf(p1, (float)c1.y, p0 * (float)c0.y));
                         col.z = fmaf(p2, (float)c2.z, fmaf(p1, (float)c1.z, p0 * (float)c0.z));
                     }
-                    r = quant8(col.x * sAmb[0], sLut);
-                    g = quant8(col.y * sAmb[1], sLut);
-                    bl = quant8(col.z * sAmb[2], sLut);
+                    r = quant8(col.x * lit0, sLut);
+                    g = quant8(col.y * lit1, sLut);
+                    bl = quant8(col.z * lit2, sLut);
                 }
             }
         };
@@ -811,7 +855,7 @@ int hpb_launch_raster(hpb_ctx *ctx, const int32_t *mesh_ids, const float *TCO, c
                       int b, int h, int w, float z_near, float z_far, uint32_t flags, float *rgb, int64_t rgb_bs,
                       float *nrm, int64_t nrm_bs, float *depth, int64_t depth_bs, uint8_t *mask, int64_t mask_bs,
                       int views, int64_t view_stride, cudaStream_t stream, const void *crops, int64_t crops_bs,
-                      void *s2d_out, int Cz, int crops_fmt, int pad_prezeroed) {
+                      void *s2d_out, int Cz, int crops_fmt, int pad_prezeroed, const float *lights, int n_lights) {
     if (b == 0) return HPB_OK;
     const int npix = h * w;
     const int nv_pad = (ctx->max_nv + 1) & ~1;  // keeps the int2 array 8-byte aligned in every CTA's slice
@@ -819,20 +863,23 @@ int hpb_launch_raster(hpb_ctx *ctx, const int32_t *mesh_ids, const float *TCO, c
     static size_t static_smem = 0;  // the kernel's own __shared__ variables count against the per-block opt-in limit
     if (static_smem == 0) {
         cudaFuncAttributes fa;
-        HPB_CUDA_OK(cudaFuncGetAttributes(&fa, hpb_raster_kernel<false>));
+        HPB_CUDA_OK(cudaFuncGetAttributes(&fa, hpb_raster_kernel<false, true>));
         static_smem = fa.sharedSizeBytes + 256;
     }
     const size_t smem_cap = (size_t)ctx->max_smem_optin > static_smem ? (size_t)ctx->max_smem_optin - static_smem : 0;
     const int verts_in_smem = smem_need <= smem_cap;
     // when some mesh does not fit, the others still use as much shared memory as there is (per-scene choice in the kernel)
     const size_t smem = verts_in_smem ? smem_need : (smem_cap / 24) * 24;
-    void (*kern)(const RasterParams) = s2d_out ? hpb_raster_kernel<true> : hpb_raster_kernel<false>;
-    // both instantiations get the attribute: the cluster-occupancy query below is made on <false> whichever runs first
-    HPB_CUDA_OK(cudaFuncSetAttribute(hpb_raster_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    HPB_CUDA_OK(cudaFuncSetAttribute(hpb_raster_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const bool lit = lights != nullptr && n_lights > 0;
+    void (*kern)(const RasterParams) = s2d_out ? hpb_raster_kernel<true, false> : (lit ? hpb_raster_kernel<false, true> : hpb_raster_kernel<false, false>);
+    // all instantiations get the attribute: the cluster-occupancy query below is made on <false,false> whichever runs first
+    HPB_CUDA_OK(cudaFuncSetAttribute(hpb_raster_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    HPB_CUDA_OK(cudaFuncSetAttribute(hpb_raster_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    HPB_CUDA_OK(cudaFuncSetAttribute(hpb_raster_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // clusters of 16 CTAs (non-portable size) for the smallest batches: a 4-view refiner launch then spreads over 64 SMs
-    static bool np_ok = cudaFuncSetAttribute(hpb_raster_kernel<false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
-                        cudaFuncSetAttribute(hpb_raster_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
+    static bool np_ok = cudaFuncSetAttribute(hpb_raster_kernel<false, false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
+                        cudaFuncSetAttribute(hpb_raster_kernel<false, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
+                        cudaFuncSetAttribute(hpb_raster_kernel<true, false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
     if (!np_ok) cudaGetLastError();
 
     // how many clusters of 1/2/4/8 CTAs can be co-resident (one CTA per SM); queried once per shared-memory size
@@ -851,7 +898,7 @@ int hpb_launch_raster(hpb_ctx *ctx, const int32_t *mesh_ids, const float *TCO, c
             int n = 0;
             if (G == 1) n = ctx->sm_count;
             else if (G == 16 && !np_ok) n = 0;
-            else if (cudaOccupancyMaxActiveClusters(&n, hpb_raster_kernel<false>, &cfg) != cudaSuccess) { n = 0; cudaGetLastError(); }
+            else if (cudaOccupancyMaxActiveClusters(&n, hpb_raster_kernel<false, true>, &cfg) != cudaSuccess) { n = 0; cudaGetLastError(); }
             ctx->max_clusters[k] = n;
         }
         ctx->max_clusters_smem = smem;
@@ -886,6 +933,8 @@ int hpb_launch_raster(hpb_ctx *ctx, const int32_t *mesh_ids, const float *TCO, c
     p.TCO = TCO;
     p.K = K;
     p.ambient = ambient;
+    p.lights = lit ? lights : nullptr;
+    p.n_lights = lit ? n_lights : 0;
     p.b = b; p.h = h; p.w = w;
     p.z_near = z_near;
     p.inv_near = 1.0f / z_near;

@@ -329,24 +329,24 @@ class PosePredictor(nn.Module):
         n_views = TCV_O.shape[1]
         assert isinstance(self.renderer, Panda3dBatchRenderer)
         device = TCV_O.device
-        ambient = None
-        if random_ambient_light:
-            inten = np.random.uniform(0.7, 1.0, size=(bsz * n_views, 1)).astype(np.float32)
-            ambient = torch.as_tensor(np.repeat(inten, 3, 1)).to(device)
-        elif not self.render_normals:
-            raise NotImplementedError(
-                "render_normals=False selects make_scene_lights() (1 ambient + 6 point lights, pose_rigid.py:421-422); "
-                "point lights are not evaluated by the CUDA rasteriser")
+        ambient = lights = None
         if mesh_ids is None:
             mesh_ids = self.renderer.mesh_ids(labels)
         if not mesh_ids_per_view:
             mesh_ids = mesh_ids.repeat_interleave(n_views) if n_views > 1 else mesh_ids
+        if random_ambient_light:
+            inten = np.random.uniform(0.7, 1.0, size=(bsz * n_views, 1)).astype(np.float32)
+            ambient = torch.as_tensor(np.repeat(inten, 3, 1)).to(device)
+        elif not self.render_normals:
+            # make_scene_lights() (pose_rigid.py:421-422): ambient 0.1 + six point lights 0.4 at +-10 bounding radii
+            lights = self.renderer.scene_light_rig(mesh_ids)
+            ambient = torch.full((bsz * n_views, 3), 0.1, dtype=torch.float32, device=device)
         C_in = self.n_input_channels
         if out is None:
             out = torch.empty((bsz, C_in + n_views * self._n_single_render_channels) + tuple(self.render_size), dtype=torch.float32, device=device)
         self.renderer.render_into(
             mesh_ids, TCV_O.flatten(0, 1), KV.flatten(0, 1), self.render_size, out, C_in,
-            render_normals=self.render_normals, render_depth=self.render_depth, views=n_views, ambient=ambient)
+            render_normals=self.render_normals, render_depth=self.render_depth, views=n_views, ambient=ambient, lights=lights)
         return out[:, C_in:]
 
     # ---- depth normalisation -------------------------------------------------------------------

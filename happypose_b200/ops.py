@@ -145,8 +145,12 @@ def render(
     out: Optional[torch.Tensor] = None,
     out_channel_offset: int = 0,
     views: int = 1,
+    lights: Optional[torch.Tensor] = None,
 ):
     """Renders b scenes.  Returns (rgb, normals, depth, mask) tensors (None when not requested).
+
+    lights: [b, n_lights, 8] float32 (type 0 point / 1 directional, xyz in the object = world frame, rgb, -): per-pixel Lambert
+    shading on top of the ambient term (hpb_render's lights_dev); None = ambient only (the hot path).
 
     If `out` ([b, C_total, h, w] float32, contiguous) is given, rgb / normals / depth are written into consecutive
     channels of `out` starting at `out_channel_offset` (rgb 3, then normals 3, then depth 1) and the returned
@@ -164,6 +168,11 @@ def render(
     mesh_ids = _i32(mesh_ids, dev)
     assert mesh_ids.numel() == b, "Need same number of labels as TCO/K batch size"
     amb = None if ambient is None else _f32(ambient, dev).reshape(b, 3)
+    lts, n_lights = None, 0
+    if lights is not None and lights.numel() > 0:
+        lts = _f32(lights, dev)
+        assert lts.dim() == 3 and lts.shape[0] == b and lts.shape[2] == 8 and lts.shape[1] <= 8, "lights must be [b, n<=8, 8]"
+        n_lights = lts.shape[1]
     flags = (1 if render_rgb else 0) | (2 if render_normals else 0) | (4 if render_depth else 0) | (8 if render_binary_mask else 0)
     rgb = nrm = dep = msk = None
     view_stride = 0
@@ -201,7 +210,7 @@ def render(
         rc = ctx.lib.hpb_render(
             ctx.handle, ptr(mesh_ids), ptr(TCO), ptr(K), ptr(amb), b, h, w, z_near, z_far, flags,
             ptr(rgb), strides[0], ptr(nrm), strides[1], ptr(dep), strides[2], ptr(msk), h * w,
-            views, view_stride if views > 1 else 0, stream_ptr(dev))
+            views, view_stride if views > 1 else 0, ptr(lts), n_lights, stream_ptr(dev))
         if ev is not None:
             ev[1].record()
         ctx.check(rc, "hpb_render")

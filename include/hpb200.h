@@ -136,6 +136,13 @@ int hpb_mesh_set_cull(hpb_ctx *ctx, int32_t mesh_id, int enable);
  * Batched rasteriser: renders b single-object scenes in ONE launch.
  *   mesh_ids_dev [b] int32, TCO_dev [b,16], K_dev [b,9] float32 (device)
  *   ambient_dev  [b,3] summed ambient light colour per scene, or NULL (= 1,1,1)
+ *   lights_dev   [b, n_lights, 8] float32 or NULL (n_lights = 0): point / directional lights of each scene,
+ *                (type 0 = point | 1 = directional, x, y, z, r, g, b, unused): a point light's POSITION, a directional
+ *                light's DIRECTION of travel, in the world frame (= the object frame: the reference renders the object at
+ *                the identity and moves the camera, panda3d_batch_renderer.py:144-192).  n_lights <= 8.  Shading is
+ *                per-pixel Lambert without attenuation, colour = albedo * min(1, ambient + sum_i c_i * max(0, n . l_i)) with n
+ *                the unit eye-space normal: the render_normals=False light rig of pose_rigid.py:105-141,421-422
+ *                (1 ambient 0.1 + 6 point lights 0.4 at +-10 bounding radii, panda3d_scene_renderer.py:105-141).
  *   flags        HPB_RENDER_* ; outputs not selected may be NULL
  *   rgb/normals  [b,3,h,w] float32 in {k/255};  depth [b,1,h,w] float32 metres (0 = background);
  *   mask         [b,1,h,w] uint8 0/1.
@@ -150,7 +157,7 @@ int hpb_render(hpb_ctx *ctx, const int32_t *mesh_ids_dev, const float *TCO_dev, 
                const float *ambient_dev, int b, int h, int w, float z_near, float z_far, uint32_t flags,
                float *rgb_dev, int64_t rgb_bstride, float *normals_dev, int64_t normals_bstride,
                float *depth_dev, int64_t depth_bstride, uint8_t *mask_dev, int64_t mask_bstride,
-               int views, int64_t view_stride, void *stream);
+               int views, int64_t view_stride, const float *lights_dev, int n_lights, void *stream);
 
 /*
  * Perspective crop + resize of the observed frame(s) (crop_inputs).

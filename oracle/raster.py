@@ -58,7 +58,7 @@ def _load():
         _lib = ctypes.CDLL(_LIB_PATH)
         _lib.hpo_render_batch.restype = ctypes.c_int
         _lib.hpo_render_batch.argtypes = (
-            [ctypes.c_void_p] * 5 + [ctypes.c_int] * 4 + [ctypes.c_float] * 2 + [ctypes.c_uint32] + [ctypes.c_void_p] * 4
+            [ctypes.c_void_p] * 6 + [ctypes.c_int] * 5 + [ctypes.c_float] * 2 + [ctypes.c_uint32] + [ctypes.c_void_p] * 4
         )
         _lib.hpo_mip_downsample.restype = None
         _lib.hpo_mip_downsample.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
@@ -208,8 +208,10 @@ def render(
     z_near: float = 0.1,
     z_far: float = 10.0,
     n_threads: int = 1,
+    lights=None,
 ):
-    """Render b hypotheses.  Returns dict(rgb [b,3,h,w] f32, normals, depth [b,1,h,w] f32, mask bool)."""
+    """Render b hypotheses.  Returns dict(rgb [b,3,h,w] f32, normals, depth [b,1,h,w] f32, mask bool).
+    lights: [b, n_lights, 8] (type 0 point / 1 directional, xyz in the object = world frame, rgb, -) or None."""
     lib = _load()
     if render_binary_mask:
         assert render_depth, "Binary mask can only be rendered if depth is rendered"  # panda3d_scene_renderer.py:331-332
@@ -222,6 +224,8 @@ def render(
     assert len(mesh_ids) == b
     arr = (_HpoMesh * len(meshes))(*[m.c_struct() for m in meshes])
     amb = None if ambient is None else np.ascontiguousarray(np.asarray(ambient, np.float32).reshape(b, 3))
+    lts = None if lights is None else np.ascontiguousarray(np.asarray(lights, np.float32).reshape(b, -1, 8))
+    n_lights = 0 if lts is None else lts.shape[1]
     flags = (FLAG_RGB if render_rgb else 0) | (FLAG_NORMALS if render_normals else 0) | (FLAG_DEPTH if render_depth else 0) | (FLAG_MASK if render_binary_mask else 0)
     rgb = np.empty((b, 3, h, w), np.float32) if render_rgb else None
     nrm = np.empty((b, 3, h, w), np.float32) if render_normals else None
@@ -233,7 +237,7 @@ def render(
 
     def run(n0, n1):
         return lib.hpo_render_batch(
-            ctypes.addressof(arr), mesh_ids.ctypes.data, TCO.ctypes.data, K.ctypes.data, ptr(amb),
+            ctypes.addressof(arr), mesh_ids.ctypes.data, TCO.ctypes.data, K.ctypes.data, ptr(amb), ptr(lts), n_lights,
             n0, n1, h, w, z_near, z_far, flags, ptr(rgb), ptr(nrm), ptr(dep), ptr(msk),
         )
 

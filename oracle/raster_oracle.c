@@ -202,7 +202,7 @@ static inline float quant8(float c) {
 
 /* Render one hypothesis.  Outputs are CHW float32 planes (any may be NULL); mask is uint8 0/1. */
 static int render_one(const hpo_mesh *m, const float *T, const float *K, int h, int w, float znear, float zfar,
-                      const float *ambient, uint32_t flags, float *rgb, float *nrm_out, float *depth,
+                      const float *ambient, const float *lights, int n_lights, uint32_t flags, float *rgb, float *nrm_out, float *depth,
                       uint8_t *mask) {
     const int64_t npix = (int64_t)h * w;
     if (rgb) memset(rgb, 0, sizeof(float) * 3 * npix);
@@ -293,7 +293,19 @@ static int render_one(const hpo_mesh *m, const float *T, const float *K, int h, 
 
     /* pass 2: shade the winning triangle of every covered pixel */
     float amb[3] = {1.0f, 1.0f, 1.0f};
-    if (ambient) for (int k = 0; k < 3; ++k) { amb[k] = ambient[k]; if (amb[k] > 1.0f) amb[k] = 1.0f; if (!(amb[k] > 0.0f)) amb[k] = 0.0f; }
+    const int lit = lights != NULL && n_lights > 0;
+    if (ambient) for (int k = 0; k < 3; ++k) { amb[k] = ambient[k]; if (!lit && amb[k] > 1.0f) amb[k] = 1.0f; if (!(amb[k] > 0.0f)) amb[k] = 0.0f; }
+    /* point / directional lights (render_normals=False light rig, pose_rigid.py:105-141,421-422): given in the world =
+     * object frame, moved into the camera frame once per scene; per-pixel Lambert, no attenuation, sum clamped at 1 */
+    float Lc[8][8];
+    for (int i = 0; lit && i < n_lights; ++i) {
+        const float *L = lights + 8 * i;
+        const float x = L[1], y = L[2], z = L[3];
+        float cx3 = fmaf(T[2], z, fmaf(T[1], y, T[0] * x)), cy3 = fmaf(T[6], z, fmaf(T[5], y, T[4] * x));
+        float cz3 = fmaf(T[10], z, fmaf(T[9], y, T[8] * x));
+        if (L[0] == 0.0f) { cx3 = cx3 + T[3]; cy3 = cy3 + T[7]; cz3 = cz3 + T[11]; }
+        Lc[i][0] = L[0]; Lc[i][1] = cx3; Lc[i][2] = cy3; Lc[i][3] = cz3; Lc[i][4] = L[4]; Lc[i][5] = L[5]; Lc[i][6] = L[6];
+    }
     for (int py = 0; py < h; ++py) {
         for (int px = 0; px < w; ++px) {
             const int64_t pi = (int64_t)py * w + px;
@@ -322,7 +334,8 @@ static int render_one(const hpo_mesh *m, const float *T, const float *K, int h, 
                 if (depth) depth[pi] = z;
                 if (mask) mask[pi] = z > 0.0f;
             }
-            if (nrm_out) {
+            float lit3[3] = {amb[0], amb[1], amb[2]};
+            if (nrm_out || lit) {
                 /* object-space normal interpolated perspective-correctly, then rotated into the eye frame and
                  * normalised once per pixel (for an orthonormal R identical to interpolating per-vertex eye normals) */
                 float ox = 0.0f, oy = 0.0f, oz = 0.0f;
@@ -337,9 +350,30 @@ static int render_one(const hpo_mesh *m, const float *T, const float *K, int h, 
                 float nz = fmaf(T[10], oz, fmaf(T[9], oy, T[8] * ox));
                 const float len2 = fmaf(nz, nz, fmaf(ny, ny, nx * nx));
                 if (len2 > 0.0f) { const float r = 1.0f / sqrtf(len2); nx *= r; ny *= r; nz *= r; }
-                nrm_out[pi] = encode_normal(nx);
-                nrm_out[npix + pi] = encode_normal(nz);
-                nrm_out[2 * npix + pi] = encode_normal(-ny);
+                if (nrm_out) {
+                    nrm_out[pi] = encode_normal(nx);
+                    nrm_out[npix + pi] = encode_normal(nz);
+                    nrm_out[2 * npix + pi] = encode_normal(-ny);
+                }
+                if (lit) {
+                    const float dk = u2f((uint32_t)(key >> 32));
+                    const float zc = a_f / (dk - b_f);
+                    const float X = (((float)px + 0.5f) - K[2]) / K[0] * zc, Y = (((float)py + 0.5f) - K[5]) / K[4] * zc;
+                    for (int i = 0; i < n_lights; ++i) {
+                        float ndl;
+                        if (Lc[i][0] != 0.0f) {
+                            ndl = -fmaf(nz, Lc[i][3], fmaf(ny, Lc[i][2], nx * Lc[i][1]));
+                        } else {
+                            const float lx = Lc[i][1] - X, ly = Lc[i][2] - Y, lz = Lc[i][3] - zc;
+                            const float l2 = fmaf(lz, lz, fmaf(ly, ly, lx * lx));
+                            ndl = fmaf(nz, lz, fmaf(ny, ly, nx * lx));
+                            if (l2 > 0.0f) ndl = ndl * (1.0f / sqrtf(l2));
+                        }
+                        if (ndl > 0.0f)
+                            for (int k = 0; k < 3; ++k) lit3[k] = fmaf(ndl, Lc[i][4 + k], lit3[k]);
+                    }
+                    for (int k = 0; k < 3; ++k) if (lit3[k] > 1.0f) lit3[k] = 1.0f;
+                }
             }
             if (rgb) {
                 float col[3] = {255.0f, 255.0f, 255.0f};
@@ -381,7 +415,7 @@ static int render_one(const hpo_mesh *m, const float *T, const float *K, int h, 
                     for (int k = 0; k < 3; ++k)
                         col[k] = fmaf(p2, (float)c2[k], fmaf(p1, (float)c1[k], p0 * (float)c0[k]));
                 }
-                for (int k = 0; k < 3; ++k) rgb[k * npix + pi] = quant8(col[k] * amb[k]);
+                for (int k = 0; k < 3; ++k) rgb[k * npix + pi] = quant8(col[k] * lit3[k]);
             }
         }
     }
@@ -394,13 +428,13 @@ static int render_one(const hpo_mesh *m, const float *T, const float *K, int h, 
  * Renders hypotheses n0 <= n < n1 serially; the Python wrapper runs disjoint ranges on host threads
  * (ctypes releases the GIL), mirroring the reference's n_workers pool (panda3d_batch_renderer.py:288-330). */
 int hpo_render_batch(const hpo_mesh *meshes, const int32_t *mesh_ids, const float *TCO, const float *K,
-                     const float *ambient, int n0, int n1, int h, int w, float znear, float zfar, uint32_t flags,
-                     float *rgb, float *normals, float *depth, uint8_t *mask) {
+                     const float *ambient, const float *lights, int n_lights, int n0, int n1, int h, int w, float znear, float zfar,
+                     uint32_t flags, float *rgb, float *normals, float *depth, uint8_t *mask) {
     const int64_t npix = (int64_t)h * w;
     int err = 0;
     for (int n = n0; n < n1; ++n) {
         int r = render_one(meshes + mesh_ids[n], TCO + 16 * n, K + 9 * n, h, w, znear, zfar,
-                           ambient ? ambient + 3 * n : NULL, flags,
+                           ambient ? ambient + 3 * n : NULL, lights ? lights + (size_t)8 * n_lights * n : NULL, n_lights, flags,
                            (flags & HPO_FLAG_RGB) && rgb ? rgb + 3 * npix * n : NULL,
                            (flags & HPO_FLAG_NORMALS) && normals ? normals + 3 * npix * n : NULL,
                            (flags & HPO_FLAG_DEPTH) && depth ? depth + npix * n : NULL,

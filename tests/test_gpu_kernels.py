@@ -538,6 +538,41 @@ def test_pack_input_s2d_matches_torch_statement(ctx):
         assert torch.equal(got, ref)
 
 
+def test_point_lights_match_oracle(ctx, can):
+    """hpb_render with point / directional lights (the render_normals=False light rig of pose_rigid.py:105-141,421-422) is
+    bit-identical to the oracle's per-pixel Lambert shading: rig of 6 point lights, a directional light, mixed batch with
+    an unlit scene padded with black lights, written into a network-input slice with 4 views."""
+    from happypose_b200 import ops
+
+    om, mid = can
+    rs = np.random.RandomState(41)
+    b = 8
+    T, K = random_crop_scene(rs, b)
+    radius = float(np.linalg.norm(om.pos - 0.5 * (om.pos.min(0) + om.pos.max(0)), axis=1).max())
+    axes = np.array([[1, 0, 0], [-1, 0, 0], [0, 1, 0], [0, -1, 0], [0, 0, 1], [0, 0, -1]], np.float32)
+    lights = np.zeros((b, 7, 8), np.float32)
+    lights[:, :6, 1:4] = axes * radius * 10
+    lights[:, :6, 4:7] = 0.4
+    lights[:, 6, 0] = 1.0                      # a directional light
+    lights[:, 6, 1:4] = rs.randn(b, 3)
+    lights[:, 6, 1:4] /= np.linalg.norm(lights[:, 6, 1:4], axis=1, keepdims=True)
+    lights[:, 6, 4:7] = rs.uniform(0, 0.5, (b, 3))
+    lights[3] = 0.0                            # scene 3: black lights only
+    amb = np.full((b, 3), 0.1, np.float32)
+    ref = oraster.render([om], np.zeros(b, int), T, K, (H, W), ambient=amb, lights=lights, render_depth=True, n_threads=4)
+    ids = torch.full((b,), mid, dtype=torch.int32)
+    rgb, _, dep, _ = ops.render(ctx, ids, torch.as_tensor(T), torch.as_tensor(K), (H, W), ambient=torch.as_tensor(amb),
+                                lights=torch.as_tensor(lights), render_depth=True)
+    assert np.array_equal(dep.cpu().numpy(), ref["depth"])
+    d = np.abs(rgb.cpu().numpy() - ref["rgb"]) * 255
+    assert d.max() <= 1.0 + 1e-3 and (d > 0.5).mean() < 1e-3  # 8-bit levels: identical up to rare rounding flips
+    # 4 views interleaved into a [b/4, 3 + 4*3, h, w] input (render_normals=False refiner layout)
+    x = torch.zeros((2, 15, H, W), device="cuda")
+    ops.render(ctx, ids, torch.as_tensor(T), torch.as_tensor(K), (H, W), ambient=torch.as_tensor(amb), lights=torch.as_tensor(lights),
+               out=x, out_channel_offset=3, views=4)
+    assert torch.equal(x[:, 3:].reshape(8, 3, H, W), rgb)
+
+
 def test_render_s2d_bf16_equals_render_then_pack(ctx, can):
     """hpb_render_s2d_bf16 (the rasteriser writing the stem's bf16 space-to-depth input itself) is bit-identical to
     hpb_crop -> hpb_render into the float32 network input -> hpb_pack_input_s2d_bf16, including the zero border, the

@@ -105,11 +105,55 @@ def test_batch_renderer_like_reference_test(object_dataset):
         renderer.render(labels=Nc * ["unknown"], TCO=TCO, K=K, light_datas=light_datas, resolution=(height, width))
     with pytest.raises(AssertionError):
         renderer.render(labels=["my_favorite_object_label"], TCO=TCO, K=K, light_datas=light_datas, resolution=(height, width))
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(AssertionError):  # a point light needs a positioning_function (panda3d_scene_renderer.py:301-303)
         renderer.render(labels=Nc * ["my_favorite_object_label"], TCO=TCO, K=K, resolution=(height, width),
                         light_datas=Nc * [[Panda3dLightData(light_type="point")]])
+    with pytest.raises(NotImplementedError):  # unknown light types: panda3d_scene_renderer.py:309-310
+        renderer.render(labels=Nc * ["my_favorite_object_label"], TCO=TCO, K=K, resolution=(height, width),
+                        light_datas=Nc * [[Panda3dLightData(light_type="spot", positioning_function=lambda r, n: None)]])
     renderer.stop()
     renderer.stop()
+
+
+def test_light_rig_through_the_renderer_api_and_predictor(object_dataset, scene):
+    """make_scene_lights() (1 ambient + 6 point lights placed by positioning_functions that ask the scene root for its
+    bounding radius, panda3d_scene_renderer.py:105-141) through Panda3dBatchRenderer.render, against the oracle; and a
+    render_normals=False PosePredictor (pose_rigid.py:421-422 selects that rig) producing its 3-channel renders."""
+    from happypose_b200.megapose.pose_models_cfg import REFINER_RGB, create_model_pose
+    from happypose_b200.lib3d.rigid_mesh_database import MeshDataBase
+    from happypose_b200.renderer import Panda3dBatchRenderer, make_scene_lights
+    from dataclasses import replace
+    from oracle import raster as oraster
+
+    renderer = Panda3dBatchRenderer(asset_dataset=object_dataset, n_workers=1)
+    T, Km, (height, width) = reference_test_scene()
+    TCO = torch.from_numpy(T).unsqueeze(0).repeat(2, 1, 1)
+    K = torch.from_numpy(Km).unsqueeze(0).repeat(2, 1, 1)
+    r = renderer.render(labels=2 * ["my_favorite_object_label"], TCO=TCO, K=K, light_datas=[make_scene_lights(), make_scene_lights()],
+                        resolution=(height, width))
+    om = scene.meshes[0]
+    radius = float(np.linalg.norm(om.pos - 0.5 * (om.pos.min(0) + om.pos.max(0)), axis=1).max())
+    assert abs(renderer._label_to_radius["my_favorite_object_label"] - radius) < 1e-6
+    rig = np.zeros((2, 6, 8), np.float32)
+    rig[:, :, 1:4] = np.array([[1, 0, 0], [-1, 0, 0], [0, 1, 0], [0, -1, 0], [0, 0, 1], [0, 0, -1]], np.float32) * np.float32(radius * 10)
+    rig[:, :, 4:7] = 0.4
+    ref = oraster.render([om], np.zeros(2, int), np.stack([T, T]).astype(np.float32), np.stack([Km, Km]).astype(np.float32), (height, width),
+                         ambient=np.full((2, 3), 0.1, np.float32), lights=rig, n_threads=2)
+    d = np.abs(r.rgbs.cpu().numpy() - ref["rgb"]) * 255
+    assert d.max() <= 1.0 + 1e-3 and (d > 0.5).mean() < 2e-3
+    assert r.rgbs[0, :, height // 2, width // 2].sum() > 0.05  # lit, not black
+    # a refiner that renders without normals: 3 + 4*3 = 15 input channels
+    mesh_db = MeshDataBase.from_object_ds(object_dataset).batched().cuda()
+    model = create_model_pose(replace(REFINER_RGB, render_normals=False), renderer, mesh_db).cuda().eval()
+    _tame_heads(model, 3)
+    model.compute_dtype = torch.float32
+    image, R = _coarse_inputs(2, 33)
+    TCO0 = O.TCO_init_from_boxes_autodepth_with_R(np.tile(BBOX_BBQ, (2, 1)), scene.points[np.zeros(2, int)], np.tile(K_BBQ, (2, 1, 1)), R)
+    out = model(images=torch.as_tensor(image).cuda(), K=torch.as_tensor(K_BBQ[None]).cuda(), labels=2 * ["my_favorite_object_label"],
+                TCO=torch.as_tensor(TCO0).cuda(), n_iterations=1, im_ids=torch.zeros(2, dtype=torch.int32))["iteration=1"]
+    assert out.renders.shape == (2, 12, 240, 320) and torch.isfinite(out.TCO_output).all()
+    lit_px = out.renders[:, :3].sum(1) > 0
+    assert lit_px.float().mean() > 0.05 and out.renders.max() <= 1.0
 
 
 def _coarse_inputs(n, seed):

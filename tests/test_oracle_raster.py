@@ -139,3 +139,41 @@ def test_backface_skipping_is_invisible(can, can_mesh_arrays):
     for k in ("rgb", "normals", "depth"):
         assert (a[k] != b[k]).mean() <= 1e-4, k  # silhouette depth ties may pick the other face of a shared edge
     assert (a["depth"][0] == b["depth"][0]).all() and (a["rgb"][0] == b["rgb"][0]).all()
+
+
+def test_point_light_rig_lambert_shading(can_mesh_arrays):
+    """The render_normals=False light rig (1 ambient 0.1 + 6 point lights 0.4 at +-10 bounding radii,
+    panda3d_scene_renderer.py:105-141) as per-pixel Lambert shading: same geometry as the ambient render, colour =
+    albedo * min(1, 0.1 + 0.4 * sum max(0, n.l)); black lights change nothing; a single light from the camera side lights
+    the centre of the can more than its limbs."""
+    d = can_mesh_arrays
+    mesh = raster.OracleMesh(d["verts"], d["faces"], d["normals"], d["uv"], texture=d["texture"], scale=0.001)
+    T, K, (H, W) = reference_test_scene()
+    T32, K32 = T[None].astype(np.float32), K[None].astype(np.float32)
+    amb1 = raster.render([mesh], np.zeros(1, int), T32, K32, (H, W), render_depth=True)
+    radius = float(np.linalg.norm(mesh.pos - 0.5 * (mesh.pos.min(0) + mesh.pos.max(0)), axis=1).max())
+    axes = np.array([[1, 0, 0], [-1, 0, 0], [0, 1, 0], [0, -1, 0], [0, 0, 1], [0, 0, -1]], np.float32)
+    rig = np.zeros((1, 6, 8), np.float32)
+    rig[0, :, 1:4] = axes * radius * 10
+    rig[0, :, 4:7] = 0.4
+    lit = raster.render([mesh], np.zeros(1, int), T32, K32, (H, W), ambient=np.full((1, 3), 0.1, np.float32), lights=rig, render_depth=True)
+    assert np.array_equal(lit["depth"], amb1["depth"])
+    cov = amb1["depth"][0, 0] > 0
+    ratio = lit["rgb"][0][:, cov].sum(0) / np.maximum(amb1["rgb"][0][:, cov].sum(0), 1e-6)
+    bright = amb1["rgb"][0][:, cov].sum(0) > 0.5
+    assert 0.1 <= ratio[bright].min() and ratio[bright].max() <= 1.0 + 1e-6 and 0.3 < ratio[bright].mean() < 0.9
+    dark = raster.render([mesh], np.zeros(1, int), T32, K32, (H, W), ambient=np.full((1, 3), 0.1, np.float32), lights=np.zeros((1, 2, 8), np.float32))
+    only_amb = raster.render([mesh], np.zeros(1, int), T32, K32, (H, W), ambient=np.full((1, 3), 0.1, np.float32))
+    assert np.array_equal(dark["rgb"], only_amb["rgb"])
+    # one point light at the camera (object frame position of the camera centre = -R^T t): n.l ~ 1 at the centre of the can
+    cam_in_obj = -(T[:3, :3].T @ T[:3, 3])
+    one = np.zeros((1, 1, 8), np.float32)
+    one[0, 0, 1:4] = cam_in_obj
+    one[0, 0, 4:7] = 1.0
+    head = raster.render([mesh], np.zeros(1, int), T32, K32, (H, W), ambient=np.zeros((1, 3), np.float32), lights=one)["rgb"][0].sum(0)
+    full = amb1["rgb"][0].sum(0)
+    ys, xs = np.nonzero(cov)
+    cy, cx = int(ys.mean()), int(xs.mean())
+    centre = head[cy - 5:cy + 5, cx - 5:cx + 5].sum() / full[cy - 5:cy + 5, cx - 5:cx + 5].sum()
+    limb = head[cy - 5:cy + 5, xs.min() + 1:xs.min() + 6].sum() / max(full[cy - 5:cy + 5, xs.min() + 1:xs.min() + 6].sum(), 1e-6)
+    assert centre > 0.9 and limb < 0.6
