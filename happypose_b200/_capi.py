@@ -47,6 +47,11 @@ SIGNATURES = {
     "hpb_set_crop_tap_precision": (c_int, [c_void_p, c_int]),
     "hpb_crop_boxes": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "hpb_crop_pixels": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int64,
+                                c_int, c_void_p]),
+    "hpb_refiner_prologue": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int,
+                                     c_int, c_int, c_float, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                     c_void_p, c_void_p, c_void_p]),
     "hpb_normalize_T": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "hpb_pose_update": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "hpb_tco_init": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_float,

@@ -37,6 +37,12 @@ int hpb_launch_icp_points(hpb_ctx *ctx, const float *depth_measured, int n_im, c
                           const int32_t *im_ids, const float *K, int N, int H, int W, float delta, int64_t cap, float *pts_tgt,
                           float *pts_src, int32_t *counts, uint8_t *mask_out, int32_t *idx_tgt, int32_t *idx_src, cudaStream_t stream);
 
+int hpb_launch_refiner_prologue(hpb_ctx *ctx, const float *TCO_in, const float *K, const int32_t *obj_ids, const float *pts_crop,
+                                int n_crop, const float *pts_mv, int n_mv, int b, int H, int W, int h, int w, float lamb,
+                                const float *positions_host, int n_extra, int n_views, int keep_tco, float *T_norm, float *tCR,
+                                float *TCV_O, float *K_crop, float *boxes_rend, float *boxes_crop, float *KV_crop,
+                                cudaStream_t stream);
+
 static thread_local char g_err[512] = "";
 
 int hpb_ws_grow(hpb_ctx *ctx, void **ptr, size_t *cur_bytes, size_t need, cudaStream_t stream, const char *what) {
@@ -569,12 +575,9 @@ int hpb_tco_init(hpb_ctx *ctx, int variant, const float *boxes_dev, const float 
                                TCO_out_dev, (cudaStream_t)stream);
 }
 
-int hpb_multiview(hpb_ctx *ctx, const float *TCO_dev, const float *tCR_dev, int b, int mv_type, int n_views,
-                  int remove_tco_rendering, float *TCV_O_dev, void *stream) {
-    HPB_REQUIRE(ctx && b >= 0 && n_views >= 1, "bad argument");
-    if (b == 0) return HPB_OK;
-    HPB_REQUIRE(TCO_dev && tCR_dev && TCV_O_dev, "NULL pointer");
-    float pos[26 * 3];
+// camera positions (in units of |tCR|, in the frame of the look-at camera at C0) of a multiview type
+// (toolbox/lib3d/multiview.py:95-163); returns HPB_OK and fills pos / n_extra / keep
+static int hpb_mv_positions(int mv_type, int n_views, int remove_tco_rendering, float *pos, int *n_extra_out, int *keep_out) {
     int n_extra = 0, keep = 1;
     if (n_views == 1) {  // multiview.py:190-197: identity view only
         n_extra = 0;
@@ -599,13 +602,67 @@ int hpb_multiview(hpb_ctx *ctx, const float *TCO_dev, const float *tCR_dev, int 
                         ++n_extra;
                     }
         } else {
-            hpb_set_error("hpb_multiview: unknown multiview type %d", mv_type);
+            hpb_set_error("unknown multiview type %d", mv_type);
             return HPB_EINVAL;
         }
         HPB_REQUIRE(n_views == n_extra + keep, "n_views does not match the multiview type");
     }
+    *n_extra_out = n_extra;
+    *keep_out = keep;
+    return HPB_OK;
+}
+
+int hpb_multiview(hpb_ctx *ctx, const float *TCO_dev, const float *tCR_dev, int b, int mv_type, int n_views,
+                  int remove_tco_rendering, float *TCV_O_dev, void *stream) {
+    HPB_REQUIRE(ctx && b >= 0 && n_views >= 1, "bad argument");
+    if (b == 0) return HPB_OK;
+    HPB_REQUIRE(TCO_dev && tCR_dev && TCV_O_dev, "NULL pointer");
+    float pos[26 * 3];
+    int n_extra = 0, keep = 1;
+    const int rc = hpb_mv_positions(mv_type, n_views, remove_tco_rendering, pos, &n_extra, &keep);
+    if (rc != HPB_OK) return rc;
     HpbDeviceGuard guard(ctx->device);
     return hpb_launch_multiview(ctx, TCO_dev, tCR_dev, b, pos, n_extra, n_views, keep, TCV_O_dev, (cudaStream_t)stream);
+}
+
+int hpb_refiner_prologue(hpb_ctx *ctx, const float *TCO_dev, const float *K_dev, const int32_t *obj_ids_dev,
+                         const float *points_crop_dev, int n_obj, int n_pts_crop, const float *points_mv_dev, int n_pts_mv, int b,
+                         int H, int W, int h, int w, float lamb, int mv_type, int n_views, int remove_tco_rendering,
+                         float *T_norm_dev, float *tCR_dev, float *TCV_O_dev, float *K_crop_dev, float *boxes_rend_dev,
+                         float *boxes_crop_dev, float *KV_crop_dev, void *stream) {
+    HPB_REQUIRE(ctx && b >= 0 && n_views >= 1 && n_obj > 0 && n_pts_crop > 0, "bad argument");
+    HPB_REQUIRE(H > 0 && W > 0 && h > 0 && w > 0, "bad sizes");
+    if (b == 0) return HPB_OK;
+    HPB_REQUIRE(TCO_dev && K_dev && obj_ids_dev && points_crop_dev, "NULL input");
+    HPB_REQUIRE(T_norm_dev && tCR_dev && TCV_O_dev && K_crop_dev && boxes_rend_dev && boxes_crop_dev, "NULL output");
+    HPB_REQUIRE(!KV_crop_dev || (points_mv_dev && n_pts_mv > 0), "KV_crop needs the multiview point set");
+    float pos[26 * 3];
+    int n_extra = 0, keep = 1;
+    const int rc = hpb_mv_positions(mv_type, n_views, remove_tco_rendering, pos, &n_extra, &keep);
+    if (rc != HPB_OK) return rc;
+    HpbDeviceGuard guard(ctx->device);
+    return hpb_launch_refiner_prologue(ctx, TCO_dev, K_dev, obj_ids_dev, points_crop_dev, n_pts_crop, points_mv_dev, n_pts_mv, b, H, W,
+                                       h, w, lamb, pos, n_extra, n_views, keep, T_norm_dev, tCR_dev, TCV_O_dev, K_crop_dev,
+                                       boxes_rend_dev, boxes_crop_dev, KV_crop_dev, (cudaStream_t)stream);
+}
+
+int hpb_crop_pixels(hpb_ctx *ctx, const float *images_dev, int n_im, int C, int H, int W, const int32_t *im_ids_dev,
+                    const float *boxes_crop_dev, int b, int h, int w, float *crops_dev, int64_t crops_bstride, int tap_bits,
+                    void *stream) {
+    HPB_REQUIRE(ctx && b >= 0 && H > 0 && W > 0 && h > 0 && w > 0, "bad sizes");
+    HPB_REQUIRE(C == 3 || C == 4, "images must have 3 or 4 channels");
+    HPB_REQUIRE(tap_bits == 0 || tap_bits == 16 || tap_bits == 32, "tap_bits must be 0 (context default), 16 or 32");
+    if (b == 0) return HPB_OK;
+    HPB_REQUIRE(n_im > 0 && images_dev && im_ids_dev && boxes_crop_dev && crops_dev, "NULL pointer");
+    if (tap_bits == 0) tap_bits = ctx->crop_tap_bits;
+    HpbDeviceGuard guard(ctx->device);
+    for (int s0 = 0; s0 < b; s0 += 32768) {  // grid.y limit
+        const int nb = b - s0 < 32768 ? b - s0 : 32768;
+        const int rc = hpb_launch_crop_pixels(ctx, images_dev, n_im, C, H, W, im_ids_dev + s0, boxes_crop_dev + (size_t)s0 * 4, nb, h, w,
+                                              crops_dev + (size_t)s0 * crops_bstride, crops_bstride, tap_bits, (cudaStream_t)stream);
+        if (rc != HPB_OK) return rc;
+    }
+    return HPB_OK;
 }
 
 int hpb_normalize_depth(hpb_ctx *ctx, float *depth_dev, int64_t bstride, const int32_t *plane_channels_host,

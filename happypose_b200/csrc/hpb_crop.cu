@@ -21,7 +21,7 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
-#include "hpb_common.cuh"
+#include "hpb_pose_math.cuh"
 
 namespace {
 
@@ -41,77 +41,11 @@ struct CropBoxParams {
 
 __global__ void __launch_bounds__(256) hpb_crop_boxes_kernel(const CropBoxParams p) {
     const int n = blockIdx.x;
-    const int tid = threadIdx.x;
     __shared__ float sP[12];
     __shared__ float red[4][8];
-    const float *K = p.K + (size_t)n * 9;
-    const float *T = p.TCO + (size_t)n * 16;
-    if (tid < 12) {
-        const int i = tid / 4, j = tid % 4;  // P = K @ TCO[:3]
-        sP[tid] = fmaf(K[i * 3 + 2], T[8 + j], fmaf(K[i * 3 + 1], T[4 + j], K[i * 3] * T[j]));
-    }
-    __syncthreads();
-    const float *pts = p.points + (size_t)p.obj_ids[n] * p.n_pts * 3;
-    float mnx = INFINITY, mny = INFINITY, mxx = -INFINITY, mxy = -INFINITY;
-    for (int i = tid; i < p.n_pts; i += blockDim.x) {
-        const float x = __ldg(pts + 3 * i), y = __ldg(pts + 3 * i + 1), z = __ldg(pts + 3 * i + 2);
-        const float su = fmaf(sP[2], z, fmaf(sP[1], y, fmaf(sP[0], x, sP[3])));
-        const float sv = fmaf(sP[6], z, fmaf(sP[5], y, fmaf(sP[4], x, sP[7])));
-        float sz = fmaf(sP[10], z, fmaf(sP[9], y, fmaf(sP[8], x, sP[11])));
-        sz = fmaxf(0.1f, sz);  // project_points_robust z_min (camera_geometry.py:53-54)
-        const float u = su / sz, v = sv / sz;
-        mnx = fminf(mnx, u); mxx = fmaxf(mxx, u);
-        mny = fminf(mny, v); mxy = fmaxf(mxy, v);
-    }
-    for (int o = 16; o > 0; o >>= 1) {
-        mnx = fminf(mnx, __shfl_xor_sync(0xffffffffu, mnx, o));
-        mny = fminf(mny, __shfl_xor_sync(0xffffffffu, mny, o));
-        mxx = fmaxf(mxx, __shfl_xor_sync(0xffffffffu, mxx, o));
-        mxy = fmaxf(mxy, __shfl_xor_sync(0xffffffffu, mxy, o));
-    }
-    if ((tid & 31) == 0) {
-        red[0][tid >> 5] = mnx; red[1][tid >> 5] = mny; red[2][tid >> 5] = mxx; red[3][tid >> 5] = mxy;
-    }
-    __syncthreads();
-    if (tid == 0) {
-        const int nw = blockDim.x >> 5;
-        for (int k = 1; k < nw; ++k) {
-            mnx = fminf(mnx, red[0][k]); mny = fminf(mny, red[1][k]);
-            mxx = fmaxf(mxx, red[2][k]); mxy = fmaxf(mxy, red[3][k]);
-        }
-        // reference point projection: TCR = TCO with translation tCR, point (0,0,0) (cropping.py:131-137)
-        const float *c = p.tCR + (size_t)n * 3;
-        const float su = fmaf(K[2], c[2], fmaf(K[1], c[1], K[0] * c[0]));
-        const float sv = fmaf(K[5], c[2], fmaf(K[4], c[1], K[3] * c[0]));
-        float sz = fmaf(K[8], c[2], fmaf(K[7], c[1], K[6] * c[0]));
-        sz = fmaxf(0.1f, sz);
-        const float xc = su / sz, yc = sv / sz;
-        // deepim_boxes (cropping.py:27-75); obs box == rend box on this path
-        const float r = (float)max(p.H, p.W) / (float)min(p.H, p.W);
-        const float xdist = fmaxf(fabsf(mnx - xc), fabsf(mxx - xc));
-        const float ydist = fmaxf(fabsf(mny - yc), fabsf(mxy - yc));
-        const float width = fmaxf(xdist, ydist * r) * 2.0f * p.lamb;
-        const float height = fmaxf(xdist / r, ydist) * 2.0f * p.lamb;
-        const float x1 = xc - width / 2.0f, y1 = yc - height / 2.0f, x2 = xc + width / 2.0f, y2 = yc + height / 2.0f;
-        float *br = p.boxes_rend + (size_t)n * 4;
-        br[0] = mnx; br[1] = mny; br[2] = mxx; br[3] = mxy;
-        float *bc = p.boxes_crop + (size_t)n * 4;
-        bc[0] = x1; bc[1] = y1; bc[2] = x2; bc[3] = y2;
-        // get_K_crop_resize (camera_geometry.py:70-122)
-        const float final_w = (float)max(p.h, p.w), final_h = (float)min(p.h, p.w);
-        const float cw = x2 - x1, ch = y2 - y1;
-        const float ccj = (x1 + x2) / 2.0f, cci = (y1 + y2) / 2.0f;
-        const float cx = K[2] + (cw - 1.0f) / 2.0f - ccj;
-        const float cy = K[5] + (ch - 1.0f) / 2.0f - cci;
-        const float dcx = cx - (cw - 1.0f) / 2.0f, dcy = cy - (ch - 1.0f) / 2.0f;
-        const float sx = final_w / cw, sy = final_h / ch;
-        float *ko = p.K_crop + (size_t)n * 9;
-        for (int k = 0; k < 9; ++k) ko[k] = K[k];
-        ko[0] = sx * K[0];
-        ko[4] = sy * K[4];
-        ko[2] = (final_w - 1.0f) / 2.0f + sx * dcx;
-        ko[5] = (final_h - 1.0f) / 2.0f + sy * dcy;
-    }
+    hpbm::crop_boxes_cta(p.K + (size_t)n * 9, p.TCO + (size_t)n * 16, p.tCR + (size_t)n * 3,
+                         p.points + (size_t)p.obj_ids[n] * p.n_pts * 3, p.n_pts, p.H, p.W, p.h, p.w, p.lamb, p.K_crop + (size_t)n * 9,
+                         p.boxes_rend + (size_t)n * 4, p.boxes_crop + (size_t)n * 4, sP, red);
 }
 
 struct CropPixParams {

@@ -7,36 +7,18 @@
 //   hpb_tco_init_kernel      toolbox/lib3d/cosypose_ops.py:159-181,184-238,241-283
 //   hpb_multiview_kernel     toolbox/lib3d/multiview.py:28-92,166-251 (Panda3D NodePath.lookAt in closed form)
 //   hpb_normalize_depth_kernel  megapose/models/pose_rigid.py:510-544
-#include "hpb_common.cuh"
+#include "hpb_pose_math.cuh"
 
 namespace {
 
-// columns (x, y, z) of R from the 6-D representation (a = first column, b = second column)
-__device__ __forceinline__ void ortho6d(const float a[3], const float bb[3], float R[9]) {
-    const float na = sqrtf(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
-    const float x0 = a[0] / na, x1 = a[1] / na, x2 = a[2] / na;
-    float z0 = x1 * bb[2] - x2 * bb[1], z1 = x2 * bb[0] - x0 * bb[2], z2 = x0 * bb[1] - x1 * bb[0];
-    const float nz = sqrtf(z0 * z0 + z1 * z1 + z2 * z2);
-    z0 /= nz; z1 /= nz; z2 /= nz;
-    const float y0 = z1 * x2 - z2 * x1, y1 = z2 * x0 - z0 * x2, y2 = z0 * x1 - z1 * x0;
-    R[0] = x0; R[1] = y0; R[2] = z0;
-    R[3] = x1; R[4] = y1; R[5] = z1;
-    R[6] = x2; R[7] = y2; R[8] = z2;
-}
+using namespace hpbm;
 
 __global__ void hpb_normalize_T_kernel(const float *T, int b, float *out) {
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= b) return;
-    const float *t = T + (size_t)n * 16;
-    const float a[3] = {t[0], t[4], t[8]}, c[3] = {t[1], t[5], t[9]};
-    const float tr[3] = {t[3], t[7], t[11]};
-    float R[9];
-    ortho6d(a, c, R);
-    float *o = out + (size_t)n * 16;
-    o[0] = R[0]; o[1] = R[1]; o[2] = R[2]; o[3] = tr[0];
-    o[4] = R[3]; o[5] = R[4]; o[6] = R[5]; o[7] = tr[1];
-    o[8] = R[6]; o[9] = R[7]; o[10] = R[8]; o[11] = tr[2];
-    o[12] = 0.f; o[13] = 0.f; o[14] = 0.f; o[15] = 1.f;
+    float o[16];
+    normalize_T_row(T + (size_t)n * 16, o);
+    for (int k = 0; k < 16; ++k) out[(size_t)n * 16 + k] = o[k];
 }
 
 // xyzw quaternion -> R through the angle-axis route of the reference (rotations.py:196-229: quat2mat ->
@@ -165,48 +147,6 @@ __global__ void __launch_bounds__(256) hpb_tco_init_kernel(const TcoInitParams p
     }
 }
 
-// ---- multiview camera placement (float64 like the reference's numpy path, cast to float32 at the end) ----
-struct M4 { double m[16]; };
-
-__device__ __forceinline__ M4 m4_mul(const M4 &a, const M4 &b) {
-    M4 r;
-    for (int i = 0; i < 4; ++i)
-        for (int j = 0; j < 4; ++j) {
-            double s = 0;
-            for (int k = 0; k < 4; ++k) s += a.m[i * 4 + k] * b.m[k * 4 + j];
-            r.m[i * 4 + j] = s;
-        }
-    return r;
-}
-__device__ __forceinline__ M4 m4_rigid_inv(const M4 &a) {  // (R, t) -> (R^T, -R^T t)
-    M4 r;
-    for (int i = 0; i < 3; ++i)
-        for (int j = 0; j < 3; ++j) r.m[i * 4 + j] = a.m[j * 4 + i];
-    for (int i = 0; i < 3; ++i) r.m[i * 4 + 3] = -(r.m[i * 4] * a.m[3] + r.m[i * 4 + 1] * a.m[7] + r.m[i * 4 + 2] * a.m[11]);
-    r.m[12] = r.m[13] = r.m[14] = 0;
-    r.m[15] = 1;
-    return r;
-}
-// Panda3D look_at(): +Y exactly at the target, +Z as close to `up` as possible, +X = Y x Z; node axes as columns.
-__device__ __forceinline__ void look_at(const double pos[3], const double tgt[3], const double up[3], double R[9]) {
-    double f[3] = {tgt[0] - pos[0], tgt[1] - pos[1], tgt[2] - pos[2]};
-    const double nf = sqrt(f[0] * f[0] + f[1] * f[1] + f[2] * f[2]);
-    f[0] /= nf; f[1] /= nf; f[2] /= nf;
-    double r[3] = {f[1] * up[2] - f[2] * up[1], f[2] * up[0] - f[0] * up[2], f[0] * up[1] - f[1] * up[0]};
-    const double nr = sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
-    r[0] /= nr; r[1] /= nr; r[2] /= nr;
-    const double u[3] = {r[1] * f[2] - r[2] * f[1], r[2] * f[0] - r[0] * f[2], r[0] * f[1] - r[1] * f[0]};
-    R[0] = r[0]; R[1] = f[0]; R[2] = u[0];
-    R[3] = r[1]; R[4] = f[1]; R[5] = u[1];
-    R[6] = r[2]; R[7] = f[2]; R[8] = u[2];
-}
-
-// camera positions of the extra views travel BY VALUE in the kernel parameters: nothing is read from host memory after the
-// launch call returns, so the launch can be captured into a CUDA graph
-struct MvPositions {
-    float p[26 * 3];
-};
-
 __global__ void hpb_multiview_kernel(const float *TCO, const float *tCR, int b, int n_extra, int n_views,
                                      int keep_tco, const MvPositions mv, float *out) {
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
@@ -219,58 +159,9 @@ __global__ void hpb_multiview_kernel(const float *TCO, const float *tCR, int b, 
         v0 = 1;
     }
     if (n_extra == 0) return;
-    M4 T;
-    for (int k = 0; k < 16; ++k) T.m[k] = (double)Tf[k];
-    double c[3] = {(double)tCR[(size_t)n * 3], (double)tCR[(size_t)n * 3 + 1], (double)tCR[(size_t)n * 3 + 2]};
-    T.m[12] = T.m[13] = T.m[14] = 0; T.m[15] = 1;
-    M4 TOC = m4_rigid_inv(T);
-    bool fin = true;
-    for (int k = 0; k < 12; ++k) fin = fin && isfinite(TOC.m[k]);
-    if (!fin) {  // multiview.py:44-46
-        for (int k = 0; k < 16; ++k) TOC.m[k] = (k % 5 == 0) ? 1.0 : 0.0;
-        c[0] = c[1] = c[2] = 0;
-    }
-    const M4 CCGL = {{1, 0, 0, 0, 0, 0, -1, 0, 0, 1, 0, 0, 0, 0, 0, 1}};
-    const M4 CCGLi = {{1, 0, 0, 0, 0, 0, 1, 0, 0, -1, 0, 0, 0, 0, 0, 1}};
-    const M4 WC0 = m4_mul(TOC, CCGL);
-    const double ref[3] = {TOC.m[0] * c[0] + TOC.m[1] * c[1] + TOC.m[2] * c[2] + TOC.m[3],
-                           TOC.m[4] * c[0] + TOC.m[5] * c[1] + TOC.m[6] * c[2] + TOC.m[7],
-                           TOC.m[8] * c[0] + TOC.m[9] * c[1] + TOC.m[10] * c[2] + TOC.m[11]};
-    const double radius = sqrt(c[0] * c[0] + c[1] * c[1] + c[2] * c[2]);
-    const double up[3] = {WC0.m[2], WC0.m[6], WC0.m[10]};
-    const double c0[3] = {WC0.m[3], WC0.m[7], WC0.m[11]};
-    double Rp[9];
-    look_at(c0, ref, up, Rp);
-    const M4 C0W = m4_rigid_inv(WC0);
-    for (int e = 0; e < n_extra; ++e) {
-        const double q[3] = {mv.p[3 * e] * radius, mv.p[3 * e + 1] * radius, mv.p[3 * e + 2] * radius};
-        const double pos[3] = {c0[0] + Rp[0] * q[0] + Rp[1] * q[1] + Rp[2] * q[2],
-                               c0[1] + Rp[3] * q[0] + Rp[4] * q[1] + Rp[5] * q[2],
-                               c0[2] + Rp[6] * q[0] + Rp[7] * q[1] + Rp[8] * q[2]};
-        double Rn[9];
-        look_at(pos, ref, up, Rn);
-        M4 WN;
-        for (int i = 0; i < 3; ++i) {
-            for (int j = 0; j < 3; ++j) WN.m[i * 4 + j] = Rn[i * 3 + j];
-            WN.m[i * 4 + 3] = pos[i];
-        }
-        WN.m[12] = WN.m[13] = WN.m[14] = 0; WN.m[15] = 1;
-        const M4 TC0_CV = m4_mul(m4_mul(CCGL, m4_mul(C0W, WN)), CCGLi);
-        // cast to float32, invert as a rigid transform and compose with TCO in float32
-        // (invert_transform_matrices(TC0_CV) @ TCO, multiview.py:236)
-        float A[16];
-        for (int k = 0; k < 16; ++k) A[k] = (float)TC0_CV.m[k];
-        float Ai[12];
-        for (int i = 0; i < 3; ++i)
-            for (int j = 0; j < 3; ++j) Ai[i * 4 + j] = A[j * 4 + i];
-        for (int i = 0; i < 3; ++i) Ai[i * 4 + 3] = -(Ai[i * 4] * A[3] + Ai[i * 4 + 1] * A[7] + Ai[i * 4 + 2] * A[11]);
-        float *ov = o + (size_t)(v0 + e) * 16;
-        for (int i = 0; i < 3; ++i)
-            for (int j = 0; j < 4; ++j)
-                ov[i * 4 + j] = Ai[i * 4] * Tf[j] + Ai[i * 4 + 1] * Tf[4 + j] + Ai[i * 4 + 2] * Tf[8 + j] + Ai[i * 4 + 3] * Tf[12 + j];
-        for (int j = 0; j < 4; ++j)
-            ov[12 + j] = A[12] * Tf[j] + A[13] * Tf[4 + j] + A[14] * Tf[8 + j] + A[15] * Tf[12 + j];
-    }
+    MvFrame F;
+    multiview_frame(Tf, tCR + (size_t)n * 3, F);
+    for (int e = 0; e < n_extra; ++e) multiview_view(F, Tf, mv.p[3 * e], mv.p[3 * e + 1], mv.p[3 * e + 2], o + (size_t)(v0 + e) * 16);
 }
 
 __global__ void hpb_normalize_depth_kernel(float *depth, long long bstride, int c0, int c1, int c2, int c3, int c4,

@@ -443,33 +443,23 @@ class PosePredictor(nn.Module):
         n_views = self.n_rendered_views
         pts2000 = self.mesh_db.points_subset(2000)
 
-        # loop invariants of the iterations (each of these is one or more tiny kernels): per-view copies of the ids / K
-        multi = n_views > 1 or self.remove_TCO_rendering
-        if multi:
-            Kmv = K.unsqueeze(1).expand(bsz, n_views, 3, 3).reshape(-1, 3, 3)
-            obj_ids_v = obj_ids.repeat_interleave(n_views)
+        # loop invariant of the iterations: the renderer's mesh id of every (row, view)
         mesh_ids_v = mesh_ids.repeat_interleave(n_views) if (mesh_ids is not None and n_views > 1) else mesh_ids
+        pts200 = self.mesh_db.points_subset(200)
+        K = K.contiguous().float()
 
         outputs = {}
         TCO_input = TCO
         for n in range(n_iterations):
-            TCO_input = ops.normalize_T(ctx, TCO_input).detach()
-            tCR = TCO_input[..., :3, 3].contiguous()  # reference point = object origin (tOR = 0, pose_rigid.py:574-576)
-            TCV_O_input = ops.multiview(ctx, TCO_input, tCR, self.multiview_type, n_views, self.remove_TCO_rendering)
-            tCV_R = TCV_O_input[..., :3, 3].contiguous()
+            # ONE launch: normalize_T, tCR (reference point = object origin, tOR = 0, pose_rigid.py:574-576), the extra views,
+            # the row's crop geometry (2000 points) and the per-view K_crop (200 points), KV_crop[:, 0] = K_crop
+            pro = ops.refiner_prologue(ctx, TCO_input, K, obj_ids, pts2000, pts200, images.shape[-2:], self.render_size,
+                                       self.multiview_type, n_views, self.remove_TCO_rendering)
+            TCO_input, tCR, TCV_O_input = pro["T_norm"], pro["tCR"], pro["TCV_O"]
+            K_crop, boxes_rend, boxes_crop, KV_crop = pro["K_crop"], pro["boxes_rend"], pro["boxes_crop"], pro["KV_crop"]
 
             x = self._alloc_input(bsz, device)
-            images_crop, K_crop, boxes_rend, boxes_crop = ops.crop(
-                ctx, images, im_ids, pts2000, obj_ids, K, TCO_input, tCR, self.render_size, out=x, tap_bits=self.crop_tap_bits)
-            if multi:
-                KV_crop, _, _ = ops.crop_boxes(
-                    ctx, images.shape[-2:], self.mesh_db.points_subset(200), obj_ids_v, Kmv,
-                    TCV_O_input.flatten(0, 1), tCV_R.flatten(0, 1), self.render_size, lamb=1.4)
-                KV_crop = KV_crop.view(bsz, n_views, 3, 3)
-                if not self.remove_TCO_rendering:
-                    KV_crop[:, 0] = K_crop
-            else:
-                KV_crop = K_crop.unsqueeze(1)
+            images_crop = ops.crop_pixels(ctx, images, im_ids, boxes_crop, self.render_size, out=x, tap_bits=self.crop_tap_bits)
 
             t = time.time()
             renders = self.render_images_multiview(labels, TCV_O_input, KV_crop, random_ambient_light, out=x, mesh_ids=mesh_ids_v,

@@ -315,6 +315,62 @@ def crop_bf16x4(ctx: Context, images, im_ids, points, obj_ids, K, TCO, tCR, rend
     return crops, K_crop, boxes_rend, boxes_crop
 
 
+def crop_pixels(ctx: Context, images, im_ids, boxes_crop, render_size, out: Optional[torch.Tensor] = None, tap_bits: int = 32) -> torch.Tensor:
+    """The resampling half of `crop`: roi_align of the frames at boxes_crop [b,4] (hpb_crop_pixels).  With `out` ([b,C_total,h,w])
+    the crop is written into its channels [0,C)."""
+    dev = ctx.device
+    images = _f32(images, dev)
+    n_im, C, H, W = images.shape
+    h, w = int(render_size[0]), int(render_size[1])
+    boxes = _f32(boxes_crop, dev).reshape(-1, 4)
+    b = boxes.shape[0]
+    im_ids = _i32(im_ids, dev)
+    if out is not None:
+        assert out.is_contiguous() and out.dtype == torch.float32 and out.shape[0] == b and tuple(out.shape[2:]) == (h, w)
+        crops, bs = out[:, :C], out.stride(0)
+    else:
+        crops = torch.empty((b, C, h, w), dtype=torch.float32, device=dev)
+        bs = C * h * w
+    ev = None
+    if _kernel_timer is not None:
+        ev = _kernel_timer.bracket("hpb_crop", b * C * h * w * 4)
+        ev[0].record()
+    rc = ctx.lib.hpb_crop_pixels(ctx.handle, ptr(images), n_im, C, H, W, ptr(im_ids), ptr(boxes), b, h, w, ptr(crops), bs,
+                                 16 if (tap_bits == 16 and C == 3) else 32, stream_ptr(dev))
+    if ev is not None:
+        ev[1].record()
+    ctx.check(rc, "hpb_crop_pixels")
+    return crops
+
+
+def refiner_prologue(ctx: Context, TCO, K, obj_ids, points_crop, points_mv, image_size, render_size, multiview_type: str, n_views: int,
+                     remove_TCO_rendering: bool = False, lamb: float = 1.4):
+    """Everything of one refiner iteration in front of the image kernels, in one launch (hpb_refiner_prologue):
+    dict(T_norm [b,4,4], tCR [b,3], TCV_O [b,V,4,4], K_crop [b,3,3], boxes_rend [b,4], boxes_crop [b,4], KV_crop [b,V,3,3])."""
+    dev = ctx.device
+    TCO = _f32(TCO, dev).reshape(-1, 16)
+    b = TCO.shape[0]
+    K = _f32(K, dev).reshape(-1, 9)
+    assert K.shape[0] == b
+    obj_ids = _i32(obj_ids, dev)
+    pc, pm = _f32(points_crop, dev), _f32(points_mv, dev)
+    assert pc.dim() == 3 and pm.dim() == 3 and pc.shape[0] == pm.shape[0]
+    if n_views > 1 and multiview_type not in _capi.MV_TYPES:
+        raise ValueError(multiview_type)
+    mv = _capi.MV_TYPES.get(multiview_type, 0)
+    H, W = int(image_size[0]), int(image_size[1])
+    h, w = int(render_size[0]), int(render_size[1])
+    f = lambda *shape: torch.empty(shape, dtype=torch.float32, device=dev)  # noqa: E731
+    out = {"T_norm": f(b, 4, 4), "tCR": f(b, 3), "TCV_O": f(b, n_views, 4, 4), "K_crop": f(b, 3, 3), "boxes_rend": f(b, 4),
+           "boxes_crop": f(b, 4), "KV_crop": f(b, n_views, 3, 3)}
+    rc = ctx.lib.hpb_refiner_prologue(
+        ctx.handle, ptr(TCO), ptr(K), ptr(obj_ids), ptr(pc), pc.shape[0], pc.shape[1], ptr(pm), pm.shape[1], b, H, W, h, w, lamb, mv,
+        n_views, int(remove_TCO_rendering), ptr(out["T_norm"]), ptr(out["tCR"]), ptr(out["TCV_O"]), ptr(out["K_crop"]),
+        ptr(out["boxes_rend"]), ptr(out["boxes_crop"]), ptr(out["KV_crop"]), stream_ptr(dev))
+    ctx.check(rc, "hpb_refiner_prologue")
+    return out
+
+
 def crop_boxes(ctx: Context, image_size, points, obj_ids, K, TCO, tCR, render_size, lamb: float = 1.4):
     """compute_crops_multiview maths: (K_crop, boxes_rend, boxes_crop) without resampling any pixels."""
     dev = ctx.device

@@ -205,6 +205,29 @@ int hpb_crop_boxes(hpb_ctx *ctx, int H, int W, const float *points_dev, int n_ob
                    int b, int h, int w, float lamb, float *K_crop_dev, float *boxes_rend_dev,
                    float *boxes_crop_dev, void *stream);
 
+/*
+ * The resampling half of hpb_crop on its own: crops_dev [b,C,h,w] = roi_align of the frames at boxes_crop_dev [b,4]
+ * (x1,y1,x2,y2), e.g. the boxes hpb_refiner_prologue produced.  Arguments as in hpb_crop.
+ */
+int hpb_crop_pixels(hpb_ctx *ctx, const float *images_dev, int n_im, int C, int H, int W, const int32_t *im_ids_dev,
+                    const float *boxes_crop_dev, int b, int h, int w, float *crops_dev, int64_t crops_bstride, int tap_bits,
+                    void *stream);
+
+/*
+ * Fused prologue of one refiner iteration (PosePredictor.forward, pose_rigid.py:570-612), ONE launch for what the reference
+ * does in ~60 eager ops plus a per-sample CPU loop: T_norm = normalize_T(TCO); tCR = its translation (reference point =
+ * object origin); TCV_O = make_TCO_multiview(T_norm, tCR, mv_type, n_views, remove_tco_rendering); the row's crop geometry
+ * (boxes_rend, boxes_crop, K_crop) from the n_pts_crop-point set (crop_inputs :199-277 without the resampling); and
+ * KV_crop [b,n_views,9] from the n_pts_mv-point set per view (compute_crops_multiview :279-337) with view 0 = K_crop unless
+ * remove_tco_rendering (:610-611).  Bit-identical to hpb_normalize_T -> hpb_multiview -> hpb_crop_boxes -> hpb_crop_boxes.
+ * KV_crop_dev may be NULL (single-view models).  points_*_dev [n_obj, n_pts, 3], obj_ids_dev [b].
+ */
+int hpb_refiner_prologue(hpb_ctx *ctx, const float *TCO_dev, const float *K_dev, const int32_t *obj_ids_dev,
+                         const float *points_crop_dev, int n_obj, int n_pts_crop, const float *points_mv_dev, int n_pts_mv, int b,
+                         int H, int W, int h, int w, float lamb, int mv_type, int n_views, int remove_tco_rendering,
+                         float *T_norm_dev, float *tCR_dev, float *TCV_O_dev, float *K_crop_dev, float *boxes_rend_dev,
+                         float *boxes_crop_dev, float *KV_crop_dev, void *stream);
+
 /* T -> normalize_T(T): Gram-Schmidt on columns 0,1 of R, translation kept, last row (0,0,0,1). In place allowed. */
 int hpb_normalize_T(hpb_ctx *ctx, const float *T_dev, int b, float *T_out_dev, void *stream);
 

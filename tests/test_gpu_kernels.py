@@ -459,6 +459,48 @@ def test_multiview_matches_oracle(ctx):
     assert np.isfinite(got[1:]).all()
 
 
+def test_refiner_prologue_equals_the_separate_kernels(ctx, can):
+    """hpb_refiner_prologue (one launch per refiner iteration) is bit-identical to hpb_normalize_T -> hpb_multiview ->
+    hpb_crop_boxes (2000 points) -> hpb_crop_boxes per view (200 points) -> KV_crop[:, 0] = K_crop, for every multiview
+    type, with and without the TCO view, and hpb_crop_pixels at its boxes equals hpb_crop's pixels."""
+    from happypose_b200 import ops
+
+    om, _ = can
+    rs = np.random.RandomState(17)
+    dev = torch.device("cuda")
+    b = 7
+    T, _ = random_crop_scene(rs, b, z_range=(0.35, 1.0))
+    T[:, :2, 3] += rs.uniform(-0.1, 0.1, (b, 2)).astype(np.float32)
+    T[:, :3, :3] += rs.uniform(-0.01, 0.01, (b, 3, 3)).astype(np.float32)  # not orthonormal: normalize_T has work to do
+    K = np.tile(np.array([[605.95, 0, 319.03], [0, 605.01, 249.68], [0, 0, 1]], np.float32), (b, 1, 1))
+    pts2000 = torch.as_tensor(np.stack([om.pos[rs.choice(len(om.pos), 2000, replace=False)] for _ in range(2)])).to(dev)
+    pts200 = torch.as_tensor(np.stack([om.pos[rs.choice(len(om.pos), 200, replace=False)] for _ in range(2)])).to(dev)
+    obj_ids = torch.as_tensor(rs.randint(0, 2, b).astype(np.int32)).to(dev)
+    Tt, Kt = torch.as_tensor(T).to(dev), torch.as_tensor(K).to(dev)
+    for mv, nv, remove in (("TCO+front_3views", 4, False), ("TCO+front_3views", 3, True), ("TCO+front_1view", 2, False),
+                           ("sphere_26views", 27, False), ("TCO+front_3views", 1, False)):
+        got = ops.refiner_prologue(ctx, Tt, Kt, obj_ids, pts2000, pts200, (480, 640), (240, 320), mv, nv, remove)
+        Tn = ops.normalize_T(ctx, Tt)
+        tCR = Tn[:, :3, 3].contiguous()
+        TV = ops.multiview(ctx, Tn, tCR, mv, nv, remove)
+        Kc, br, bc = ops.crop_boxes(ctx, (480, 640), pts2000, obj_ids, Kt, Tn, tCR, (240, 320))
+        KV, _, _ = ops.crop_boxes(ctx, (480, 640), pts200, obj_ids.repeat_interleave(nv), Kt.repeat_interleave(nv, 0), TV.flatten(0, 1),
+                                  TV[:, :, :3, 3].reshape(-1, 3).contiguous(), (240, 320))
+        KV = KV.view(b, nv, 3, 3).clone()
+        if not remove:
+            KV[:, 0] = Kc
+        for name, a, w in (("T_norm", got["T_norm"], Tn), ("tCR", got["tCR"], tCR), ("TCV_O", got["TCV_O"], TV), ("K_crop", got["K_crop"], Kc),
+                           ("boxes_rend", got["boxes_rend"], br), ("boxes_crop", got["boxes_crop"], bc), ("KV_crop", got["KV_crop"], KV)):
+            assert torch.equal(a, w), f"{name} differs for {mv} / {nv} views"
+    img = torch.as_tensor(rs.rand(2, 3, 480, 640).astype(np.float32)).to(dev)
+    im_ids = torch.as_tensor(rs.randint(0, 2, b).astype(np.int32)).to(dev)
+    for tap in (32, 16):
+        want, _, _, bc2 = ops.crop(ctx, img, im_ids, pts2000, obj_ids, Kt, Tn, tCR, (240, 320), tap_bits=tap)
+        x = torch.zeros((b, 9, 240, 320), device=dev)
+        crops = ops.crop_pixels(ctx, img, im_ids, bc2, (240, 320), out=x, tap_bits=tap)
+        assert torch.equal(crops, want) and crops.data_ptr() == x.data_ptr() and not x[:, 3:].any()
+
+
 def test_normalize_depth(ctx):
     from happypose_b200 import ops
 
@@ -547,6 +589,7 @@ def test_point_lights_match_oracle(ctx, can):
     om, mid = can
     rs = np.random.RandomState(41)
     b = 8
+    H, W = 240, 320
     T, K = random_crop_scene(rs, b)
     radius = float(np.linalg.norm(om.pos - 0.5 * (om.pos.min(0) + om.pos.max(0)), axis=1).max())
     axes = np.array([[1, 0, 0], [-1, 0, 0], [0, 1, 0], [0, -1, 0], [0, 0, 1], [0, 0, -1]], np.float32)
