@@ -32,6 +32,7 @@ SIGNATURES = {
     "hpb_destroy": (c_int, [c_void_p]),
     "hpb_launch_count": (c_int64, [c_void_p]),
     "hpb_workspace_epoch": (c_int64, [c_void_p]),
+    "hpb_raster_clipped_scenes": (c_int, [c_void_p, ctypes.POINTER(c_int64), c_int]),
     "hpb_reserve": (c_int, [c_void_p, c_int, c_int, c_int64, c_int64, c_int64]),
     "hpb_mesh_upload": (c_int, [c_void_p] * 5 + [c_int64, c_void_p, c_int64, c_void_p, c_int, c_int, c_int, ctypes.POINTER(c_int32)]),
     "hpb_mesh_count": (c_int, [c_void_p]),
@@ -154,6 +155,12 @@ class Context:
     def workspace_epoch(self) -> int:
         """Bumped whenever a workspace buffer was replaced by a larger one (captured graphs may want re-capturing)."""
         return int(self.lib.hpb_workspace_epoch(self.handle))
+
+    def clipped_scenes(self, reset: bool = False) -> int:
+        """Scenes rendered so far in which the near plane cut the mesh (their cut triangles were dropped, not clipped)."""
+        n = c_int64(0)
+        _check(self.lib.hpb_raster_clipped_scenes(self.handle, ctypes.byref(n), 1 if reset else 0), "hpb_raster_clipped_scenes")
+        return int(n.value)
 
     def reserve(self, render_size=(0, 0), frame_pixels: int = 0, topk_rows: int = 0, topk_groups: int = 0) -> None:
         """Sizes the workspaces up front (hpb_reserve) so that no launch has to allocate, e.g. under graph capture."""

@@ -212,6 +212,12 @@ int hpb_create(int device, hpb_ctx **out) {
         delete ctx;
         return HPB_EINVAL;
     }
+    if (cudaMalloc(&ctx->clipped_scenes, sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMemset(ctx->clipped_scenes, 0, sizeof(unsigned long long)) != cudaSuccess) {
+        hpb_set_error("hpb_create: device allocation failed");
+        delete ctx;
+        return HPB_ENOMEM;
+    }
     *out = ctx;
     return HPB_OK;
 }
@@ -224,6 +230,7 @@ int hpb_destroy(hpb_ctx *ctx) {
     }
     for (void *p : ctx->retired) cudaFree(p);
     if (ctx->done_ev) cudaEventDestroy(ctx->done_ev);
+    cudaFree(ctx->clipped_scenes);
     cudaFree(ctx->meshes_dev);
     cudaFree(ctx->vis);
     cudaFree(ctx->vert_scratch);
@@ -235,6 +242,16 @@ int hpb_destroy(hpb_ctx *ctx) {
 
 int64_t hpb_launch_count(const hpb_ctx *ctx) { return ctx ? ctx->launches : 0; }
 int64_t hpb_workspace_epoch(const hpb_ctx *ctx) { return ctx ? ctx->workspace_epoch : 0; }
+
+int hpb_raster_clipped_scenes(hpb_ctx *ctx, int64_t *count, int reset) {
+    HPB_REQUIRE(ctx && count, "NULL argument");
+    HpbDeviceGuard guard(ctx->device);
+    unsigned long long v = 0;
+    HPB_CUDA_OK(cudaMemcpy(&v, ctx->clipped_scenes, sizeof(v), cudaMemcpyDeviceToHost));  // synchronises the device
+    if (reset) HPB_CUDA_OK(cudaMemset(ctx->clipped_scenes, 0, sizeof(v)));
+    *count = (int64_t)v;
+    return HPB_OK;
+}
 
 int hpb_reserve(hpb_ctx *ctx, int render_h, int render_w, int64_t frame_pixels, int64_t topk_rows, int64_t topk_groups) {
     HPB_REQUIRE(ctx, "NULL ctx");

@@ -69,6 +69,7 @@ struct hpb_ctx {
     void *topk_ws = nullptr;
     size_t topk_ws_bytes = 0;
     int64_t launches = 0;
+    unsigned long long *clipped_scenes = nullptr;  // device counter (hpb_raster_clipped_scenes)
     // Workspaces only ever GROW, and a buffer that is replaced is retired (kept allocated until hpb_destroy), never freed:
     // kernel parameters baked into captured CUDA graphs keep pointing at valid, correctly initialised memory.
     // workspace_epoch counts replacements so that a caller can re-capture its graphs onto the new buffers.

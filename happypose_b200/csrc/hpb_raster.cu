@@ -67,6 +67,7 @@ struct RasterParams {
     long long rgb_bs, nrm_bs, depth_bs, mask_bs;
     int views;            // scene i writes at base + (i / views) * bstride + (i % views) * view_stride
     long long view_stride;
+    unsigned long long *clipped_scenes;  // device counter: scenes in which the near plane cut the mesh (those triangles are dropped)
     unsigned long long *vis;      // [clusters][h*w]
     unsigned char *vert_scratch;  // [CTAs][max_nv * 12]: screen-space vertices of the meshes that do not fit in shared memory
     int max_nv;                   // largest (even-padded) vertex count of any uploaded mesh = scratch slice size / 12
@@ -437,6 +438,7 @@ __global__ void __launch_bounds__(RASTER_THREADS, 1) hpb_raster_kernel(const Ras
             }
             if (__any_sync(0xffffffffu, clipped) && lane == 0) sClipped = 1;
             __syncthreads();
+            if (tid == 0 && rank == 0 && sClipped && p.clipped_scenes) atomicAdd(p.clipped_scenes, 1ull);
             HPB_PHASE_MARK(1)  // phase A
             if (sBox[0] <= sBox[2]) {
                 bx0 = max(ceil_div_pix(sBox[0]), 0); bx1 = min(floor_div_pix(sBox[2]), p.w - 1);
@@ -949,6 +951,7 @@ int hpb_launch_raster(hpb_ctx *ctx, const int32_t *mesh_ids, const float *TCO, c
     p.rgb_bs = rgb_bs; p.nrm_bs = nrm_bs; p.depth_bs = depth_bs; p.mask_bs = mask_bs;
     p.views = views; p.view_stride = view_stride;
     p.vis = ctx->vis;
+    p.clipped_scenes = ctx->clipped_scenes;
     p.vert_scratch = ctx->vert_scratch;
     p.max_nv = nv_pad;
     p.smem_verts = (int)(smem / 12);

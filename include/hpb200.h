@@ -102,6 +102,14 @@ int64_t hpb_launch_count(const hpb_ctx *ctx);
  * streams the library orders them with an event, so two streams never race on it.
  */
 int64_t hpb_workspace_epoch(const hpb_ctx *ctx);
+
+/*
+ * Number of rendered scenes, since the context was created (or since the last call with reset != 0), in which at least one
+ * mesh vertex lay in front of the near plane.  The rasteriser DROPS the triangles of such vertices instead of clipping them
+ * against the plane as OpenGL does (stated deviation); this counter lets a caller (and the parity tests) check
+ * that a workload never gets there: MegaPose / CosyPose place objects at 0.3 .. 2 m with z_near = 0.1 m.  Synchronises.
+ */
+int hpb_raster_clipped_scenes(hpb_ctx *ctx, int64_t *count, int reset);
 int hpb_reserve(hpb_ctx *ctx, int render_h, int render_w, int64_t frame_pixels, int64_t topk_rows, int64_t topk_groups);
 
 /*

@@ -437,3 +437,50 @@ def test_cuda_graph_replay_matches_eager(models):
     for poses, logits in results[1:]:
         assert torch.allclose(poses, results[0][0], atol=1e-5)
         np.testing.assert_allclose(logits, results[0][1], rtol=1e-4, atol=1e-4)
+
+
+def test_hot_path_never_reaches_the_near_plane_and_the_counter_sees_it_when_forced(models, scene):
+    """The rasteriser drops near-plane triangles instead of clipping them (stated deviation from OpenGL).  A full pipeline
+    run (576 SO(3)-grid hypotheses initialised from the detection box, 5 refiner iterations x 4 views, scoring) renders 597
+    scenes and none of them has a vertex in front of z_near = 0.1 m; a pose pushed through the near plane is counted."""
+    from happypose_b200 import ops
+    from happypose_b200.inference.types import ObservationTensor
+    from happypose_b200.megapose.pose_estimator import PoseEstimator
+
+    coarse, refiner = models[0], models[1]
+    ctx = coarse._ctx()
+    est = PoseEstimator(refiner_model=refiner, coarse_model=coarse, bsz_objects=8, bsz_images=576, SO3_grid_size=576)
+    image = np.random.RandomState(28).rand(1, 3, 480, 640).astype(np.float32)
+    obs = ObservationTensor(torch.as_tensor(image), torch.as_tensor(K_BBQ[None])).cuda()
+    ctx.clipped_scenes(reset=True)
+    det, _, _ = _detections(2)
+    final, _ = est.run_inference_pipeline(obs, detections=det, n_refiner_iterations=5, n_pose_hypotheses=1)
+    assert len(final) == 2 and ctx.clipped_scenes() == 0
+    T, Km, res = reference_test_scene()
+    T = T.copy()
+    T[2, 3] = 0.12  # the can (70 mm half height, here along the optical axis) now straddles z = 0.1
+    mesh_ids = coarse.renderer.mesh_ids(["my_favorite_object_label"])
+    ops.render(ctx, mesh_ids, torch.as_tensor(T[None]).float(), torch.as_tensor(Km[None]).float(), res, render_depth=True)
+    assert ctx.clipped_scenes(reset=True) == 1 and ctx.clipped_scenes() == 0
+
+
+def test_prediction_runner_with_the_real_estimator(models):
+    """evaluation/prediction_runner.py over two synthetic frames with ground-truth-style detections."""
+    from happypose_b200.evaluation.prediction_runner import PredictionRunner
+    from happypose_b200.inference.types import InferenceConfig
+    from happypose_b200.megapose.pose_estimator import PoseEstimator
+
+    coarse, refiner = models[0], models[1]
+    est = PoseEstimator(refiner_model=refiner, coarse_model=coarse, SO3_grid_size=72)
+    frames = []
+    for i in range(2):
+        det, _, _ = _detections(2, device="cpu")
+        frames.append({"rgb": (np.random.RandomState(40 + i).rand(480, 640, 3) * 255).astype(np.uint8), "K": K_BBQ, "detections": det,
+                       "im_info": {"scene_id": 1, "view_id": 10 + i}})
+    cfg = InferenceConfig(detection_type="gt", n_refiner_iterations=2, n_pose_hypotheses=1, bsz_images=72, bsz_objects=4)
+    preds = PredictionRunner(frames, cfg).get_predictions(est)
+    assert set(preds) == {"final", "refiner/iteration=2", "refiner/final", "coarse"}
+    assert len(preds["final"]) == 4 and len(preds["coarse"]) == 4 * 72
+    f = preds["final"].infos
+    assert f["view_id"].tolist() == [10, 10, 11, 11] and (f["time"] > 0).all() and "pose_score" in f
+    assert preds["final"].poses.shape == (4, 4, 4) and torch.isfinite(preds["final"].poses).all()
