@@ -43,6 +43,8 @@ int hpb_launch_refiner_prologue(hpb_ctx *ctx, const float *TCO_in, const float *
                                 float *TCV_O, float *K_crop, float *boxes_rend, float *boxes_crop, float *KV_crop,
                                 cudaStream_t stream);
 
+int hpb_launch_maxpool_tma(hpb_ctx *ctx, const void *in, int b, int H, int W, int C, void *out, cudaStream_t stream);
+
 static thread_local char g_err[512] = "";
 
 int hpb_ws_grow(hpb_ctx *ctx, void **ptr, size_t *cur_bytes, size_t need, cudaStream_t stream, const char *what) {
@@ -551,6 +553,12 @@ int hpb_crop_bf16x4(hpb_ctx *ctx, const float *images_dev, int n_im, int H, int 
     return HPB_OK;
 }
 
+int hpb_set_maxpool_tma(hpb_ctx *ctx, int enable) {
+    HPB_REQUIRE(ctx, "NULL ctx");
+    ctx->maxpool_tma = enable ? 1 : 0;
+    return HPB_OK;
+}
+
 int hpb_set_crop_tap_precision(hpb_ctx *ctx, int bits) {
     HPB_REQUIRE(ctx, "NULL ctx");
     HPB_REQUIRE(bits == 32 || bits == 16, "bits must be 32 or 16");
@@ -733,6 +741,10 @@ int hpb_maxpool3x3s2_bf16_nhwc(hpb_ctx *ctx, const void *in_dev, int b, int H, i
     HPB_REQUIRE(in_dev && out_dev, "NULL pointer");
     HPB_REQUIRE((((uintptr_t)in_dev | (uintptr_t)out_dev) & 15) == 0, "buffers must be 16-byte aligned");
     HpbDeviceGuard guard(ctx->device);
+    if (ctx->maxpool_tma) {  // TMA-staged tiles for the shapes it serves (C = 64, the ResNet stem); otherwise the plain kernel
+        const int rc = hpb_launch_maxpool_tma(ctx, in_dev, b, H, W, C, out_dev, (cudaStream_t)stream);
+        if (rc != HPB_ENOTFOUND) return rc;
+    }
     return hpb_launch_maxpool(ctx, in_dev, b, H, W, C, out_dev, (cudaStream_t)stream);
 }
 

@@ -338,6 +338,9 @@ int hpb_icp_points(hpb_ctx *ctx, const float *depth_measured_dev, int n_im, cons
  * Bit-identical to torch.nn.functional.max_pool2d (max is exact; NaN propagates).
  */
 int hpb_maxpool3x3s2_bf16_nhwc(hpb_ctx *ctx, const void *in_dev, int b, int H, int W, int C, void *out_dev, void *stream);
+/* C = 64 (the stem) is served by a tile kernel whose input box is staged by TMA (cp.async.bulk.tensor.4d + mbarrier);
+ * enable = 0 selects the plain 9-loads-per-output kernel for every shape (A/B measurements, tests).  Same results. */
+int hpb_set_maxpool_tma(hpb_ctx *ctx, int enable);
 
 #ifdef __cplusplus
 }

@@ -66,5 +66,23 @@ def main():
         ms = timeit(lambda: ops.crop(ctx, img, zero, pts, zero, K, TCO, tCR, (240, 320), out=x, tap_bits=16))
         print(json.dumps({"kernel": "crop (boxes+pixels), fp16 taps", "b": b, "ms": round(ms, 4), "hyps_per_s": round(b / ms * 1e3), "GBps": round(gb / ms * 1e3, 1), "frac": round(gb / ms * 1e3 / peak, 4)}))
 
+def maxpool_bench():
+    """The stem's max-pool at the coarse batch: plain kernel vs the TMA-staged tile kernel (same process, same box)."""
+    dev = torch.device("cuda:0")
+    ctx = Context.get(dev)
+    peak = B.measured_peak_gbs()[0]
+    x = torch.randn(576, 64, 120, 160, device=dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    gb = (x.numel() * 2 + x.numel() // 4 * 2) / 1e9
+    for tma in (0, 1, 0, 1):
+        ctx.check(ctx.lib.hpb_set_maxpool_tma(ctx.handle, tma), "hpb_set_maxpool_tma")
+        ms = timeit(lambda: ops.maxpool3x3s2_bf16(ctx, x), it=20)
+        print(json.dumps({"kernel": "maxpool3x3s2 bf16 NHWC [576,64,120,160]", "tma": tma, "ms": round(ms, 4), "GBps": round(gb / ms * 1e3, 1),
+                          "frac": round(gb / ms * 1e3 / peak, 4)}))
+    ctx.check(ctx.lib.hpb_set_maxpool_tma(ctx.handle, 1), "hpb_set_maxpool_tma")
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "maxpool":
+        maxpool_bench()
+        sys.exit(0)
     main()

@@ -694,11 +694,19 @@ def test_maxpool_bf16_nhwc_is_bit_exact(ctx):
     from happypose_b200 import ops
 
     torch.manual_seed(2)
-    for shape in ((2, 64, 120, 160), (1, 8, 7, 9), (3, 16, 2, 2)):
-        x = torch.randn(shape, device="cuda").to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
-        got = ops.maxpool3x3s2_bf16(ctx, x)
+    # C = 64 goes through the TMA-staged tile kernel (hpb_maxpool_tma.cu: tiles of 16 x 8 outputs, so odd sizes exercise
+    # partial tiles and the masked padding taps; negative inputs show that the TMA's zero fill never leaks into a result),
+    # other channel counts through the plain kernel; both against torch
+    for shape in ((2, 64, 120, 160), (3, 64, 37, 53), (1, 64, 5, 3), (150, 64, 16, 24), (1, 8, 7, 9), (3, 16, 2, 2)):
+        x = (torch.randn(shape, device="cuda") - 0.5).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
         ref = torch.nn.functional.max_pool2d(x, 3, 2, 1)
-        assert got.shape == ref.shape and torch.equal(got, ref)
+        for tma in (True, False):
+            ctx.check(ctx.lib.hpb_set_maxpool_tma(ctx.handle, 1 if tma else 0), "hpb_set_maxpool_tma")
+            got = ops.maxpool3x3s2_bf16(ctx, x)
+            assert got.shape == ref.shape and torch.equal(got, ref), f"{shape} tma={tma}"
+    ctx.check(ctx.lib.hpb_set_maxpool_tma(ctx.handle, 1), "hpb_set_maxpool_tma")
+    x = torch.full((1, 64, 6, 6), float("nan"), device="cuda").to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    assert torch.isnan(ops.maxpool3x3s2_bf16(ctx, x)).all()  # NaN propagates like torch
 
 
 def test_folded_resnet_bf16_close_to_module(ctx):
