@@ -70,6 +70,7 @@ SIGNATURES = {
     "hpb_icp_points": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_int64,
                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "hpb_set_maxpool_tma": (c_int, [c_void_p, c_int]),
+    "hpb_set_crop_tma": (c_int, [c_void_p, c_int]),
     "hpb_topk_segmented": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
 }
 

@@ -553,6 +553,12 @@ int hpb_crop_bf16x4(hpb_ctx *ctx, const float *images_dev, int n_im, int H, int 
     return HPB_OK;
 }
 
+int hpb_set_crop_tma(hpb_ctx *ctx, int enable) {
+    HPB_REQUIRE(ctx, "NULL ctx");
+    ctx->crop_tma = enable ? 1 : 0;
+    return HPB_OK;
+}
+
 int hpb_set_maxpool_tma(hpb_ctx *ctx, int enable) {
     HPB_REQUIRE(ctx, "NULL ctx");
     ctx->maxpool_tma = enable ? 1 : 0;

@@ -18,16 +18,12 @@
 //                           im_id: no per-hypothesis copy of the frame (the reference materialises images[batch_im_ids],
 //                           pose_estimator.py:390).  Stores are coalesced along x.  RGB-D frames also resample the
 //                           depth-validity map and zero depth where validity < 0.99 (cropping.py:181-195).
-#include <cuda_bf16.h>
-#include <cuda_fp16.h>
-
+#include "hpb_crop_math.cuh"
 #include "hpb_pose_math.cuh"
 
 namespace {
 
-constexpr int CROP_SPAN = 4;       // dense tap span handled by the fast path
-constexpr int CROP_BAND_MAX = 120;  // most output rows one CTA handles (fewer when the batch is small)
-constexpr int CROP_MAX_THREADS = 320;  // output columns per CTA (wider outputs use several column tiles, blockIdx.z)
+using namespace hpbc;
 
 struct CropBoxParams {
     const float *points;
@@ -46,27 +42,6 @@ __global__ void __launch_bounds__(256) hpb_crop_boxes_kernel(const CropBoxParams
     hpbm::crop_boxes_cta(p.K + (size_t)n * 9, p.TCO + (size_t)n * 16, p.tCR + (size_t)n * 3,
                          p.points + (size_t)p.obj_ids[n] * p.n_pts * 3, p.n_pts, p.H, p.W, p.h, p.w, p.lamb, p.K_crop + (size_t)n * 9,
                          p.boxes_rend + (size_t)n * 4, p.boxes_crop + (size_t)n * 4, sP, red);
-}
-
-struct CropPixParams {
-    const float *images;
-    const int32_t *im_ids;
-    const float *boxes;  // [b,4]
-    int n_im, C, H, W, b, h, w;
-    float *crops;
-    long long crops_bs;
-    int band;  // output rows per CTA
-    const float4 *packed;  // [n_im,H,W] pixel-interleaved copy of `images` (r,g,b,depth|0) or nullptr
-    const uint2 *packed_h;  // same in fp16 (r,g,b,0): 8-byte taps (hpb_set_crop_tap_precision(ctx, 16), RGB frames)
-    uint2 *crops_h;         // OUTFMT 1: [b][h][w] (r,g,b,0) bfloat16 pixels, batch stride crops_bs pixels (hpb_crop_bf16x4)
-};
-
-__device__ __forceinline__ uint2 pack_bf16x4(float r, float g, float b) {
-    const __nv_bfloat162 rg = __floats2bfloat162_rn(r, g);
-    uint2 v;
-    v.x = *reinterpret_cast<const unsigned *>(&rg);
-    v.y = (unsigned)__bfloat16_as_ushort(__float2bfloat16_rn(b));
-    return v;
 }
 
 // Planar [n_im,C,H,W] -> pixel-interleaved float4 [n_im,H,W]: the crop then fetches all channels of a tap with ONE
@@ -101,66 +76,6 @@ __global__ void hpb_pack_frames_half_kernel(const float *images, long long n_px_
         v.y = *reinterpret_cast<const unsigned *>(&b0);
         out[i] = v;
     }
-}
-
-// One roi_align sample coordinate along one axis (torchvision roi_align bilinear_interpolate, aligned=False).
-struct AxisTap {
-    int lo, hi;
-    float wlo, whi;
-    bool valid;
-};
-
-__device__ __forceinline__ AxisTap axis_tap(float c, int n) {
-    AxisTap t;
-    t.valid = !(c < -1.0f || c > (float)n);
-    if (c <= 0.0f) c = 0.0f;
-    int lo = (int)c;
-    int hi;
-    if (lo >= n - 1) {
-        lo = hi = n - 1;
-        c = (float)lo;
-    } else {
-        hi = lo + 1;
-    }
-    const float l = c - (float)lo;
-    t.lo = lo; t.hi = hi; t.whi = l; t.wlo = 1.0f - l;
-    return t;
-}
-
-// Dense tap weights of the 4 samples of output bin `i` along one axis.  Returns false when the span exceeds
-// CROP_SPAN (heavy down-sampling): the caller then takes the generic path.
-__device__ __forceinline__ bool axis_weights(float start, float bin, int i, int n, int &base, float (&wt)[CROP_SPAN]) {
-    AxisTap t0 = axis_tap(start + (float)i * bin + (0.0f + 0.5f) * bin / 4.0f, n);
-    AxisTap t1 = axis_tap(start + (float)i * bin + (1.0f + 0.5f) * bin / 4.0f, n);
-    AxisTap t2 = axis_tap(start + (float)i * bin + (2.0f + 0.5f) * bin / 4.0f, n);
-    AxisTap t3 = axis_tap(start + (float)i * bin + (3.0f + 0.5f) * bin / 4.0f, n);
-    int lo_min = 0x7fffffff, hi_max = -1;
-    if (t0.valid) { lo_min = min(lo_min, t0.lo); hi_max = max(hi_max, t0.hi); }
-    if (t1.valid) { lo_min = min(lo_min, t1.lo); hi_max = max(hi_max, t1.hi); }
-    if (t2.valid) { lo_min = min(lo_min, t2.lo); hi_max = max(hi_max, t2.hi); }
-    if (t3.valid) { lo_min = min(lo_min, t3.lo); hi_max = max(hi_max, t3.hi); }
-    float w0 = 0.0f, w1 = 0.0f, w2 = 0.0f, w3 = 0.0f;
-    wt[0] = wt[1] = wt[2] = wt[3] = 0.0f;
-    if (hi_max < 0) {  // no valid sample: all-zero weights
-        base = 0;
-        return true;
-    }
-    if (hi_max - lo_min >= CROP_SPAN) return false;
-    base = lo_min;
-    // scatter-add of the 8 (tap, weight) pairs written as selects on scalars: keeps everything in registers (an indexed
-    // wt[lo - base] += ... is turned into local-memory loads/stores by the compiler)
-    auto add = [&](int d, float v) {
-        w0 += d == 0 ? v : 0.0f;
-        w1 += d == 1 ? v : 0.0f;
-        w2 += d == 2 ? v : 0.0f;
-        w3 += d == 3 ? v : 0.0f;
-    };
-    if (t0.valid) { add(t0.lo - lo_min, 0.25f * t0.wlo); add(t0.hi - lo_min, 0.25f * t0.whi); }
-    if (t1.valid) { add(t1.lo - lo_min, 0.25f * t1.wlo); add(t1.hi - lo_min, 0.25f * t1.whi); }
-    if (t2.valid) { add(t2.lo - lo_min, 0.25f * t2.wlo); add(t2.hi - lo_min, 0.25f * t2.whi); }
-    if (t3.valid) { add(t3.lo - lo_min, 0.25f * t3.wlo); add(t3.hi - lo_min, 0.25f * t3.whi); }
-    wt[0] = w0; wt[1] = w1; wt[2] = w2; wt[3] = w3;
-    return true;
 }
 
 // One thread per output COLUMN, marching down the band's rows.  roi_align's 4x4 samples per output pixel are separable:
@@ -386,6 +301,8 @@ __global__ void __launch_bounds__(CROP_MAX_THREADS, 3) hpb_crop_pixels_kernel(co
 
 }  // namespace
 
+int hpb_launch_crop_tma(hpb_ctx *ctx, const hpbc::CropPixParams &p0, int band, cudaStream_t stream);
+
 int hpb_launch_crop_boxes(hpb_ctx *ctx, int H, int W, const float *points, int n_pts, const int32_t *obj_ids,
                           const float *K, const float *TCO, const float *tCR, int b, int h, int w, float lamb,
                           float *K_crop, float *boxes_rend, float *boxes_crop, cudaStream_t stream) {
@@ -444,6 +361,13 @@ int hpb_launch_crop_pixels(hpb_ctx *ctx, const float *images, int n_im, int C, i
     const int threads = w >= CROP_MAX_THREADS ? CROP_MAX_THREADS : ((w + 31) / 32) * 32;  // one thread per output column
     const size_t smem = (size_t)band * CROP_SPAN * sizeof(float) + (size_t)band * sizeof(int);
     dim3 grid((h + band - 1) / band, b, (w + threads - 1) / threads);
+    if (C == 3 && p.packed_h && ctx->crop_tma) {  // fp16 taps of an RGB frame: source rows streamed by TMA (hpb_crop_tma.cu)
+        const int rc = hpb_launch_crop_tma(ctx, p, band, stream);
+        if (rc != HPB_ENOTFOUND) {
+            if (rc == HPB_OK) hpb_stream_leave(ctx, stream);
+            return rc;
+        }
+    }
     if (C == 3 && p.crops_h) {
         if (p.packed_h) hpb_crop_pixels_kernel<3, 2, 1><<<grid, threads, smem, stream>>>(p);
         else if (p.packed) hpb_crop_pixels_kernel<3, 1, 1><<<grid, threads, smem, stream>>>(p);

@@ -206,6 +206,12 @@ int hpb_crop_bf16x4(hpb_ctx *ctx, const float *images_dev, int n_im, int H, int 
  * used by launches that pass tap_bits = 0.  Host-side switch, no sync.
  */
 int hpb_set_crop_tap_precision(hpb_ctx *ctx, int bits);
+/*
+ * With 16-bit taps of an RGB frame the crop's source rows are streamed into shared memory by the TMA unit
+ * (cp.async.bulk.tensor.3d boxes + mbarrier ring, hpb_crop_tma.cu) instead of being gathered by per-lane loads; results are
+ * bit-identical.  enable = 0 selects the per-lane kernel for everything (A/B measurements, tests).  Default: enabled.
+ */
+int hpb_set_crop_tma(hpb_ctx *ctx, int enable);
 
 /* Boxes and K_crop only (compute_crops_multiview: return_crops=False, 200 points). H,W = source frame size. */
 int hpb_crop_boxes(hpb_ctx *ctx, int H, int W, const float *points_dev, int n_obj, int n_pts,

@@ -66,6 +66,34 @@ def main():
         ms = timeit(lambda: ops.crop(ctx, img, zero, pts, zero, K, TCO, tCR, (240, 320), out=x, tap_bits=16))
         print(json.dumps({"kernel": "crop (boxes+pixels), fp16 taps", "b": b, "ms": round(ms, 4), "hyps_per_s": round(b / ms * 1e3), "GBps": round(gb / ms * 1e3, 1), "frac": round(gb / ms * 1e3 / peak, 4)}))
 
+def crop_bench():
+    """fp16-tap crop at the coarse batch: per-lane gather kernel vs the TMA ring kernel (same process, same box)."""
+    dev = torch.device("cuda:0")
+    ctx = Context.get(dev)
+    d = np.load(B.MESH)
+    pos = (d["verts"].astype(np.float64) * 0.001).astype(np.float32)
+    grid = transform_utils.load_SO3_grid(576).to(dev)
+    pts_all = torch.as_tensor(pos[None]).to(dev)
+    pts = torch.as_tensor(pos[np.random.RandomState(0).choice(len(pos), 2000, replace=False)][None]).to(dev)
+    img = torch.rand(1, 3, 480, 640, device=dev)
+    peak = B.measured_peak_gbs()[0]
+    for b in (576, 2304):
+        R = grid[torch.arange(b, device=dev) % 576]
+        zero = torch.zeros(b, dtype=torch.int32, device=dev)
+        K = torch.as_tensor(B.K_BBQ).to(dev).expand(b, 3, 3).contiguous()
+        boxes = torch.as_tensor(B.BBOX_BBQ).to(dev).expand(b, 4).contiguous()
+        TCO = ops.tco_init(ctx, _capi.TCO_INIT_AUTODEPTH_WITH_R, boxes, K, pts_all, zero, R)
+        tCR = TCO[:, :3, 3].contiguous()
+        gb = b * 3 * 240 * 320 * 4 / 1e9
+        for tma in (0, 1, 0, 1):
+            ctx.check(ctx.lib.hpb_set_crop_tma(ctx.handle, tma), "hpb_set_crop_tma")
+            ms = timeit(lambda: ops.crop_bf16x4(ctx, img, zero, pts, zero, K, TCO, tCR, (240, 320), tap_bits=16), it=20)
+            ms32 = timeit(lambda: ops.crop(ctx, img, zero, pts, zero, K, TCO, tCR, (240, 320), tap_bits=16), it=20)
+            print(json.dumps({"kernel": "crop fp16 taps (boxes + pixels)", "b": b, "tma": tma, "bf16x4_ms": round(ms, 4), "planar_f32_ms": round(ms32, 4),
+                              "bf16x4_GBps_8d": round(gb / ms * 1e3, 1), "bf16x4_frac_8d": round(gb / ms * 1e3 / peak, 4)}))
+    ctx.check(ctx.lib.hpb_set_crop_tma(ctx.handle, 1), "hpb_set_crop_tma")
+
+
 def maxpool_bench():
     """The stem's max-pool at the coarse batch: plain kernel vs the TMA-staged tile kernel (same process, same box)."""
     dev = torch.device("cuda:0")
@@ -84,5 +112,8 @@ def maxpool_bench():
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "maxpool":
         maxpool_bench()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "crop":
+        crop_bench()
         sys.exit(0)
     main()

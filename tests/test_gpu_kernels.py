@@ -661,6 +661,43 @@ def test_render_s2d_bf16_equals_render_then_pack(ctx, can):
         assert torch.equal(got128.view(torch.int16), ops.pack_input_s2d_bf16(ctx, x, 128).view(torch.int16))
 
 
+def test_crop_tma_ring_equals_per_lane_kernel(ctx, can):
+    """hpb_crop_tma.cu (source rows streamed by TMA into a shared-memory ring) returns bit for bit what the per-lane gather
+    kernel returns, for fp16 taps of RGB frames: 576-row coarse batch, boxes hanging over every frame edge, narrow outputs,
+    several frames, tiny batches (short bands), both output formats; wide boxes take the generic path in both."""
+    from happypose_b200 import ops
+
+    om, _ = can
+    rs = np.random.RandomState(52)
+    dev = torch.device("cuda")
+    pts = torch.as_tensor(om.pos[rs.choice(len(om.pos), 2000, replace=False)][None]).to(dev)
+
+    def both(fn):
+        out = []
+        for tma in (1, 0):
+            ctx.check(ctx.lib.hpb_set_crop_tma(ctx.handle, tma), "hpb_set_crop_tma")
+            out.append(fn())
+        ctx.check(ctx.lib.hpb_set_crop_tma(ctx.handle, 1), "hpb_set_crop_tma")
+        return out
+
+    for b, n_im, res, spread in ((576, 1, (240, 320), 0.02), (64, 2, (240, 320), 0.35), (9, 1, (60, 80), 0.2), (40, 1, (118, 162), 0.1), (1, 1, (240, 320), 0.0)):
+        T, _ = random_crop_scene(rs, b, z_range=(0.3, 1.1))
+        T[:, :2, 3] += rs.uniform(-spread, spread, (b, 2)).astype(np.float32)  # large spread: boxes leave the frame on all sides
+        if b == 64:
+            T[:4, 2, 3] = 0.13  # a few very wide boxes: generic path
+        K = np.tile(np.array([[605.95, 0, 319.03], [0, 605.01, 249.68], [0, 0, 1]], np.float32), (b, 1, 1))
+        img = torch.as_tensor(rs.rand(n_im, 3, 480, 640).astype(np.float32)).to(dev)
+        im_ids = torch.as_tensor(rs.randint(0, n_im, b).astype(np.int32)).to(dev)
+        zero = torch.zeros(b, dtype=torch.int32, device=dev)
+        Tt, Kt = torch.as_tensor(T).to(dev), torch.as_tensor(K).to(dev)
+        tCR = Tt[:, :3, 3].contiguous()
+        a, c = both(lambda: ops.crop(ctx, img, im_ids, pts, zero, Kt, Tt, tCR, res, tap_bits=16)[0])
+        assert torch.equal(a, c), f"planar b={b} res={res}"
+        assert a.abs().sum() > 0
+        a, c = both(lambda: ops.crop_bf16x4(ctx, img, im_ids, pts, zero, Kt, Tt, tCR, res, tap_bits=16)[0])
+        assert torch.equal(a.view(torch.int16), c.view(torch.int16)), f"bf16x4 b={b} res={res}"
+
+
 def test_crop_bf16x4_is_the_rounded_float32_crop(ctx, can):
     """hpb_crop_bf16x4 = hpb_crop rounded to bfloat16 (nearest even), pixel-interleaved, for float32 and fp16 taps, the
     fast (few frames, many rows) and the generic (wide box) paths; K_crop / boxes identical."""
