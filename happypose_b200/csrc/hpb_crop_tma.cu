@@ -131,7 +131,8 @@ __global__ void __launch_bounds__(TMA_THREADS, 3) hpb_crop_tma_kernel(const __gr
         atomicMax(&sC1, bxx + CROP_SPAN - 1);
     }
     __syncthreads();
-    const int R0 = sR0, R1 = sR1, C0 = sC0;
+    // the TMA wants the first pixel of a box row on a 16-byte boundary: 8-byte pixels -> an even column
+    const int R0 = sR0, R1 = sR1, C0 = sC0 & ~1;
     const int nbx = sC1 >= C0 ? ((sC1 - C0) / BOX_W + 1) : 0;
     const bool generic = sGeneric != 0 || nbx > BOXES_MAX;
     const int im = p.im_ids[n];

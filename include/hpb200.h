@@ -209,7 +209,8 @@ int hpb_set_crop_tap_precision(hpb_ctx *ctx, int bits);
 /*
  * With 16-bit taps of an RGB frame the crop's source rows are streamed into shared memory by the TMA unit
  * (cp.async.bulk.tensor.3d boxes + mbarrier ring, hpb_crop_tma.cu) instead of being gathered by per-lane loads; results are
- * bit-identical.  enable = 0 selects the per-lane kernel for everything (A/B measurements, tests).  Default: enabled.
+ * bit-identical.  Default: DISABLED -- measured on B200 (profiles/r2_tma_kernels.txt) the ring is as fast as the per-lane
+ * kernel at 576 rows and 5 % slower at 2304: the crop is bound by its filter arithmetic, not by where the taps come from.
  */
 int hpb_set_crop_tma(hpb_ctx *ctx, int enable);
 

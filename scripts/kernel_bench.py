@@ -91,7 +91,7 @@ def crop_bench():
             ms32 = timeit(lambda: ops.crop(ctx, img, zero, pts, zero, K, TCO, tCR, (240, 320), tap_bits=16), it=20)
             print(json.dumps({"kernel": "crop fp16 taps (boxes + pixels)", "b": b, "tma": tma, "bf16x4_ms": round(ms, 4), "planar_f32_ms": round(ms32, 4),
                               "bf16x4_GBps_8d": round(gb / ms * 1e3, 1), "bf16x4_frac_8d": round(gb / ms * 1e3 / peak, 4)}))
-    ctx.check(ctx.lib.hpb_set_crop_tma(ctx.handle, 1), "hpb_set_crop_tma")
+    ctx.check(ctx.lib.hpb_set_crop_tma(ctx.handle, 0), "hpb_set_crop_tma")
 
 
 def maxpool_bench():

@@ -677,7 +677,7 @@ def test_crop_tma_ring_equals_per_lane_kernel(ctx, can):
         for tma in (1, 0):
             ctx.check(ctx.lib.hpb_set_crop_tma(ctx.handle, tma), "hpb_set_crop_tma")
             out.append(fn())
-        ctx.check(ctx.lib.hpb_set_crop_tma(ctx.handle, 1), "hpb_set_crop_tma")
+        ctx.check(ctx.lib.hpb_set_crop_tma(ctx.handle, 0), "hpb_set_crop_tma")  # the default
         return out
 
     for b, n_im, res, spread in ((576, 1, (240, 320), 0.02), (64, 2, (240, 320), 0.35), (9, 1, (60, 80), 0.2), (40, 1, (118, 162), 0.1), (1, 1, (240, 320), 0.0)):
