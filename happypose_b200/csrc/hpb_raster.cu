@@ -43,7 +43,10 @@ namespace cg = cooperative_groups;
 
 namespace {
 
-constexpr int RASTER_THREADS = 1024;
+#ifndef HPB_RASTER_THREADS
+#define HPB_RASTER_THREADS 1024
+#endif
+constexpr int RASTER_THREADS = HPB_RASTER_THREADS;
 constexpr int RASTER_WARPS = RASTER_THREADS / 32;
 constexpr int SMALL_TRI_MAX = 32;  // bbox pixels a lane walks on its own; larger triangles are walked by the warp
 constexpr int VTX_CLIPPED = (int)0x80000000;  // screen x/y of a vertex in front of the near plane
@@ -719,15 +722,16 @@ __global__ void __launch_bounds__(RASTER_THREADS, 1) hpb_raster_kernel(const Ras
             // packed the 36 values densely, (r*2+s)*9 + c: the shuffles / funnel shifts / selects that re-aligned them cost 142
             // warp instructions per 8 cells -- a third of the whole kernel, more than the shading itself.)
             const int n_cells = p.Hz * p.Wz;
-            uint4 *zbase = p.s2d + (size_t)hyp * n_cells * p.Cz8;
             const int sub = lane & 3;
-            const int sub_g = sub * (p.Cz8 >> 2);  // first 16-byte group of this lane's sub-pixel
+            // this lane's 16-byte group inside cell 0 of the scene; a cell is addressed by a 32-bit offset from it
+            uint4 *zlane = p.s2d + (size_t)hyp * n_cells * p.Cz8 + sub * (p.Cz8 >> 2);
             const uint2 *crop_h = p.crops_h ? p.crops_h + (size_t)hyp * p.crops_bs : nullptr;
             const float *crop_f = p.crops ? p.crops + (size_t)hyp * p.crops_bs : nullptr;
-            // The crop pixel of the NEXT work unit is loaded one iteration ahead (software pipelining through two registers):
-            // ncu attributed 27 % of the kernel's stall samples to the first use of this load -- it streams from HBM, and a
-            // warp had nothing else to do until it arrived.  The cell coordinates (I, J) advance incrementally, so the
-            // look-ahead costs no second division.
+            // The crop pixel AND the visibility key of the NEXT work unit are loaded one iteration ahead (software pipelining
+            // through registers).  ncu attributed 27 % of the kernel's stall samples to the first use of the crop load (it
+            // streams from HBM) and, once that was hidden, 10 % to the key load (L2): the key heads a chain of dependent
+            // loads (key -> face -> vertex attributes -> texels), so taking it off the chain shortens every shaded pixel.
+            // The cell coordinates (I, J) advance incrementally, so the look-ahead costs no second division.
             const int q_stride = G * RASTER_WARPS * 8;
             const int dI = q_stride / p.Wz, dJ = q_stride - dI * p.Wz;
             int q = (rank * RASTER_WARPS + warp) * 8 + (lane >> 2);
@@ -737,56 +741,55 @@ __global__ void __launch_bounds__(RASTER_THREADS, 1) hpb_raster_kernel(const Ras
             const int oy = (sub >> 1) - 3, ox = (sub & 1) - 3;
             auto crop_fetch = [&](int qq, int II, int JJ) -> uint2 {
                 const int yy = 2 * II + oy, xx = 2 * JJ + ox;
-                if (crop_h && qq < n_cells && (unsigned)yy < (unsigned)p.h && (unsigned)xx < (unsigned)p.w) return __ldcs(crop_h + yy * p.w + xx);
+                if (crop_h && qq < n_cells && (unsigned)yy < (unsigned)p.h && (unsigned)xx < (unsigned)p.w)
+                    return __ldcs(crop_h + (unsigned)(yy * p.w + xx));
                 return make_uint2(0u, 0u);
             };
+            // the scene's bounding box lies inside the image, so no separate image-bounds test
+            auto key_fetch = [&](int qq, int II, int JJ) -> unsigned long long {
+                const int yy = 2 * II + oy, xx = 2 * JJ + ox;
+                if (qq < n_cells && yy >= by0 && yy <= by1 && xx >= bx0 && xx <= bx1) return __ldcg(vis + (unsigned)(yy * p.w + xx));
+                return HPB_VIS_EMPTY;
+            };
             uint2 cw = crop_fetch(q, I, J);
-            for (int q0 = (rank * RASTER_WARPS + warp) * 8; q0 < n_cells; q0 += q_stride) {
+            unsigned long long key = key_fetch(q, I, J);
+            while (q < n_cells) {
                 int In = I + dI, Jn = J + dJ;
                 if (Jn >= p.Wz) { Jn -= p.Wz; ++In; }
                 const uint2 cw_next = crop_fetch(q + q_stride, In, Jn);
+                const unsigned long long key_next = key_fetch(q + q_stride, In, Jn);
                 const int py = 2 * I + oy, px = 2 * J + ox;
-                // own values o0..o8 as bf16 pairs: e0 = (o0,o1) .. e3 = (o6,o7), e4 = (o8,0)
-                unsigned e0 = 0u, e1 = 0u, e2 = 0u, e3 = 0u, e4 = 0u;
-                if (q < n_cells && (unsigned)py < (unsigned)p.h && (unsigned)px < (unsigned)p.w) {
-                    const int pix = py * p.w + px;
-                    float v[6];
+                float v[6];
 #pragma unroll
-                    for (int c = 0; c < 6; ++c) v[c] = 0.f;
-                    if (py >= by0 && py <= by1 && px >= bx0 && px <= bx1) {
-                        const unsigned long long key = __ldcg(vis + pix);
-                        if (key != HPB_VIS_EMPTY) {
-                            __stcg(vis + pix, HPB_VIS_EMPTY);  // re-arm for the next scene
-                            float zz = 0.f;
-                            shade(key, px, py, v[0], v[1], v[2], v[3], v[4], v[5], zz);
-                        }
-                    }
-                    unsigned c2;  // crop channel 2 as bf16 bits
-                    if (crop_h) {
-                        e0 = cw.x;
-                        c2 = cw.y & 0xffffu;
-                    } else {
-                        const float c0 = __ldcs(crop_f + pix), c1 = __ldcs(crop_f + npix + pix), cb = __ldcs(crop_f + 2 * npix + pix);
-                        const __nv_bfloat162 h01 = __floats2bfloat162_rn(c0, c1);
-                        e0 = *reinterpret_cast<const unsigned *>(&h01);
-                        c2 = (unsigned)__bfloat16_as_ushort(__float2bfloat16_rn(cb));
-                    }
-                    e1 = c2 | ((unsigned)__bfloat16_as_ushort(__float2bfloat16_rn(v[0])) << 16);
-                    const __nv_bfloat162 h45 = __floats2bfloat162_rn(v[1], v[2]), h67 = __floats2bfloat162_rn(v[3], v[4]);
-                    e2 = *reinterpret_cast<const unsigned *>(&h45);
-                    e3 = *reinterpret_cast<const unsigned *>(&h67);
-                    e4 = (unsigned)__bfloat16_as_ushort(__float2bfloat16_rn(v[5]));
+                for (int c = 0; c < 6; ++c) v[c] = 0.f;
+                if (key != HPB_VIS_EMPTY) {
+                    __stcg(vis + (unsigned)(py * p.w + px), HPB_VIS_EMPTY);  // re-arm for the next scene
+                    float zz = 0.f;
+                    shade(key, px, py, v[0], v[1], v[2], v[3], v[4], v[5], zz);
                 }
-                if (q < n_cells) {
-                    uint4 *cell = zbase + (size_t)q * p.Cz8 + sub_g;
-                    __stcs(cell, make_uint4(e0, e1, e2, e3));
-                    __stcs(cell + 1, make_uint4(e4, 0u, 0u, 0u));
-                    // channels 16.. of the sub-pixel block are zero padding: written unless the caller keeps a persistent
-                    // pre-zeroed buffer that only this kernel writes
-                    if (!p.pad_prezeroed)
-                        for (int x = 2; x < (p.Cz8 >> 2); ++x) __stcs(cell + x, make_uint4(0u, 0u, 0u, 0u));
+                // own values o0..o8 as bf16 pairs: e0 = (o0,o1) .. e3 = (o6,o7), e4 = (o8,0).  A pixel of the 3-pixel zero
+                // border has an all-zero crop word and an empty key, so it needs no branch of its own.
+                unsigned e0 = cw.x, c2 = cw.y & 0xffffu;  // crop channels 0,1 and 2 as bf16 bits
+                if (!crop_h && (unsigned)py < (unsigned)p.h && (unsigned)px < (unsigned)p.w) {
+                    const unsigned pix = (unsigned)(py * p.w + px);
+                    const float c0 = __ldcs(crop_f + pix), c1 = __ldcs(crop_f + npix + pix), cb = __ldcs(crop_f + 2 * npix + pix);
+                    const __nv_bfloat162 h01 = __floats2bfloat162_rn(c0, c1);
+                    e0 = *reinterpret_cast<const unsigned *>(&h01);
+                    c2 = (unsigned)__bfloat16_as_ushort(__float2bfloat16_rn(cb));
                 }
-                q += q_stride; I = In; J = Jn; cw = cw_next;
+                const unsigned e1 = c2 | ((unsigned)__bfloat16_as_ushort(__float2bfloat16_rn(v[0])) << 16);
+                const __nv_bfloat162 h45 = __floats2bfloat162_rn(v[1], v[2]), h67 = __floats2bfloat162_rn(v[3], v[4]);
+                const unsigned e2 = *reinterpret_cast<const unsigned *>(&h45);
+                const unsigned e3 = *reinterpret_cast<const unsigned *>(&h67);
+                const unsigned e4 = (unsigned)__bfloat16_as_ushort(__float2bfloat16_rn(v[5]));
+                uint4 *cell = zlane + (unsigned)(q * p.Cz8);
+                __stcs(cell, make_uint4(e0, e1, e2, e3));
+                __stcs(cell + 1, make_uint4(e4, 0u, 0u, 0u));
+                // channels 16.. of the sub-pixel block are zero padding: written unless the caller keeps a persistent
+                // pre-zeroed buffer that only this kernel writes
+                if (!p.pad_prezeroed)
+                    for (int x = 2; x < (p.Cz8 >> 2); ++x) __stcs(cell + x, make_uint4(0u, 0u, 0u, 0u));
+                q += q_stride; I = In; J = Jn; cw = cw_next; key = key_next;
             }
         }
         HPB_PHASE_MARK(4)  // phase C, thread 0's own share

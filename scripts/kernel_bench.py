@@ -4,7 +4,9 @@ import os, sys, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import bench as B
-from happypose_b200 import ops, _capi
+from happypose_b200 import ops, _capi, _build
+if os.environ.get("HPB200_LIB"):  # A/B of a library variant built elsewhere (e.g. -DHPB_RASTER_THREADS=768)
+    _build.LIB_PATH = os.environ["HPB200_LIB"]
 from happypose_b200._capi import Context
 from happypose_b200.utils import transform_utils
 
@@ -56,7 +58,8 @@ def main():
         ms = timeit(lambda: ops.render_s2d_bf16(ctx, ids, TCO, K_crop, crops_h, 64, out=zbuf, pad_prezeroed=True))
         gb_moved = b * (123 * 163 * 128 + 240 * 320 * 8) / 1e9
         print(json.dumps({"kernel": "fused hand-off, bf16x4 crop + aligned 128 B cells (shipped)", "b": b, "ms": round(ms, 4), "hyps_per_s": round(b / ms * 1e3),
-                          "moved_GBps": round(gb_moved / ms * 1e3, 1), "GBps_8d": round(gb / ms * 1e3, 1), "frac_8d": round(gb / ms * 1e3 / peak, 4)}))
+                          "moved_GBps": round(gb_moved / ms * 1e3, 1), "GBps_8d": round(gb / ms * 1e3, 1), "frac_8d": round(gb / ms * 1e3 / peak, 4),
+                          "checksum": int(zbuf.view(torch.int16).to(torch.int64).sum())}))
         ms = timeit(lambda: ops.crop_bf16x4(ctx, img, zero, pts, zero, K, TCO, tCR, (240, 320), tap_bits=16))
         gbc = b * 3 * 240 * 320 * 4 / 1e9
         print(json.dumps({"kernel": "crop_bf16x4 (boxes+pixels), fp16 taps (shipped)", "b": b, "ms": round(ms, 4), "GBps_8d": round(gbc / ms * 1e3, 1), "frac_8d": round(gbc / ms * 1e3 / peak, 4)}))
