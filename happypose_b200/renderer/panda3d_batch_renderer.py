@@ -14,6 +14,8 @@ Differences a caller can observe (all documented in DESIGN.md):
 """
 from __future__ import annotations
 
+import hashlib
+
 from typing import Dict, List, Optional, Sequence
 
 import numpy as np
@@ -175,8 +177,16 @@ class Panda3dBatchRenderer:
         # Panda3D's bounding sphere of a GeomNode: centred on the bounding box, reaching the farthest vertex
         centre = 0.5 * (verts_m.min(0).astype(np.float64) + verts_m.max(0).astype(np.float64))
         self._label_to_radius[obj.label] = float(np.linalg.norm(verts_m.astype(np.float64) - centre, axis=1).max())
-        self._label_to_mesh_id[obj.label] = ops.mesh_upload(
-            self._ctx, verts_m, mesh.faces, normals, mesh.uv, mesh.vcolor, mesh.texture)
+        # Meshes live in the per-device context for its lifetime: a second renderer over the same assets (the coarse and the
+        # refiner model each build one in the reference's set-up code) reuses the uploaded copy instead of adding another.
+        h = hashlib.blake2b(digest_size=16)
+        for a in (verts_m, mesh.faces, normals, mesh.uv, mesh.vcolor, mesh.texture):
+            h.update(b"-" if a is None else np.ascontiguousarray(a).tobytes() + str(np.asarray(a).shape).encode())
+        cache = self._ctx.__dict__.setdefault("_uploaded_meshes", {})
+        key = h.digest()
+        if key not in cache:
+            cache[key] = ops.mesh_upload(self._ctx, verts_m, mesh.faces, normals, mesh.uv, mesh.vcolor, mesh.texture)
+        self._label_to_mesh_id[obj.label] = cache[key]
 
     def __deepcopy__(self, memo):  # meshes live in the per-device context: model copies share the renderer
         return self

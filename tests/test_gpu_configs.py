@@ -237,3 +237,18 @@ def test_full_mip_chain_of_a_4096_texture():
         w, h, off = int(ws[lvl]), int(hs[lvl]), int(offs[lvl])
         ref = buf[off:off + w * h].reshape(h, w, 4)
         assert got.shape == ref.shape and (got == ref).all(), f"level {lvl}"
+
+
+def test_second_renderer_reuses_uploaded_meshes():
+    """every Panda3dBatchRenderer used to add its own copy of every mesh to the shared per-device context."""
+    from happypose_b200._capi import Context, load_library
+    from happypose_b200.datasets.object_dataset import RigidObject, RigidObjectDataset
+    from happypose_b200.renderer.panda3d_batch_renderer import Panda3dBatchRenderer
+
+    ds = RigidObjectDataset([RigidObject(label="can", mesh_path=MESH, mesh_units="mm")])
+    r1 = Panda3dBatchRenderer(ds, device="cuda:0")
+    ctx = Context.get("cuda:0")
+    n = load_library().hpb_mesh_count(ctx.handle)
+    r2 = Panda3dBatchRenderer(ds, device="cuda:0")
+    assert load_library().hpb_mesh_count(ctx.handle) == n
+    assert r1.mesh_ids(["can"]).tolist() == r2.mesh_ids(["can"]).tolist()
