@@ -44,6 +44,8 @@ int hpb_launch_refiner_prologue(hpb_ctx *ctx, const float *TCO_in, const float *
                                 cudaStream_t stream);
 
 int hpb_launch_maxpool_tma(hpb_ctx *ctx, const void *in, int b, int H, int W, int C, void *out, cudaStream_t stream);
+int hpb_launch_stem_tc(hpb_ctx *ctx, const void *z, int b, int Hz, int Wz, int C, const void *w, const float *bias, int O, void *out,
+                       unsigned long long kmask, cudaStream_t stream);
 
 static thread_local char g_err[512] = "";
 
@@ -559,6 +561,12 @@ int hpb_set_crop_tma(hpb_ctx *ctx, int enable) {
     return HPB_OK;
 }
 
+int hpb_set_stem_tc_halo(hpb_ctx *ctx, int enable) {
+    HPB_REQUIRE(ctx, "NULL context");
+    ctx->stem_tc_halo = enable ? 1 : 0;
+    return HPB_OK;
+}
+
 int hpb_set_maxpool_tma(hpb_ctx *ctx, int enable) {
     HPB_REQUIRE(ctx, "NULL ctx");
     ctx->maxpool_tma = enable ? 1 : 0;
@@ -752,6 +760,15 @@ int hpb_maxpool3x3s2_bf16_nhwc(hpb_ctx *ctx, const void *in_dev, int b, int H, i
         if (rc != HPB_ENOTFOUND) return rc;
     }
     return hpb_launch_maxpool(ctx, in_dev, b, H, W, C, out_dev, (cudaStream_t)stream);
+}
+
+int hpb_stem_conv4x4_relu_bf16_nhwc(hpb_ctx *ctx, const void *z_dev, int b, int Hz, int Wz, int C, const void *w_dev, const float *bias_dev,
+                                    int O, uint64_t k_slice_mask, void *out_dev, void *stream) {
+    HPB_REQUIRE(ctx && b >= 0 && Hz > 3 && Wz > 3 && C > 0 && O > 0, "bad argument");
+    if (b == 0) return HPB_OK;
+    HPB_REQUIRE(z_dev && w_dev && bias_dev && out_dev, "NULL pointer");
+    HpbDeviceGuard guard(ctx->device);
+    return hpb_launch_stem_tc(ctx, z_dev, b, Hz, Wz, C, w_dev, bias_dev, O, out_dev, (unsigned long long)k_slice_mask, (cudaStream_t)stream);
 }
 
 int hpb_pack_input_s2d_bf16(hpb_ctx *ctx, const float *x_dev, int64_t x_bstride, int b, int C, int H, int W, void *out_dev,

@@ -70,6 +70,7 @@ struct hpb_ctx {
     size_t topk_ws_bytes = 0;
     int64_t launches = 0;
     int crop_tma = 0;     // hpb_crop*: TMA-fed shared-memory ring for fp16 taps of RGB frames (hpb_set_crop_tma); measured: no gain
+    int stem_tc_halo = 1;  // hpb_stem_conv4x4_relu_bf16_nhwc: one halo box per tile (1) or one box per tap (0); hpb_set_stem_tc_halo
     int maxpool_tma = 1;  // hpb_maxpool3x3s2_bf16_nhwc: TMA-staged tile kernel for C = 64 (hpb_set_maxpool_tma)
     unsigned long long *clipped_scenes = nullptr;  // device counter (hpb_raster_clipped_scenes)
     // Workspaces only ever GROW, and a buffer that is replaced is retired (kept allocated until hpb_destroy), never freed:

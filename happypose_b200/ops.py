@@ -544,6 +544,35 @@ def maxpool3x3s2_bf16(ctx: Context, x: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def stem_k_slice_mask(weight: torch.Tensor) -> int:
+    """64-bit mask of the non-zero 16-channel weight slices of a [O,64,4,4] stem weight: bit 4 * (4 * kh + kw) + k."""
+    O, C, kh, kw = weight.shape
+    assert (C, kh, kw) == (64, 4, 4)
+    nz = (weight.detach().float().permute(2, 3, 1, 0).reshape(16, 4, 16 * O) != 0).any(dim=2).cpu().numpy().reshape(-1)
+    return int(sum(1 << i for i, v in enumerate(nz) if v))
+
+
+def stem_conv4x4_relu_bf16(ctx: Context, z: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor,
+                           k_slice_mask: int = (1 << 64) - 1) -> Optional[torch.Tensor]:
+    """relu(conv2d(z, weight) + bias) for the space-to-depth stem on the tensor cores (tcgen05 implicit GEMM, hpb_stem_tc.cu):
+    z [b,64,Hz,Wz] bf16 channels_last, weight [64,64,4,4] bf16 channels_last, bias [64] float32 -> [b,64,Hz-3,Wz-3] bf16
+    channels_last.  Returns None when the library does not serve the shape (the caller keeps its cuDNN convolution)."""
+    assert z.dtype == torch.bfloat16 and z.dim() == 4 and z.is_contiguous(memory_format=torch.channels_last)
+    assert weight.dtype == torch.bfloat16 and weight.is_contiguous(memory_format=torch.channels_last) and tuple(weight.shape[2:]) == (4, 4)
+    assert bias.dtype == torch.float32 and bias.is_contiguous() and bias.numel() == weight.shape[0]
+    b, C, Hz, Wz = z.shape
+    O = weight.shape[0]
+    assert weight.shape[1] == C
+    if C != 64 or O != 64 or Hz < 4 or Wz < 4:
+        return None
+    out = torch.empty((b, O, Hz - 3, Wz - 3), dtype=torch.bfloat16, device=z.device, memory_format=torch.channels_last)
+    rc = ctx.lib.hpb_stem_conv4x4_relu_bf16_nhwc(ctx.handle, ptr(z), b, Hz, Wz, C, ptr(weight), ptr(bias), O, int(k_slice_mask) & ((1 << 64) - 1), ptr(out), stream_ptr(ctx.device))
+    if rc == -4:  # HPB_ENOTFOUND: shape / driver entry point not served
+        return None
+    ctx.check(rc, "hpb_stem_conv4x4_relu_bf16_nhwc")
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 # ICP depth refiner, input stage
 # ------------------------------------------------------------------------------------------------

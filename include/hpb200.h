@@ -349,6 +349,25 @@ int hpb_maxpool3x3s2_bf16_nhwc(hpb_ctx *ctx, const void *in_dev, int b, int H, i
  * enable = 0 selects the plain 9-loads-per-output kernel for every shape (A/B measurements, tests).  Same results. */
 int hpb_set_maxpool_tma(hpb_ctx *ctx, int enable);
 
+/*
+ * The ResNet stem `conv1` + `bn1` + `relu` (torchvision_resnet.py:197-214) after batch-norm folding and the space-to-depth
+ * rewrite of the 7x7 / stride-2 convolution (megapose/fast_resnet.py s2d_weight): a 4x4 / stride-1 convolution of the
+ * space-to-depth input, + bias, ReLU, bfloat16 out -- as a tcgen05 implicit GEMM (TMA-fed, accumulators in tensor memory):
+ *   z_dev [b,Hz,Wz,C] bf16 (hpb_render_s2d_bf16 / hpb_pack_input_s2d_bf16), w_dev [O,4,4,C] bf16 (= the channels_last
+ *   [O,C,4,4] weight), bias_dev [O] f32  ->  out_dev [b,Hz-3,Wz-3,O] bf16.
+ * Served shape: C = 64, O = 64, Hz >= 19, Wz >= 16 (edge tiles are clipped by TMA); anything else returns HPB_ENOTFOUND and
+ * the caller keeps its library convolution.  fp32 accumulation like cuDNN's; the summation order differs, so outputs agree to bf16
+ * rounding, not bit for bit.
+ * k_slice_mask: bit (4 * tap + k), tap = 4 * kh + kw, is set when the weight slice w[:, kh, kw, 16k .. 16k+15] is not all
+ * zero; cleared slices are not multiplied (the 7x7 kernel leaves 15 of the 64 slices of its 8x8 space-to-depth footprint
+ * empty).  ~0 multiplies everything.
+ */
+int hpb_stem_conv4x4_relu_bf16_nhwc(hpb_ctx *ctx, const void *z_dev, int b, int Hz, int Wz, int C, const void *w_dev,
+                                    const float *bias_dev, int O, uint64_t k_slice_mask, void *out_dev, void *stream);
+/* Operand feeding of the kernel above: 1 (default) = one TMA box per tile holding the tile and its halo, the 16 taps are
+ * start-address offsets into it; 0 = one TMA box per tap (16x the L2 -> SM traffic; kept as the cross-check).  Same results. */
+int hpb_set_stem_tc_halo(hpb_ctx *ctx, int enable);
+
 #ifdef __cplusplus
 }
 #endif

@@ -761,3 +761,40 @@ def test_folded_resnet_bf16_close_to_module(ctx):
         got = folded(x).float()
     assert got.shape == ref.shape
     assert (got - ref).abs().max() <= 0.03 * ref.abs().max()  # bf16 end to end
+
+
+@pytest.mark.parametrize("halo,shape", [(1, (2, 19, 35)), (1, (2, 30, 41)), (1, (5, 123, 163)), (0, (2, 19, 35)), (0, (5, 123, 163))])
+def test_stem_tensor_core_conv_matches_float_conv(ctx, halo, shape):
+    """hpb_stem_conv4x4_relu_bf16_nhwc (tcgen05 implicit GEMM) vs relu(conv2d + bias) in float32 on the same bf16 operands:
+    fp32 accumulation on both sides, so the results differ by summation order + the final bf16 rounding only.  The big shape
+    is the real stem (123 x 163 cells): several tiles per CTA, every ring stage and both accumulators reused.  halo = 1 is the
+    shipped operand feeding (one box per tile, taps by descriptor offset; 27 x 38 outputs exercise the clipped edge tiles),
+    halo = 0 the box-per-tap cross-check."""
+    from happypose_b200 import ops
+
+    b, Hz, Wz = shape
+    g = torch.Generator(device="cpu").manual_seed(21)
+    z = torch.randn(b, 64, Hz, Wz, generator=g).to(torch.bfloat16).cuda().contiguous(memory_format=torch.channels_last)
+    w = (torch.randn(64, 64, 4, 4, generator=g) * 0.05).to(torch.bfloat16).cuda().contiguous(memory_format=torch.channels_last)
+    bias = torch.randn(64, generator=g).cuda()
+    ctx.check(ctx.lib.hpb_set_stem_tc_halo(ctx.handle, halo), "hpb_set_stem_tc_halo")
+    try:
+        out = ops.stem_conv4x4_relu_bf16(ctx, z, w, bias)
+        declined = ops.stem_conv4x4_relu_bf16(ctx, z[:, :, :Hz - 1].contiguous(memory_format=torch.channels_last), w, bias) if not halo else None
+    finally:
+        ctx.check(ctx.lib.hpb_set_stem_tc_halo(ctx.handle, 1), "hpb_set_stem_tc_halo")
+    assert out is not None and out.shape == (b, 64, Hz - 3, Wz - 3) and out.is_contiguous(memory_format=torch.channels_last)
+    assert declined is None  # the box-per-tap scheme declines shapes it cannot tile instead of mangling them
+    tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        ref = torch.relu(torch.nn.functional.conv2d(z.float(), w.float(), bias))
+    finally:
+        torch.backends.cudnn.allow_tf32 = tf32
+    got = out.float()
+    assert (ref > 0).float().mean() > 0.3
+    # one bf16 ulp (2^-8 relative) of the result + the fp32 summation noise of 1024 products
+    err = (got - ref).abs()
+    assert bool((err <= ref.abs() * 2.0 ** -8 + 1e-3).all()), float((err - ref.abs() * 2.0 ** -8).max())
+    # and it is the correctly rounded value almost everywhere
+    assert float((got == ref.to(torch.bfloat16).float()).float().mean()) > 0.99
