@@ -563,7 +563,7 @@ int hpb_set_crop_tma(hpb_ctx *ctx, int enable) {
 
 int hpb_set_stem_tc_halo(hpb_ctx *ctx, int enable) {
     HPB_REQUIRE(ctx, "NULL context");
-    ctx->stem_tc_halo = enable ? 1 : 0;
+    ctx->stem_tc_halo = enable < 0 || enable > 2 ? 1 : enable;
     return HPB_OK;
 }
 

@@ -149,7 +149,7 @@ template <bool HALO, unsigned long long KMASK>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 hpb_stem_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_w,
                    const __grid_constant__ CUtensorMap map_out, const float *__restrict__ bias, int tiles_x, int tiles_per_image,
-                   int n_tiles) {
+                   int n_tiles, uint4 *__restrict__ out, int Hc, int Wc, int direct_store) {
     static_assert(KMASK & 1ull, "slice 0 initialises the accumulator");
     constexpr int FIRST_SLICE = 0;
     extern __shared__ unsigned char smem_raw[];
@@ -159,7 +159,6 @@ hpb_stem_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_cons
     constexpr int TC_STAGES = Cfg::STAGES, TC_TILE_W = Cfg::TILE_W, TC_TILE_H = Cfg::TILE_H;
     constexpr unsigned TC_A_BYTES = Cfg::A_BYTES, OFF_BAR = Cfg::OFF_BAR;
     const unsigned sB = base + Cfg::OFF_B, sA = base + Cfg::OFF_A, sOut = base + Cfg::OFF_OUT;
-    float *sBias = reinterpret_cast<float *>(base_ptr + Cfg::OFF_BIAS);
     const unsigned bars = base + OFF_BAR;
     // barriers (8 bytes each): full[s] 0..3, empty[s] 4..7, weights 8, tmem_full[a] 9..10, tmem_empty[a] 11..12; word 13*8: TMEM base
     auto full_bar = [&](int s) { return bars + 8u * s; };
@@ -171,7 +170,6 @@ hpb_stem_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_cons
     volatile unsigned *tmem_slot_ptr = reinterpret_cast<volatile unsigned *>(base_ptr + OFF_BAR + 8u * (2 * TC_MAX_STAGES + 5));
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    if (tid < TC_N) sBias[tid] = bias[tid];
     if (tid == 0) {
         for (int s = 0; s < TC_STAGES; ++s) {
             mbar_init(full_bar(s), 1);
@@ -286,6 +284,14 @@ hpb_stem_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_cons
         const int et = tid - 128;
         int acc = 0, ob = 0;
         unsigned acc_ph = 0;
+        // The shared-memory data pipe is this kernel's bottleneck (ncu: 82 % busy with tensor-core operand reads + 17 % with the
+        // epilogue's own accesses), so the bias lives in registers (a persistent CTA loads it once: 64 broadcast LDS per thread
+        // and tile gone).  direct_store (variant 2) also skips the staging tile and writes each pixel's 128 bytes straight to
+        // global memory: measured 8 % SLOWER than staging + TMA store (32 scattered 16-byte pieces per store instruction
+        // cost the same L1 data pipe more than 4 shared-memory wavefronts + one bulk read), so it is not the default.
+        float breg[TC_N];
+#pragma unroll
+        for (int c = 0; c < TC_N; ++c) breg[c] = __ldg(bias + c);
         for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
             const int n = t / tiles_per_image, r = t - n * tiles_per_image;
             const int ty = r / tiles_x, tx = r - ty * tiles_x;
@@ -300,6 +306,23 @@ hpb_stem_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_cons
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive(tempty_bar(acc));  // the MMA warp may overwrite this accumulator
+            if (direct_store) {
+                const int oy = ty * TC_TILE_H + p / TC_TILE_W, ox = tx * TC_TILE_W + p % TC_TILE_W;
+                if (oy < Hc && ox < Wc) {
+                    uint4 *dst = out + (((size_t)n * Hc + oy) * Wc + ox) * (TC_N / 8);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        uint4 o;
+                        o.x = bias_relu_pack(v[8 * j + 0], v[8 * j + 1], breg[8 * j + 0], breg[8 * j + 1]);
+                        o.y = bias_relu_pack(v[8 * j + 2], v[8 * j + 3], breg[8 * j + 2], breg[8 * j + 3]);
+                        o.z = bias_relu_pack(v[8 * j + 4], v[8 * j + 5], breg[8 * j + 4], breg[8 * j + 5]);
+                        o.w = bias_relu_pack(v[8 * j + 6], v[8 * j + 7], breg[8 * j + 6], breg[8 * j + 7]);
+                        dst[j] = o;
+                    }
+                }
+                if (++acc == 2) { acc = 0; acc_ph ^= 1u; }
+                continue;
+            }
             // the TMA store that last read staging tile `ob` must have finished reading it
             if (et == 0) {
                 if constexpr (Cfg::OUT_BUFS == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
@@ -309,10 +332,10 @@ hpb_stem_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_cons
             const unsigned row = sOut + ob * TC_OUT_BYTES + (unsigned)p * 128u;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                const unsigned w0 = bias_relu_pack(v[8 * j + 0], v[8 * j + 1], sBias[8 * j + 0], sBias[8 * j + 1]);
-                const unsigned w1 = bias_relu_pack(v[8 * j + 2], v[8 * j + 3], sBias[8 * j + 2], sBias[8 * j + 3]);
-                const unsigned w2 = bias_relu_pack(v[8 * j + 4], v[8 * j + 5], sBias[8 * j + 4], sBias[8 * j + 5]);
-                const unsigned w3 = bias_relu_pack(v[8 * j + 6], v[8 * j + 7], sBias[8 * j + 6], sBias[8 * j + 7]);
+                const unsigned w0 = bias_relu_pack(v[8 * j + 0], v[8 * j + 1], breg[8 * j + 0], breg[8 * j + 1]);
+                const unsigned w1 = bias_relu_pack(v[8 * j + 2], v[8 * j + 3], breg[8 * j + 2], breg[8 * j + 3]);
+                const unsigned w2 = bias_relu_pack(v[8 * j + 4], v[8 * j + 5], breg[8 * j + 4], breg[8 * j + 5]);
+                const unsigned w3 = bias_relu_pack(v[8 * j + 6], v[8 * j + 7], breg[8 * j + 6], breg[8 * j + 7]);
                 asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row + (unsigned)((j ^ (p & 7)) << 4)), "r"(w0), "r"(w1), "r"(w2), "r"(w3)
                              : "memory");
             }
@@ -404,16 +427,14 @@ int launch_stem(hpb_ctx *ctx, const void *z, int b, int Hz, int Wz, int C, const
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
             return HPB_ENOTFOUND;
     }
-    static bool attr_set = false;
-    if (!attr_set) {
-        HPB_CUDA_OK(cudaFuncSetAttribute(hpb_stem_tc_kernel<HALO, KMASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
-        attr_set = true;
-    }
+    // per launch (a microsecond): the attribute is per device, and a process may hold contexts on several
+    HPB_CUDA_OK(cudaFuncSetAttribute(hpb_stem_tc_kernel<HALO, KMASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
     const int tiles_x = (Wc + Cfg::TILE_W - 1) / Cfg::TILE_W, tiles_per_image = tiles_x * ((Hc + Cfg::TILE_H - 1) / Cfg::TILE_H);
     const long long n_tiles = (long long)tiles_per_image * b;
     if (n_tiles > 0x7fffffffll) return HPB_ENOTFOUND;
     const int grid = (int)(n_tiles < ctx->sm_count ? n_tiles : ctx->sm_count);
-    hpb_stem_tc_kernel<HALO, KMASK><<<grid, TC_THREADS, Cfg::SMEM, stream>>>(map_in, map_w, map_out, bias, tiles_x, tiles_per_image, (int)n_tiles);
+    hpb_stem_tc_kernel<HALO, KMASK><<<grid, TC_THREADS, Cfg::SMEM, stream>>>(map_in, map_w, map_out, bias, tiles_x, tiles_per_image, (int)n_tiles,
+                                                                                reinterpret_cast<uint4 *>(out), Hc, Wc, ctx->stem_tc_halo == 2 ? 1 : 0);
     HPB_CUDA_OK(cudaGetLastError());
     ctx->launches++;
     return HPB_OK;

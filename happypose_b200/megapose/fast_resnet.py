@@ -117,6 +117,14 @@ class FoldedResNet:
             s2d.bias = b.to(dtype).contiguous()
             s2d.stride, s2d.padding, s2d.dilation, s2d.groups = (1, 1), (0, 0), (1, 1), 1
             self.stem_s2d = s2d
+            # libhpb200's tcgen05 implicit GEMM serves the 64 -> 64 channel stem (hpb_stem_tc.cu): float32 folded bias, and the
+            # mask of non-zero 16-channel weight slices (49 of 64 for a 7x7 kernel) so the empty ones are not multiplied
+            self.tc_stem = self.s2d_channels == 64 and s2d.weight.shape[0] == 64
+            if self.tc_stem:
+                from .. import ops
+
+                s2d.bias_f32 = b.float().contiguous()
+                s2d.k_slice_mask = ops.stem_k_slice_mask(s2d.weight)
         mp = net.maxpool
         self.fast_pool = (ctx is not None and dtype == torch.bfloat16 and isinstance(mp, nn.MaxPool2d)
                           and mp.kernel_size in (3, (3, 3)) and mp.stride in (2, (2, 2)) and mp.padding in (1, (1, 1))
@@ -165,7 +173,7 @@ class FoldedResNet:
             from .. import ops
 
             z = ops.pack_input_s2d_bf16(self.ctx, x, self.s2d_channels)  # fp32 planar -> bf16 NHWC space-to-depth
-            return self.stem_s2d.relu(z, fused)
+            return self._stem_s2d(z, fused)
         if x.shape[1] < self.stem.c_in:  # zero channels meet zero weights
             if self.ctx is not None and self.dtype == torch.bfloat16 and x.dtype == torch.float32 and x.is_contiguous():
                 from .. import ops
@@ -176,6 +184,16 @@ class FoldedResNet:
         x = x.to(dtype=self.dtype, memory_format=torch.channels_last)
         return self.stem.relu(x, fused)
 
+    def _stem_s2d(self, z: torch.Tensor, fused: bool) -> torch.Tensor:
+        """relu(conv4x4(z) + b) of the space-to-depth input: the library's tensor-core kernel when it serves the shape, else cuDNN."""
+        if getattr(self, "tc_stem", False) and z.dtype == torch.bfloat16 and z.is_contiguous(memory_format=torch.channels_last):
+            from .. import ops
+
+            y = ops.stem_conv4x4_relu_bf16(self.ctx, z, self.stem_s2d.weight, self.stem_s2d.bias_f32, self.stem_s2d.k_slice_mask)
+            if y is not None:
+                return y
+        return self.stem_s2d.relu(z, fused)
+
     @property
     def accepts_s2d(self) -> bool:
         """True when the stem runs as the 4x4 convolution over the space-to-depth input, i.e. when a caller may hand in
@@ -185,7 +203,7 @@ class FoldedResNet:
     def __call__(self, x: torch.Tensor, packed_s2d: bool = False) -> torch.Tensor:
         """x: the float32 planar network input, or (packed_s2d=True) its bf16 space-to-depth form [b,s2d_channels,H/2+3,W/2+3]."""
         fused = self.fused
-        stem = (lambda t, f: self.stem_s2d.relu(t, f)) if packed_s2d else self._stem
+        stem = self._stem_s2d if packed_s2d else self._stem
         try:
             y = stem(x, fused)
         except torch.cuda.OutOfMemoryError:

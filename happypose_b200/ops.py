@@ -22,6 +22,7 @@ class KernelTimer:
 
     def __init__(self):
         self.records = {}
+        self.flop_records = {}
 
     def bracket(self, name: str, algorithmic_bytes: int, fp32_equivalent_bytes: Optional[int] = None):
         """algorithmic_bytes: bytes the launch has to move; fp32_equivalent_bytes: what the reference's float32 layout of
@@ -30,6 +31,28 @@ class KernelTimer:
         eq = int(algorithmic_bytes if fp32_equivalent_bytes is None else fp32_equivalent_bytes)
         self.records.setdefault(name, []).append((e0, e1, int(algorithmic_bytes), eq))
         return e0, e1
+
+    def bracket_flops(self, name: str, issued_flops: float, algorithmic_flops: float):
+        """For a tensor-core launch: issued_flops = what the MMAs it issues compute, algorithmic_flops = the reference op's."""
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.flop_records.setdefault(name, []).append((e0, e1, float(issued_flops), float(algorithmic_flops)))
+        return e0, e1
+
+    def flop_summary(self):
+        """name -> dict(launches, ms_total, ms_avg, tflops, algorithmic_tflops, largest{...}); call after torch.cuda.synchronize()."""
+        out = {}
+        for name, recs in self.flop_records.items():
+            ms = [r[0].elapsed_time(r[1]) for r in recs]
+            tot = sum(ms)
+            big = max(r[2] for r in recs)
+            sel = [(m, r) for m, r in zip(ms, recs) if r[2] == big]
+            big_ms = sum(m for m, _ in sel) / len(sel)
+            out[name] = {"launches": len(recs), "ms_total": tot, "ms_avg": tot / len(recs),
+                         "tflops": sum(r[2] for r in recs) / 1e12 / (tot / 1e3) if tot > 0 else 0.0,
+                         "algorithmic_tflops": sum(r[3] for r in recs) / 1e12 / (tot / 1e3) if tot > 0 else 0.0,
+                         "largest": {"launches": len(sel), "ms_avg": big_ms, "tflops": big / 1e12 / (big_ms / 1e3) if big_ms > 0 else 0.0,
+                                     "algorithmic_tflops": sel[0][1][3] / 1e12 / (big_ms / 1e3) if big_ms > 0 else 0.0}}
+        return out
 
     def summary(self):
         """name -> dict(launches, ms_total, ms_avg, bytes_avg, gbps); call after torch.cuda.synchronize()."""
@@ -566,7 +589,17 @@ def stem_conv4x4_relu_bf16(ctx: Context, z: torch.Tensor, weight: torch.Tensor, 
     if C != 64 or O != 64 or Hz < 4 or Wz < 4:
         return None
     out = torch.empty((b, O, Hz - 3, Wz - 3), dtype=torch.bfloat16, device=z.device, memory_format=torch.channels_last)
+    ev = None
+    if _kernel_timer is not None:
+        # issued: tiles of 16 x 8 outputs, one M128 x N64 x K16 MMA per multiplied weight slice; algorithmic: the 7x7 kernel over
+        # the (at most 16) real channels per sub-pixel the slices stand for is not known here, so the 4x4x64 form is quoted
+        tiles = b * ((Hz - 3 + 15) // 16) * ((Wz - 3 + 7) // 8)
+        slices = bin(int(k_slice_mask) & ((1 << 64) - 1)).count("1")
+        ev = _kernel_timer.bracket_flops("hpb_stem_tc_kernel", tiles * slices * 2.0 * 128 * 64 * 16, b * (Hz - 3) * (Wz - 3) * 2.0 * O * slices * 16)
+        ev[0].record()
     rc = ctx.lib.hpb_stem_conv4x4_relu_bf16_nhwc(ctx.handle, ptr(z), b, Hz, Wz, C, ptr(weight), ptr(bias), O, int(k_slice_mask) & ((1 << 64) - 1), ptr(out), stream_ptr(ctx.device))
+    if ev is not None:
+        ev[1].record()
     if rc == -4:  # HPB_ENOTFOUND: shape / driver entry point not served
         return None
     ctx.check(rc, "hpb_stem_conv4x4_relu_bf16_nhwc")

@@ -364,9 +364,11 @@ int hpb_set_maxpool_tma(hpb_ctx *ctx, int enable);
  */
 int hpb_stem_conv4x4_relu_bf16_nhwc(hpb_ctx *ctx, const void *z_dev, int b, int Hz, int Wz, int C, const void *w_dev,
                                     const float *bias_dev, int O, uint64_t k_slice_mask, void *out_dev, void *stream);
-/* Operand feeding of the kernel above: 1 (default) = one TMA box per tile holding the tile and its halo, the 16 taps are
- * start-address offsets into it; 0 = one TMA box per tap (16x the L2 -> SM traffic; kept as the cross-check).  Same results. */
-int hpb_set_stem_tc_halo(hpb_ctx *ctx, int enable);
+/* Variants of the kernel above (A/B measurements and cross-checks; same results): 1 (default) = one TMA box per tile holding
+ * the tile and its halo, the 16 taps are start-address offsets into it, epilogue through a swizzled staging tile + TMA store;
+ * 2 = the same with the epilogue storing straight from registers (8 % slower); 0 = one TMA box per tap (16x the L2 -> SM
+ * traffic). */
+int hpb_set_stem_tc_halo(hpb_ctx *ctx, int mode);
 
 #ifdef __cplusplus
 }

@@ -763,13 +763,14 @@ def test_folded_resnet_bf16_close_to_module(ctx):
     assert (got - ref).abs().max() <= 0.03 * ref.abs().max()  # bf16 end to end
 
 
-@pytest.mark.parametrize("halo,shape", [(1, (2, 19, 35)), (1, (2, 30, 41)), (1, (5, 123, 163)), (0, (2, 19, 35)), (0, (5, 123, 163))])
+@pytest.mark.parametrize("halo,shape", [(1, (2, 19, 35)), (1, (2, 30, 41)), (1, (5, 123, 163)), (2, (2, 30, 41)), (2, (5, 123, 163)),
+                                        (0, (2, 19, 35)), (0, (5, 123, 163))])
 def test_stem_tensor_core_conv_matches_float_conv(ctx, halo, shape):
     """hpb_stem_conv4x4_relu_bf16_nhwc (tcgen05 implicit GEMM) vs relu(conv2d + bias) in float32 on the same bf16 operands:
     fp32 accumulation on both sides, so the results differ by summation order + the final bf16 rounding only.  The big shape
     is the real stem (123 x 163 cells): several tiles per CTA, every ring stage and both accumulators reused.  halo = 1 is the
-    shipped operand feeding (one box per tile, taps by descriptor offset; 27 x 38 outputs exercise the clipped edge tiles),
-    halo = 0 the box-per-tap cross-check."""
+    shipped variant (one box per tile, taps by descriptor offset, staged TMA-store epilogue; 27 x 38 outputs exercise the clipped
+    edge tiles), 2 the same with the register-store epilogue, 0 the box-per-tap cross-check."""
     from happypose_b200 import ops
 
     b, Hz, Wz = shape
