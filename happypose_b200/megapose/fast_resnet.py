@@ -19,6 +19,8 @@ network's device time).  The plain module path is kept for float32 parity runs a
 """
 from __future__ import annotations
 
+import os
+
 from typing import List, Optional, Tuple
 
 import torch
@@ -119,7 +121,8 @@ class FoldedResNet:
             self.stem_s2d = s2d
             # libhpb200's tcgen05 implicit GEMM serves the 64 -> 64 channel stem (hpb_stem_tc.cu): float32 folded bias, and the
             # mask of non-zero 16-channel weight slices (49 of 64 for a 7x7 kernel) so the empty ones are not multiplied
-            self.tc_stem = self.s2d_channels == 64 and s2d.weight.shape[0] == 64
+            # HPB200_TC_STEM=0 keeps the stem on cuDNN (A/B measurements)
+            self.tc_stem = self.s2d_channels == 64 and s2d.weight.shape[0] == 64 and os.environ.get("HPB200_TC_STEM", "1") != "0"
             if self.tc_stem:
                 from .. import ops
 
