@@ -3,29 +3,35 @@
 //
 // It is the 7x7 / stride-2 `conv1` + `bn1` + `relu` of torchvision_resnet.py:197-214 after batch-norm folding and the
 // space-to-depth rewrite (megapose/fast_resnet.py: s2d_weight), i.e. the single largest kernel of a MegaPose step
-// (cuDNN: 1.44 ms of 10.7 for the 576-row coarse batch).  GEMM view per CTA tile:
+// (cuDNN: 1.44 ms of 10.7 for the 576-row coarse batch; this kernel 1.0-1.2 ms).  GEMM view per CTA tile:
 //   D[128 pixels, 64 out-channels] = sum over the 16 taps (kh, kw) of  A_tap[128 pixels, 64 channels] * W_tap[64 ch, 64 out]
-// * a tile is 8 rows x 16 columns of output pixels; A_tap is then ONE 4-D TMA box {64 ch, 16 px, 8 rows, 1 image} of the
-//   input at offset (kh, kw): 128 rows of 128 bytes, landed in shared memory in the 128-byte-swizzled K-major layout
-//   tcgen05.mma reads directly -- im2col never exists anywhere;
-// * all 16 weight taps (128 KB) stay resident in shared memory for the life of the persistent CTA;
-// * one thread issues 4 tcgen05.mma (M 128, N 64, K 16, fp32 accumulate in tensor memory) per tap, 64 per tile, and hands
-//   the shared-memory stage back to the producer with tcgen05.commit; accumulators are double-buffered in TMEM (2 x 64
-//   columns) so the epilogue of tile i overlaps the MMAs of tile i + 1;
-// * epilogue warps read their TMEM lane quarter (tcgen05.ld 32x32b), add the bias, clamp at 0, round to bf16, write the
-//   128-byte pixel rows into a swizzled staging tile and one thread stores it with a 4-D TMA store.
+// * persistent CTAs, one per SM; a tile is 16 rows x 8 columns of output pixels (HALO scheme, below);
+// * ONE 4-D TMA box per tile -- the tile and its 3-cell halo, 128-byte swizzled -- feeds all 16 taps: the A operand of a tap is
+//   a start-address offset into the box, so im2col never exists and every input cell crosses L2 -> SM once;
+// * all 16 weight taps (128 KB) stay resident in shared memory for the life of the CTA;
+// * one elected lane issues the tcgen05.mma (M 128, N 64, K 16, fp32 accumulate in tensor memory): 4 per tap, minus the
+//   weight slices that are identically zero (KMASK: 49 of 64 remain for a 7x7 kernel), fully unrolled with immediate
+//   descriptor offsets, and hands stages / accumulators on with tcgen05.commit; accumulators are double-buffered in TMEM
+//   (2 x 64 columns) so the epilogue of tile i overlaps the MMAs of tile i + 1;
+// * epilogue warps read their TMEM lane quarter (tcgen05.ld 32x32b), add the bias (registers), clamp at 0, round to bf16,
+//   write the 128-byte pixel rows into a swizzled staging tile and one thread stores it with a 4-D TMA store (edge tiles
+//   are clipped by TMA: any output size is served).
 // Warp roles: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 4..7 = epilogue.  Every mbarrier wait is bounded
 // (a protocol error traps instead of hanging the device).
+// Bound (ncu, profiles/r2_stem_tc_ncu_full.txt): the shared-memory data pipe -- N = 64 needs 4 KB of A + 2 KB of B per
+// 131 k MAC -- 82 % busy with tensor-core operand reads plus the epilogue's accesses; tensor pipe 47 % busy.
 //
 // Two operand-feeding schemes (template HALO):
-// * HALO = false, "box per tap" (the first version, kept as the cross-check): 16 TMA boxes of 16 KB per tile.  Correct but
-//   every input cell crosses L2 -> SM 16 times: 22 GB for the 576-row batch, 6.9 TB/s of L2 traffic, 3.2 ms (cuDNN 1.67).
+// * HALO = false, "box per tap" (the first version, kept as the cross-check): tile 8 x 16, 16 TMA boxes of 16 KB per tile.
+//   Correct but every input cell crosses L2 -> SM 16 times: 22 GB for the 576-row batch, 2.3-3.2 ms.
 // * HALO = true: the tile is 16 rows x 8 columns and ONE box {64 ch, 16 px, 19 rows} (38 KB: the tile + its 3-cell halo,
 //   rows padded to 16 cells = 2 KB so that consecutive image rows are exactly two swizzle atoms apart) is loaded per tile.
 //   The A operand of tap (kh, kw) is then just a different START ADDRESS into that box: 8-row groups (the 8 cells of one
-//   tile row) 2 KB apart (the descriptor's stride-dimension offset), start = box + kh * 2 KB + kw * 128 B, and because
-//   that start is not 1 KB aligned for kw > 0 the descriptor carries base_offset = (start >> 7) & 7 so the tensor core
-//   un-swizzles with the phase TMA used when it wrote the box.  6.7x less L2 -> SM traffic.
+//   tile row) 2 KB apart (the descriptor's stride-dimension offset), start = box + kh * 2 KB + kw * 128 B.  That start is
+//   not 1 KB aligned for kw > 0; with the descriptor's base_offset field left 0 the tensor core un-swizzles by the
+//   ABSOLUTE shared-memory address bits -- the phase TMA used when it wrote the box -- which is what this needs (setting
+//   base_offset = (start >> 7) & 7 makes it use the row index relative to the start instead: decoded on the device with
+//   identity weights, scripts/debug_stem_tc.py).
 #include <cuda.h>
 #include <cuda_bf16.h>
 
@@ -53,8 +59,7 @@ struct StemCfg {
     static constexpr unsigned OFF_B = 0u;
     static constexpr unsigned OFF_A = OFF_B + TC_B_BYTES;
     static constexpr unsigned OFF_OUT = OFF_A + STAGES * A_BYTES;
-    static constexpr unsigned OFF_BIAS = OFF_OUT + OUT_BUFS * TC_OUT_BYTES;
-    static constexpr unsigned OFF_BAR = OFF_BIAS + 256u;
+    static constexpr unsigned OFF_BAR = OFF_OUT + OUT_BUFS * TC_OUT_BYTES;
     static constexpr unsigned SMEM = OFF_BAR + 128u + 1024u;  // + slack for the manual 1024-byte alignment
     static_assert(SMEM <= 232448u, "shared memory budget");
     static_assert(A_BYTES % 1024u == 0, "stages must keep the 1 KB swizzle alignment");

@@ -61,3 +61,31 @@ def test_space_to_depth_stem_is_the_same_convolution():
         got = torch.nn.functional.conv2d(s2d_reference(x, cz), s2d_weight(w, cz), b)
         assert got.shape == ref.shape == (2, 16, H // 2, W // 2)
         assert torch.allclose(ref, got, atol=1e-3)
+
+
+def test_stem_k_slice_mask_of_a_7x7_kernel():
+    """The space-to-depth form of a 7x7 kernel leaves 15 of the 64 (tap, 16-channel slice) blocks of the 4x4x64 weight empty:
+    sub-pixel column s = 1 of the taps kw = 3 and sub-pixel row r = 1 of the taps kh = 3 (the 8th row / column of the footprint).
+    ops.stem_k_slice_mask must report exactly the pattern hpb_stem_tc.cu's specialised kernel skips (bit 4 * (4 kh + kw) + k,
+    k = 2 r + s), and a dense weight must report all 64."""
+    from happypose_b200 import ops
+    from happypose_b200.megapose.fast_resnet import s2d_weight
+
+    g = torch.Generator().manual_seed(3)
+    w = s2d_weight(torch.randn(64, 9, 7, 7, generator=g), 64)
+    mask = ops.stem_k_slice_mask(w)
+    expect = 0
+    for kh in range(4):
+        for kw in range(4):
+            for k in range(4):
+                r, s = k >> 1, k & 1
+                if not ((kw == 3 and s == 1) or (kh == 3 and r == 1)):
+                    expect |= 1 << (4 * (4 * kh + kw) + k)
+    assert mask == expect and bin(mask).count("1") == 49 and mask & 1
+    assert ops.stem_k_slice_mask(torch.randn(64, 64, 4, 4, generator=g)) == (1 << 64) - 1
+    # the weight the kernel sees is the channels_last tensor: [O][kh][kw][C] in memory, slice k = channels 16k .. 16k+15
+    wl = w.contiguous(memory_format=torch.channels_last)
+    flat = wl.permute(0, 2, 3, 1).reshape(64, 16, 4, 16)
+    for tap in range(16):
+        for k in range(4):
+            assert bool((flat[:, tap, k] != 0).any()) == bool((mask >> (4 * tap + k)) & 1)
