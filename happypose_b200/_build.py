@@ -12,7 +12,7 @@ import subprocess
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libhpb200.so")
-SOURCES = ["hpb_api.cu", "hpb_raster.cu", "hpb_crop.cu", "hpb_pose.cu", "hpb_topk.cu", "hpb_icp.cu", "hpb_prologue.cu", "hpb_maxpool_tma.cu", "hpb_crop_tma.cu", "hpb_stem_tc.cu"]
+SOURCES = ["hpb_api.cu", "hpb_raster.cu", "hpb_crop.cu", "hpb_pose.cu", "hpb_topk.cu", "hpb_icp.cu", "hpb_prologue.cu", "hpb_maxpool_tma.cu", "hpb_crop_tma.cu", "hpb_stem_tc.cu", "hpb_conv3x3_tc.cu"]
 
 # -fmad=false: every fused multiply-add in the kernels is an explicit fmaf(), so the rasteriser's arithmetic is
 # bit-identical to the CPU oracle the parity tests compare against.

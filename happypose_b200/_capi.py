@@ -71,6 +71,7 @@ SIGNATURES = {
                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "hpb_set_maxpool_tma": (c_int, [c_void_p, c_int]),
     "hpb_set_stem_tc_halo": (c_int, [c_void_p, c_int]),
+    "hpb_conv3x3_bias_relu_bf16_nhwc": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "hpb_stem_conv4x4_relu_bf16_nhwc": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, ctypes.c_uint64, c_void_p, c_void_p]),
     "hpb_set_crop_tma": (c_int, [c_void_p, c_int]),
     "hpb_topk_segmented": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),

@@ -44,6 +44,8 @@ int hpb_launch_refiner_prologue(hpb_ctx *ctx, const float *TCO_in, const float *
                                 cudaStream_t stream);
 
 int hpb_launch_maxpool_tma(hpb_ctx *ctx, const void *in, int b, int H, int W, int C, void *out, cudaStream_t stream);
+int hpb_launch_conv3x3_tc(hpb_ctx *ctx, const void *x, int b, int H, int W, int C, const void *w, const float *bias, int O, const void *res,
+                          void *out, cudaStream_t stream);
 int hpb_launch_stem_tc(hpb_ctx *ctx, const void *z, int b, int Hz, int Wz, int C, const void *w, const float *bias, int O, void *out,
                        unsigned long long kmask, cudaStream_t stream);
 
@@ -760,6 +762,16 @@ int hpb_maxpool3x3s2_bf16_nhwc(hpb_ctx *ctx, const void *in_dev, int b, int H, i
         if (rc != HPB_ENOTFOUND) return rc;
     }
     return hpb_launch_maxpool(ctx, in_dev, b, H, W, C, out_dev, (cudaStream_t)stream);
+}
+
+int hpb_conv3x3_bias_relu_bf16_nhwc(hpb_ctx *ctx, const void *x_dev, int b, int H, int W, int C, const void *w_dev, const float *bias_dev, int O,
+                                    const void *residual_dev, void *out_dev, void *stream) {
+    HPB_REQUIRE(ctx && b >= 0 && H > 0 && W > 0 && C > 0 && O > 0, "bad argument");
+    if (b == 0) return HPB_OK;
+    HPB_REQUIRE(x_dev && w_dev && bias_dev && out_dev, "NULL pointer");
+    HPB_REQUIRE(out_dev != x_dev, "the convolution cannot run in place");
+    HpbDeviceGuard guard(ctx->device);
+    return hpb_launch_conv3x3_tc(ctx, x_dev, b, H, W, C, w_dev, bias_dev, O, residual_dev, out_dev, (cudaStream_t)stream);
 }
 
 int hpb_stem_conv4x4_relu_bf16_nhwc(hpb_ctx *ctx, const void *z_dev, int b, int Hz, int Wz, int C, const void *w_dev, const float *bias_dev,

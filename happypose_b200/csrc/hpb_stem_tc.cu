@@ -36,8 +36,11 @@
 #include <cuda_bf16.h>
 
 #include "hpb_common.cuh"
+#include "hpb_tc_common.cuh"
 
 namespace {
+
+using namespace hpbtc;
 
 constexpr int TC_N = 64;                      // output channels = the MMA's N
 constexpr int TC_KC = 64;                     // input channels per tap: one 128-byte swizzle row
@@ -64,89 +67,6 @@ struct StemCfg {
     static_assert(SMEM <= 232448u, "shared memory budget");
     static_assert(A_BYTES % 1024u == 0, "stages must keep the 1 KB swizzle alignment");
 };
-// tcgen05 instruction descriptor (kind::f16): D = f32, A = B = bf16, both K-major, N = 64, M = 128
-constexpr unsigned TC_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(TC_N >> 3) << 17) | ((128u >> 4) << 24);
-
-__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(unsigned bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
-    unsigned done = 0;
-    const long long t0 = clock64();
-    for (unsigned it = 0; !done; ++it) {
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-            "selp.u32 %0, 1, 0, p;\n"
-            "}\n"
-            : "=r"(done)
-            : "r"(bar), "r"(parity)
-            : "memory");
-        if (!done && (it & 255u) == 255u && clock64() - t0 > 4000000000ll) __trap();  // ~2 s: never hang the device
-    }
-}
-__device__ __forceinline__ bool elect_one() {  // one lane of the (converged) warp
-    unsigned pred;
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "elect.sync _|p, 0xffffffff;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(pred));
-    return pred != 0;
-}
-__device__ __forceinline__ void tma_load_4d(unsigned dst, const CUtensorMap *map, int c0, int c1, int c2, int c3, unsigned bar) {
-    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
-                 ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
-                 : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(unsigned dst, const CUtensorMap *map, int c0, int c1, unsigned bar) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-                 ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar)
-                 : "memory");
-}
-__device__ __forceinline__ void tma_store_4d(const CUtensorMap *map, int c0, int c1, int c2, int c3, unsigned src) {
-    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3, %4}], [%5];"
-                 ::"l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(src)
-                 : "memory");
-}
-// shared-memory matrix descriptor: K-major, 128-byte swizzle, 8-row groups 1024 bytes apart (version 1 = sm_100)
-// `sbo` = bytes between consecutive 8-row groups; base_offset = the swizzle phase of a start address that is not 1 KB aligned
-__device__ __forceinline__ unsigned long long umma_desc(unsigned smem_addr, unsigned sbo, unsigned base_offset = 0u) {
-    return (unsigned long long)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((unsigned long long)(sbo >> 4) << 32) | (1ull << 46) |
-           ((unsigned long long)(base_offset & 7u) << 49) | (2ull << 61);
-}
-__device__ __forceinline__ void umma_bf16(unsigned d_tmem, unsigned long long a_desc, unsigned long long b_desc, unsigned accumulate) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-        "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(TC_IDESC), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit(unsigned bar) {  // arrives on `bar` when every MMA issued so far has completed
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(unsigned taddr, unsigned *v) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-                   "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-                 : "r"(taddr));
-}
-__device__ __forceinline__ unsigned bias_relu_pack(unsigned a, unsigned b, float ba, float bb) {
-    const float x = fmaxf(__uint_as_float(a) + ba, 0.0f), y = fmaxf(__uint_as_float(b) + bb, 0.0f);
-    const __nv_bfloat162 h = __floats2bfloat162_rn(x, y);
-    return *reinterpret_cast<const unsigned *>(&h);
-}
 
 // KMASK: bit 4 * tap + k set = the 16-channel weight slice k of tap (kh, kw) is multiplied (compile time: the issue loop is
 // fully unrolled with immediate descriptor offsets).  Bit 0 must be set.
@@ -363,25 +283,6 @@ hpb_stem_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_cons
     }
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
-                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn stem_encode_fn() {
-    static EncodeTiledFn fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
-        void *p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(p);
-        else
-            cudaGetLastError();
-    }
-    return fn;
-}
-
 // The s2d form of a 7x7 kernel: its 8x8 footprint has an empty last row and column, i.e. sub-pixel blocks with s = 1 (k odd) of
 // taps kw = 3 and blocks with r = 1 (k >= 2) of taps kh = 3 are all zero: 49 of the 64 slices remain.
 constexpr unsigned long long stem_mask_7x7() {
@@ -403,7 +304,7 @@ int launch_stem(hpb_ctx *ctx, const void *z, int b, int Hz, int Wz, int C, const
     } else if (Hc < Cfg::TILE_H || Wc < Cfg::TILE_W || Hc % Cfg::TILE_H || Wc % Cfg::TILE_W) {
         return HPB_ENOTFOUND;
     }
-    EncodeTiledFn encode = stem_encode_fn();
+    EncodeTiledFn encode = encode_tiled_fn();
     if (!encode) return HPB_ENOTFOUND;
     CUtensorMap map_in, map_w, map_out;
     const cuuint32_t estr4[4] = {1u, 1u, 1u, 1u};

@@ -54,6 +54,8 @@ class _Conv:
         self.weight = w.to(dtype).contiguous(memory_format=torch.channels_last)
         self.bias = b.to(dtype).contiguous()
         self.stride, self.padding, self.dilation, self.groups = conv.stride, conv.padding, conv.dilation, conv.groups
+        self.tc_ctx = None  # set by FoldedResNet for the convolutions libhpb200's tensor-core kernel serves
+        self.bias_f32 = b.float().contiguous()
 
     def plain(self, x):
         return F.conv2d(x, self.weight, self.bias, self.stride, self.padding, self.dilation, self.groups)
@@ -64,6 +66,15 @@ class _Conv:
         return F.relu_(self.plain(x))
 
     def add_relu(self, x, z, fused: bool):
+        if self.tc_ctx is not None and x.dtype == torch.bfloat16 and x.is_contiguous(memory_format=torch.channels_last) \
+                and z.is_contiguous(memory_format=torch.channels_last):
+            # layer1's relu(conv2 + b + identity) on libhpb200's tcgen05 kernel: cuDNN only has a generic implicit-GEMM tile for
+            # the conv+add+relu form of this shape (0.77 PFLOP/s; its plain conv+relu gets a weight-stationary kernel at 1.27)
+            from .. import ops
+
+            y = ops.conv3x3_bias_relu_bf16(self.tc_ctx, x, self.weight, self.bias_f32, z, self.weight_tc)
+            if y is not None:
+                return y
         if fused:
             return torch.cudnn_convolution_add_relu(x, self.weight, z, 1.0, self.bias, self.stride, self.padding, self.dilation, self.groups)
         return F.relu_(self.plain(x).add_(z))
@@ -118,6 +129,7 @@ class FoldedResNet:
             s2d.weight = s2d_weight(w, self.s2d_channels).to(dtype).contiguous(memory_format=torch.channels_last)
             s2d.bias = b.to(dtype).contiguous()
             s2d.stride, s2d.padding, s2d.dilation, s2d.groups = (1, 1), (0, 0), (1, 1), 1
+            s2d.tc_ctx = None
             self.stem_s2d = s2d
             # libhpb200's tcgen05 implicit GEMM serves the 64 -> 64 channel stem (hpb_stem_tc.cu): float32 folded bias, and the
             # mask of non-zero 16-channel weight slices (49 of 64 for a 7x7 kernel) so the empty ones are not multiplied
@@ -148,6 +160,17 @@ class FoldedResNet:
                     _, bd = fold_conv_bn(blk.downsample[0], blk.downsample[1])
                     c2.bias = (b2 + bd).to(dtype).contiguous()
                     down.bias = None
+                    c2.bias_f32 = (b2 + bd).float().contiguous()
+                # layer1 (64 -> 64, 3x3 / stride 1 / pad 1, no projection): the block's second convolution on the library's
+                # tensor-core kernel.  HPB200_TC_LAYER1=0 keeps cuDNN (A/B measurements).
+                cv = blk.conv2
+                if (ctx is not None and dtype == torch.bfloat16 and down is None and cv.in_channels == 64 and cv.out_channels == 64
+                        and cv.kernel_size == (3, 3) and cv.stride == (1, 1) and cv.padding == (1, 1) and cv.dilation == (1, 1)
+                        and cv.groups == 1 and os.environ.get("HPB200_TC_LAYER1", "1") != "0"):
+                    from .. import ops
+
+                    c2.tc_ctx = ctx
+                    c2.weight_tc = ops.conv3x3_residual_weight(c2.weight)
                 self.blocks.append((_Conv(blk.conv1, blk.bn1, dtype), c2, down))
         # the 512-d feature (average pool + fc) is computed in float32: it feeds the pose / logit heads directly
         self.fc_w = net.fc.weight.detach().float()

@@ -606,6 +606,43 @@ def stem_conv4x4_relu_bf16(ctx: Context, z: torch.Tensor, weight: torch.Tensor, 
     return out
 
 
+def conv3x3_residual_weight(weight: torch.Tensor) -> torch.Tensor:
+    """[64,64,3,3] weight -> the [64 out][10 taps][64 ch] bf16 operand of the residual form of hpb_conv3x3_bias_relu_bf16_nhwc:
+    the nine taps followed by a 64 x 64 identity, through which the tensor core adds the residual tile."""
+    O, C = weight.shape[:2]
+    taps = weight.detach().permute(0, 2, 3, 1).reshape(O, 9, C)
+    eye = torch.eye(O, C, dtype=taps.dtype, device=taps.device).reshape(O, 1, C)
+    return torch.cat([taps, eye], dim=1).to(torch.bfloat16).contiguous()
+
+
+def conv3x3_bias_relu_bf16(ctx: Context, x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor,
+                           residual: Optional[torch.Tensor] = None, residual_weight: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
+    """relu(conv2d(x, weight, padding=1) + bias [+ residual]) for 64 -> 64 channels on the tensor cores (hpb_conv3x3_tc.cu):
+    x, residual [b,64,H,W] bf16 channels_last, weight [64,64,3,3] bf16 channels_last, bias [64] float32 -> [b,64,H,W] bf16
+    channels_last.  Returns None when the library does not serve the shape (the caller keeps its cuDNN convolution).
+    `residual_weight`: conv3x3_residual_weight(weight), cached by the caller."""
+    assert x.dtype == torch.bfloat16 and x.dim() == 4 and x.is_contiguous(memory_format=torch.channels_last)
+    assert weight.dtype == torch.bfloat16 and weight.is_contiguous(memory_format=torch.channels_last) and tuple(weight.shape[2:]) == (3, 3)
+    assert bias.dtype == torch.float32 and bias.is_contiguous() and bias.numel() == weight.shape[0]
+    b, C, H, W = x.shape
+    O = weight.shape[0]
+    assert weight.shape[1] == C
+    if residual is not None:
+        assert residual.dtype == torch.bfloat16 and tuple(residual.shape) == (b, O, H, W) and residual.is_contiguous(memory_format=torch.channels_last)
+    if C != 64 or O != 64 or H < 18 or W < 16:
+        return None
+    out = torch.empty((b, O, H, W), dtype=torch.bfloat16, device=x.device, memory_format=torch.channels_last)
+    if residual is not None:  # the residual form multiplies a tenth, identity tap (built here unless the caller caches it)
+        weight = residual_weight if residual_weight is not None else conv3x3_residual_weight(weight)
+        assert weight.dtype == torch.bfloat16 and tuple(weight.shape) == (O, 10, C) and weight.is_contiguous()
+    rc = ctx.lib.hpb_conv3x3_bias_relu_bf16_nhwc(ctx.handle, ptr(x), b, H, W, C, ptr(weight), ptr(bias), O,
+                                                 ptr(residual) if residual is not None else None, ptr(out), stream_ptr(ctx.device))
+    if rc == -4:
+        return None
+    ctx.check(rc, "hpb_conv3x3_bias_relu_bf16_nhwc")
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 # ICP depth refiner, input stage
 # ------------------------------------------------------------------------------------------------

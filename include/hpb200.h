@@ -364,7 +364,20 @@ int hpb_set_maxpool_tma(hpb_ctx *ctx, int enable);
  */
 int hpb_stem_conv4x4_relu_bf16_nhwc(hpb_ctx *ctx, const void *z_dev, int b, int Hz, int Wz, int C, const void *w_dev,
                                     const float *bias_dev, int O, uint64_t k_slice_mask, void *out_dev, void *stream);
-/* Variants of the kernel above (A/B measurements and cross-checks; same results): 1 (default) = one TMA box per tile holding
+/*
+ * A BasicBlock convolution of ResNet layer1 (torchvision_resnet.py:59-83) after batch-norm folding: 3x3 / stride 1 / pad 1,
+ * 64 -> 64 channels, + bias, + residual_dev (the block's identity; NULL for the block's first convolution), ReLU, bfloat16
+ * NHWC in and out -- the same tcgen05 construction as the stem kernel (zero padding = TMA's out-of-bounds fill):
+ *   x_dev, residual_dev, out_dev [b,H,W,64] bf16; bias_dev [64] f32; w_dev [64 out][9 taps][64] bf16 (= the channels_last
+ *   [64,64,3,3] weight) without a residual, [64 out][10 taps][64] WITH one: the nine taps followed by a 64 x 64 identity, through
+ *   which the tensor core itself adds the residual tile (bf16 -> float32 and x * 1.0 are exact).
+ * out = relu(conv(x, w) + bias + residual), accumulated and summed in float32, rounded once.  Served: C = O = 64, H >= 18,
+ * W >= 16; anything else returns HPB_ENOTFOUND and the caller keeps its library convolution.  out_dev may alias residual_dev,
+ * not x_dev.
+ */
+int hpb_conv3x3_bias_relu_bf16_nhwc(hpb_ctx *ctx, const void *x_dev, int b, int H, int W, int C, const void *w_dev,
+                                    const float *bias_dev, int O, const void *residual_dev, void *out_dev, void *stream);
+/* Variants of hpb_stem_conv4x4_relu_bf16_nhwc (A/B measurements and cross-checks; same results): 1 (default) = one TMA box per tile holding
  * the tile and its halo, the 16 taps are start-address offsets into it, epilogue through a swizzled staging tile + TMA store;
  * 2 = the same with the epilogue storing straight from registers (8 % slower); 0 = one TMA box per tap (16x the L2 -> SM
  * traffic). */

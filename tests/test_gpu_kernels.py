@@ -799,3 +799,36 @@ def test_stem_tensor_core_conv_matches_float_conv(ctx, halo, shape):
     assert bool((err <= ref.abs() * 2.0 ** -8 + 1e-3).all()), float((err - ref.abs() * 2.0 ** -8).max())
     # and it is the correctly rounded value almost everywhere
     assert float((got == ref.to(torch.bfloat16).float()).float().mean()) > 0.99
+
+
+@pytest.mark.parametrize("residual", [False, True])
+@pytest.mark.parametrize("shape", [(2, 18, 16), (3, 37, 45), (4, 60, 80)])
+def test_conv3x3_tensor_core_matches_float_conv(ctx, shape, residual):
+    """hpb_conv3x3_bias_relu_bf16_nhwc (tcgen05 implicit GEMM, zero padding = TMA out-of-bounds fill) vs
+    relu(conv2d(pad 1) + bias [+ residual]) in float32 on the same bf16 operands.  37 x 45 exercises clipped edge tiles in both
+    directions; 60 x 80 is ResNet-34 layer1 at the 240 x 320 render size (several tiles per CTA)."""
+    from happypose_b200 import ops
+
+    b, H, W = shape
+    g = torch.Generator(device="cpu").manual_seed(31)
+    x = torch.randn(b, 64, H, W, generator=g).to(torch.bfloat16).cuda().contiguous(memory_format=torch.channels_last)
+    w = (torch.randn(64, 64, 3, 3, generator=g) * 0.05).to(torch.bfloat16).cuda().contiguous(memory_format=torch.channels_last)
+    bias = torch.randn(64, generator=g).cuda()
+    res = torch.randn(b, 64, H, W, generator=g).to(torch.bfloat16).cuda().contiguous(memory_format=torch.channels_last) if residual else None
+    out = ops.conv3x3_bias_relu_bf16(ctx, x, w, bias, res)
+    assert out is not None and out.shape == (b, 64, H, W) and out.is_contiguous(memory_format=torch.channels_last)
+    tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        ref = torch.nn.functional.conv2d(x.float(), w.float(), bias, padding=1)
+    finally:
+        torch.backends.cudnn.allow_tf32 = tf32
+    if residual:
+        ref = ref + res.float()
+    ref = torch.relu(ref)
+    got = out.float()
+    assert (ref > 0).float().mean() > 0.3
+    err = (got - ref).abs()
+    assert bool((err <= ref.abs() * 2.0 ** -8 + 1e-3).all()), float((err - ref.abs() * 2.0 ** -8).max())
+    assert float((got == ref.to(torch.bfloat16).float()).float().mean()) > 0.99
+    assert ops.conv3x3_bias_relu_bf16(ctx, x[:, :, :17].contiguous(memory_format=torch.channels_last), w, bias) is None  # H < 18: declined
