@@ -89,3 +89,21 @@ def test_stem_k_slice_mask_of_a_7x7_kernel():
     for tap in range(16):
         for k in range(4):
             assert bool((flat[:, tap, k] != 0).any()) == bool((mask >> (4 * tap + k)) & 1)
+
+
+def test_conv3x3_residual_weight_layout():
+    """ops.conv3x3_residual_weight: [O][10 taps][C] = the nine taps of the [O,C,3,3] weight in (kh, kw) order, then a 64 x 64
+    identity (tap 9) through which hpb_conv3x3_tc_kernel<RES> adds the residual tile on the tensor core."""
+    from happypose_b200 import ops
+
+    g = torch.Generator().manual_seed(5)
+    w = torch.randn(64, 64, 3, 3, generator=g).to(torch.bfloat16)
+    we = ops.conv3x3_residual_weight(w.contiguous(memory_format=torch.channels_last))
+    assert we.shape == (64, 10, 64) and we.dtype == torch.bfloat16 and we.is_contiguous()
+    for kh in range(3):
+        for kw in range(3):
+            assert torch.equal(we[:, 3 * kh + kw, :], w[:, :, kh, kw])
+    assert torch.equal(we[:, 9, :].float(), torch.eye(64))
+    # the same bytes the plain kernel reads for taps 0..8: the channels_last weight is [O][kh][kw][C] in memory
+    flat = w.contiguous(memory_format=torch.channels_last).permute(0, 2, 3, 1).reshape(64, 9, 64)
+    assert torch.equal(we[:, :9], flat)
