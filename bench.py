@@ -85,6 +85,11 @@ def config_dict(args, world):
         "render_size": [H_R, W_R], "frame": [H_IM, W_IM], "bsz_images": 576, "bsz_objects": 16,
         "parallelism": f"hypothesis-sharded x{world}" + (" (strong: the detections' rows are split across the ranks)" if getattr(args, "scaling", "weak") == "strong" else ""),
         "l2": "no explicit flush: every step writes/reads 1.6 GB of network input per pose (> 126 MB L2)",
+        "batching": "bsz_images=576, bsz_objects=16 (both reference defaults of run_inference_pipeline callers; SURVEY C1 quotes 128 / 8)",
+        "frames": "`value`: the pipeline's result frames stay deferred (no pandas DataFrame is built inside the timed region); "
+                  "`e2e`: the final frame is materialised every step (pose_score to numpy + poses to host); the 576-row coarse "
+                  "frame the reference always builds is deferred in both",
+        "host": "gc.collect() + gc.freeze() after the warm-up (a serving process's setting; profiles/r2_e2e_gc_pause.txt)",
     }
 
 
