@@ -1,5 +1,7 @@
 """Decode which input element the tcgen05 stem kernel actually reads for every (tap, output pixel, channel): identity weights on
-ONE tap make out[o, y, x] = z[o, y + kh, x + kw]; z encodes its own x, y or channel index (exact in bf16)."""
+ONE tap make out[o, y, x] = z[o, y + kh, x + kw]; z encodes its own x, y or channel index (exact in bf16).
+This is how the un-swizzle rule of a descriptor whose start address is not 1 KB aligned was found (hpb_stem_tc.cu header):
+usage: python scripts/debug_stem_tc.py [variant 0|1|2]   (run on the GPU box)"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -10,11 +12,7 @@ dev = torch.device("cuda:0")
 ctx = Context.get(dev)
 halo = int(sys.argv[1]) if len(sys.argv) > 1 else 1
 ctx.lib.hpb_set_stem_tc_halo(ctx.handle, halo)
-b, Hz, Wz = 1, 19, 19 if halo else 19
-Wz = 19
-Hz = 19
-if not halo:
-    Wz = 19
+Hz, Wz = 19, 19  # one image, 16 x 16 outputs: two tiles of the halo scheme, two of the box-per-tap scheme
 yy, xx, cc = torch.meshgrid(torch.arange(Hz), torch.arange(Wz), torch.arange(64), indexing="ij")  # [Hz, Wz, 64]
 enc = {"x": xx, "y": yy, "c": cc}
 bias = torch.zeros(64, device=dev)
