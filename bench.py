@@ -299,7 +299,7 @@ class CpuPipeline:
     """Bounded sample of the pose workload on the CPU: n_coarse coarse hypotheses (crop + raster + ResNet-34 9ch) and one
     refiner iteration of one hypothesis (crop + 4 rasters + ResNet-34 27ch); pose time = 577/n_coarse * t_c + 5 * t_r."""
 
-    def __init__(self, n_coarse=8):
+    def __init__(self, n_coarse=8, cores=None):
         from oracle import np_oracle as O
         from oracle import pipeline_oracle as P
         from happypose_b200.megapose.backbones import make_backbone
@@ -310,7 +310,7 @@ class CpuPipeline:
         self.roi_kind = "torchvision.ops.roi_align (CPU)" if tv is not None else "numpy restatement"
         if tv is not None:
             O.roi_align = tv
-        self.cores = len(os.sched_getaffinity(0))
+        self.cores = int(cores) if cores else len(os.sched_getaffinity(0))
         torch.set_num_threads(self.cores)
         d = np.load(MESH)
         self.scene = P.make_scene([{k: d[k] for k in d.files}], [0.001])
@@ -347,6 +347,24 @@ class CpuPipeline:
         t2 = time.perf_counter()
         return (t1 - t0) / n * (M_GRID + 1) + (t2 - t1) * N_REFINER_ITERS
 
+    def single_thread(self):
+        """SURVEY 8(d) also asks for the reference's own setting, OMP_NUM_THREADS = 1 (megapose/__init__.py:20-39): the same
+        sample on ONE thread (a smaller one: 2 coarse hypotheses + 1 refiner iteration), all-cores setting restored after."""
+        keep = self.cores, self.n_coarse
+        try:
+            self.cores, self.n_coarse = 1, 2
+            torch.set_num_threads(1)
+            saved = self.K_rows, self.zeros, self.TCO0
+            self.K_rows, self.zeros, self.TCO0 = self.K_rows[:2], self.zeros[:2], self.TCO0[:2]
+            self.sample()
+            t = self.sample()
+            self.K_rows, self.zeros, self.TCO0 = saved
+        finally:
+            self.cores, self.n_coarse = keep
+            torch.set_num_threads(self.cores)
+        return {"value": 1.0 / t, "unit": UNIT, "cores": 1,
+                "sample": "2 of 577 coarse/scoring hypotheses + 1 of 5 refiner iterations, one thread (the reference package's own OMP_NUM_THREADS=1)"}
+
     def describe(self):
         return (f"{self.n_coarse} of 577 coarse/scoring hypotheses + 1 of 5 refiner iterations (1 hypothesis x 4 views) per sample, "
                 f"extrapolated linearly to one pose; C rasteriser port (oracle/raster_oracle.c) + {self.roi_kind} + torch-CPU fp32 ResNet-34")
@@ -366,7 +384,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": t_pose * args.dets * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "config": config_dict(args, args.gpus),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": pipe.cores, "kind": "port", "sample": pipe.describe()},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": pipe.cores, "kind": "port", "sample": pipe.describe(),
+                         "single_thread": pipe.single_thread()},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
         "note": "Panda3D/OpenGL cannot be installed offline, so the reference arm is the CPU oracle port of the same path "
@@ -619,7 +638,8 @@ def run_ours(args):
         pipe = CpuPipeline(n_coarse=8)
         pipe.sample()
         t_pose = min(pipe.sample() for _ in range(2))
-        line["cpu_baseline"] = {"value": 1.0 / t_pose, "unit": UNIT, "cores": pipe.cores, "kind": "port", "sample": pipe.describe()}
+        line["cpu_baseline"] = {"value": 1.0 / t_pose, "unit": UNIT, "cores": pipe.cores, "kind": "port", "sample": pipe.describe(),
+                                "single_thread": pipe.single_thread()}
     emit(line)
 
 
